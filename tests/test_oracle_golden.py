@@ -12,9 +12,11 @@ RTOL = 1e-9
 
 
 def close(a, b, rtol=RTOL, atol=0.0, what=""):
+    """rtol elementwise, plus an absolute floor of rtol*1e-3 of the array's largest magnitude (tiny elements of a
+    factor matrix cannot be resolved better than the rounding of the big ones they are coupled to)."""
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
-    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol + 1e-12 * scale, err_msg=what)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol + rtol * 1e-3 * scale, err_msg=what)
 
 
 def priors2(g):
