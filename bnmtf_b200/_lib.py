@@ -1,0 +1,73 @@
+"""ctypes binding of libbnmtf_b200.so (include/bnmtf_b200.h).  There is no CPU fallback: if the shared
+library is missing or a call fails, an exception is raised."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbnmtf_b200.so")
+
+c_i, c_i64, c_u64, c_d, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
+
+# name -> argument types (all return int unless listed in _RESTYPES)
+SIGNATURES = {
+    "bnmtf_version": [],
+    "bnmtf_last_error": [],
+    "bnmtf_ld_for": [c_i64],
+    "bnmtf_kp_for": [c_i],
+    "bnmtf_gram_len": [c_i],
+    "bnmtf_pack_dataset_f64": [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p],
+    "bnmtf_pack_mask_f64": [c_p, c_i64, c_i64, c_i64, c_p, c_p],
+    "bnmtf_transpose_dataset_f64": [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_p],
+    "bnmtf_pad_factor_f64": [c_p, c_p, c_i64, c_i, c_i64, c_p, c_p, c_p],
+    "bnmtf_stats_rx_f64": [c_p, c_p, c_i64, c_i64, c_p, c_i, c_i, c_p, c_p],
+    "bnmtf_stats_gram_f64": [c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "bnmtf_gram_full_f64": [c_p, c_p, c_i64, c_i, c_i64, c_p, c_p, c_p],
+    "bnmf_row_solve_f64": [c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                           c_i, c_i, c_d, c_u64, c_p, c_u64, c_p, c_p, c_p],
+    "bnmtf_masked_metrics_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "bnmtf_dense_metrics_f64": [c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_p],
+    "bnmtf_vb_factor_terms_f64": [c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p],
+    "bnmtf_reduce8_f64": [c_p, c_i, c_p, c_p],
+    "bnmtf_reduce1_f64": [c_p, c_i64, c_p, c_p],
+    "bnmf_finish_sweep_f64": [c_i, c_d, c_d, c_d, c_d, c_d, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_u64, c_i, c_p],
+    "bnmtf_tn_moments_f64": [c_p, c_p, c_i64, c_p, c_p, c_p],
+    "bnmtf_tn_draw_f64": [c_p, c_p, c_i64, c_u64, c_u64, c_p, c_p],
+    "bnmtf_gamma_draw_f64": [c_d, c_d, c_i64, c_u64, c_u64, c_p, c_p],
+    "bnmtf_exponential_draw_f64": [c_p, c_i64, c_u64, c_u64, c_p, c_p],
+}
+_RESTYPES = {"bnmtf_last_error": ctypes.c_char_p, "bnmtf_ld_for": c_i64, "bnmtf_gram_len": c_i64}
+_PLAIN = {"bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "bnmtf_gram_len"}
+
+_lib = None
+
+
+class BnmtfError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype of include/bnmtf_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BnmtfError("libbnmtf_b200.so not built (run `python -m bnmtf_b200.build` or __graft_entry__.build()); "
+                         "there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, c_i)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name in _PLAIN:
+        return rc
+    if rc != 0:
+        raise BnmtfError("%s failed (%d): %s" % (name, rc, lib.bnmtf_last_error().decode()))
+    return 0

@@ -1,0 +1,449 @@
+"""Drop-in classes for the reference's two-factor models, backed by the B200 engine.
+
+    bnmf_gibbs_optimised  (code/models/bnmf_gibbs_optimised.py:53)
+    bnmf_vb_optimised     (code/models/bnmf_vb_optimised.py:52)
+    nmf_icm               (code/models/nmf_icm.py:46)
+
+Same constructor arguments, method names, return values, attribute names and assertion messages as the
+reference.  State attributes (U, V, tau, expU, muU, ...) are host numpy arrays, assignable as in the reference's
+white-box tests; every method uploads them, runs CUDA kernels through the C ABI and downloads the result.
+run(iterations) keeps the whole loop on the device (no host round trip per column or per iteration).
+"""
+import itertools
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import (BNMFEngine, Dataset, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_MSE, S_R2, S_RP, S_SUM_E2, S_TAU,
+                     _ptr, _stream, require_cuda)
+
+METRICS = ['MSE', 'R^2', 'Rp']
+QUALITY = ['loglikelihood', 'BIC', 'AIC', 'MSE', 'ELBO']
+
+
+def _metrics_from_sums(s):
+    """{MSE,R^2,Rp} from the seven masked sums (e2, p, p2, rp, r, r2, n), reference :208-223."""
+    e2, p, p2, rp, r, r2, n = (float(x) for x in s[:7])
+    mean_r, mean_p = r / n, p / n
+    ss_tot = r2 - r * mean_r
+    with np.errstate(all='ignore'):
+        R2 = 1. - e2 / ss_tot if ss_tot != 0. else np.inf
+        Rp = np.float64(rp - r * mean_p) / (math.sqrt(max(ss_tot, 0.)) * math.sqrt(max(p2 - p * mean_p, 0.)))
+    return {'MSE': e2 / n, 'R^2': R2, 'Rp': Rp}
+
+
+class _TwoFactorBase(object):
+    _mode = None
+
+    def __init__(self, R, M, K, priors, device=None, seed=None):
+        self.R = np.array(R, dtype=float)
+        self.M = np.array(M, dtype=float)
+        self.K = K
+
+        assert len(self.R.shape) == 2, "Input matrix R is not a two-dimensional array, " \
+            "but instead %s-dimensional." % len(self.R.shape)
+        assert self.R.shape == self.M.shape, "Input matrix R is not of the same size as " \
+            "the indicator matrix M: %s and %s respectively." % (self.R.shape, self.M.shape)
+
+        (self.I, self.J) = self.R.shape
+        self.size_Omega = self.M.sum()
+        self.check_empty_rows_columns()
+
+        self.alpha, self.beta, self.lambdaU, self.lambdaV = \
+            float(priors['alpha']), float(priors['beta']), np.array(priors['lambdaU']), np.array(priors['lambdaV'])
+        if self.lambdaU.shape == ():
+            self.lambdaU = self.lambdaU * np.ones((self.I, self.K))
+        if self.lambdaV.shape == ():
+            self.lambdaV = self.lambdaV * np.ones((self.J, self.K))
+
+        assert self.lambdaU.shape == (self.I, self.K), "Prior matrix lambdaU has the wrong shape: %s instead of (%s, %s)." % (self.lambdaU.shape, self.I, self.K)
+        assert self.lambdaV.shape == (self.J, self.K), "Prior matrix lambdaV has the wrong shape: %s instead of (%s, %s)." % (self.lambdaV.shape, self.J, self.K)
+
+        self._device_arg, self._seed, self._eng = device, seed, None
+        self.verbose = False
+
+    def check_empty_rows_columns(self):
+        sums_columns = self.M.sum(axis=0)
+        sums_rows = self.M.sum(axis=1)
+        for i, c in enumerate(sums_rows):
+            assert c != 0, "Fully unobserved row in R, row %s." % i
+        for j, c in enumerate(sums_columns):
+            assert c != 0, "Fully unobserved column in R, column %s." % j
+
+    # ---- device plumbing --------------------------------------------------------------------------------
+    def _engine(self):
+        if self._eng is None:
+            dev = require_cuda(self._device_arg)
+            ds = Dataset.from_host(self.R, self.M, dev)
+            seed = self._seed if self._seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+            self._eng = BNMFEngine(ds, self.K, self._mode, self.alpha, self.beta, seed=seed)
+        return self._eng
+
+    @staticmethod
+    def _up(dst, src):
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64)), non_blocking=False)
+
+    @staticmethod
+    def _down(src):
+        return src.detach().cpu().numpy().copy()
+
+    def _set_scalars(self, eng, kv):
+        s = eng.scalars.cpu().numpy()
+        for k, v in kv.items():
+            s[k] = v
+        eng.scalars.copy_(torch.from_numpy(s))
+
+    def _sums_for(self, M_pred, U, V):
+        """Seven masked sums of the prediction U V^T over M_pred, on the device."""
+        eng = self._engine()
+        self._up(eng.U.fac, U)
+        self._up(eng.V.fac, V)
+        bits = eng.ds.bits if M_pred is None else eng.ds.pack_mask(M_pred)
+        eng.metrics(bits)
+        return eng.m8.cpu().numpy()
+
+    # ---- metric helpers on explicit matrices (reference :208-223) ----------------------------------------------
+    def _dense_sums(self, M, R, R_pred):
+        dev = require_cuda(self._device_arg)
+        t = [torch.from_numpy(np.ascontiguousarray(np.broadcast_to(x, np.shape(R)), dtype=np.float64)).to(dev) for x in (R, R_pred, M)]
+        nb = 64
+        part = torch.zeros(nb * 8, dtype=torch.float64, device=dev)
+        out = torch.zeros(8, dtype=torch.float64, device=dev)
+        _lib.call("bnmtf_dense_metrics_f64", _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), t[0].numel(), _ptr(part), nb, _ptr(out), _stream())
+        return out.cpu().numpy()
+
+    def compute_MSE(self, M, R, R_pred):
+        return _metrics_from_sums(self._dense_sums(M, R, R_pred))['MSE']
+
+    def compute_R2(self, M, R, R_pred):
+        return _metrics_from_sums(self._dense_sums(M, R, R_pred))['R^2']
+
+    def compute_Rp(self, M, R, R_pred):
+        return _metrics_from_sums(self._dense_sums(M, R, R_pred))['Rp']
+
+    def _n_params(self):
+        return self.I * self.K + self.J * self.K
+
+    def _quality_from_ll(self, metric, log_likelihood):
+        if metric == 'loglikelihood':
+            return log_likelihood
+        elif metric == 'BIC':
+            return - 2 * log_likelihood + self._n_params() * math.log(self.size_Omega)
+        elif metric == 'AIC':
+            return - 2 * log_likelihood + 2 * self._n_params()
+
+    def _init_trace_lists(self):
+        self.all_times = []
+        self.all_performances = {}
+        for metric in METRICS:
+            self.all_performances[metric] = []
+
+    def _run_loop(self, eng, iterations, minimum_TN=0.0, per_iteration=None):
+        """Enqueue `iterations` sweeps; CUDA events give the reference's cumulative all_times."""
+        eng.alloc_trace(iterations)
+        start = torch.cuda.Event(enable_timing=True)
+        marks = []
+        start.record()
+        for it in range(iterations):
+            eng.sweep(minimum_TN)
+            if per_iteration is not None:
+                per_iteration(it)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
+        torch.cuda.synchronize()
+        self.all_times = [start.elapsed_time(ev) / 1e3 for ev in marks]
+        tr = eng.trace.cpu().numpy()[:iterations]
+        for i, metric in enumerate(METRICS):
+            self.all_performances[metric] = [float(v) for v in tr[:, 1 + i]]
+        return tr
+
+
+# =====================================================================================================
+class bnmf_gibbs_optimised(_TwoFactorBase):
+    """Gibbs sampler for BNMF (reference code/models/bnmf_gibbs_optimised.py)."""
+    _mode = 'gibbs'
+
+    def train(self, init, iterations):
+        self.initialise(init=init)
+        return self.run(iterations)
+
+    def initialise(self, init='random'):
+        assert init in ['random', 'exp'], "Unknown initialisation option: %s. Should be 'random' or 'exp'." % init
+        if init == 'random':
+            # same numpy stream order as the reference's (i,k) then (j,k) loops (:106-109)
+            self.U = np.random.exponential(scale=1.0 / self.lambdaU)
+            self.V = np.random.exponential(scale=1.0 / self.lambdaV)
+        else:
+            self.U, self.V = 1.0 / self.lambdaU, 1.0 / self.lambdaV
+        self.tau = self.alpha_s() / self.beta_s()
+
+    def _push(self):
+        eng = self._engine()
+        self._up(eng.U.fac, self.U), self._up(eng.V.fac, self.V)
+        self._up(eng.U.lam, self.lambdaU), self._up(eng.V.lam, self.lambdaV)
+        self._set_scalars(eng, {S_TAU: float(getattr(self, 'tau', 1.0))})
+        return eng
+
+    def run(self, iterations):
+        eng = self._push()
+        dev = eng.ds.device
+        all_U = torch.zeros((iterations, self.I, self.K), dtype=torch.float64, device=dev)
+        all_V = torch.zeros((iterations, self.J, self.K), dtype=torch.float64, device=dev)
+        self._init_trace_lists()
+
+        def keep(it):
+            all_U[it].copy_(eng.U.fac), all_V[it].copy_(eng.V.fac)
+        tr = self._run_loop(eng, iterations, per_iteration=keep)
+        self.all_U, self.all_V = self._down(all_U), self._down(all_V)
+        self.all_tau = tr[:, 0].copy()
+        self.U, self.V = self._down(eng.U.fac), self._down(eng.V.fac)
+        if iterations > 0:
+            self.tau = float(tr[-1, 0])
+        if self.verbose:
+            for it in range(iterations):
+                print("Iteration %s. MSE: %s. R^2: %s. Rp: %s." % (it + 1, tr[it, 1], tr[it, 2], tr[it, 3]))
+        return (self.all_U, self.all_V, self.all_tau)
+
+    # ---- conditional parameters (reference :161-177) -----------------------------------------------------
+    def alpha_s(self):
+        return self.alpha + self.size_Omega / 2.0
+
+    def beta_s(self):
+        return self.beta + 0.5 * float(self._sums_for(None, self.U, self.V)[0])
+
+    def _params(self, side, k):
+        eng = self._push()
+        eng.stats(side)
+        eng.solve(side, order=[k], apply=False, want_sterm=True, use_iter=False)
+        me = eng.U if side == 0 else eng.V
+        return self._down(me.tauf)[:, k], self._down(eng.sterm[:me.n])[:, k]
+
+    def tauU(self, k):
+        return self._params(0, k)[0]
+
+    def muU(self, tauUk, k):
+        s = self._params(0, k)[1]
+        with np.errstate(all='ignore'):
+            return 1. / np.asarray(tauUk) * (-self.lambdaU[:, k] + self.tau * s)
+
+    def tauV(self, k):
+        return self._params(1, k)[0]
+
+    def muV(self, tauVk, k):
+        s = self._params(1, k)[1]
+        with np.errstate(all='ignore'):
+            return 1. / np.asarray(tauVk) * (-self.lambdaV[:, k] + self.tau * s)
+
+    # ---- posterior summaries (reference :182-251) -------------------------------------------------------------
+    def approx_expectation(self, burn_in, thinning):
+        indices = range(burn_in, len(self.all_U), thinning)
+        n = float(len(indices))
+        exp_U = np.array([self.all_U[i] for i in indices]).sum(axis=0) / n
+        exp_V = np.array([self.all_V[i] for i in indices]).sum(axis=0) / n
+        exp_tau = sum([self.all_tau[i] for i in indices]) / n
+        return (exp_U, exp_V, exp_tau)
+
+    def predict(self, M_pred, burn_in, thinning):
+        (exp_U, exp_V, _) = self.approx_expectation(burn_in, thinning)
+        return _metrics_from_sums(self._sums_for(M_pred, exp_U, exp_V))
+
+    def predict_while_running(self):
+        return _metrics_from_sums(self._sums_for(None, self.U, self.V))
+
+    def quality(self, metric, burn_in, thinning):
+        assert metric in QUALITY, 'Unrecognised metric for model quality: %s.' % metric
+        (expU, expV, exptau) = self.approx_expectation(burn_in, thinning)
+        if metric == 'MSE':
+            return _metrics_from_sums(self._sums_for(None, expU, expV))['MSE']
+        elif metric == 'ELBO':
+            return 0.
+        return self._quality_from_ll(metric, self.log_likelihood(expU, expV, exptau))
+
+    def log_likelihood(self, expU, expV, exptau):
+        explogtau = math.log(exptau)
+        return self.size_Omega / 2. * (explogtau - math.log(2 * math.pi)) \
+            - exptau / 2. * float(self._sums_for(None, expU, expV)[0])
+
+
+# =====================================================================================================
+class nmf_icm(_TwoFactorBase):
+    """Iterated conditional modes (MAP) for NMF (reference code/models/nmf_icm.py)."""
+    _mode = 'icm'
+
+    def train(self, init, iterations):
+        self.initialise(init=init)
+        return self.run(iterations)
+
+    def initialise(self, init='random'):
+        assert init in ['random', 'exp'], "Unknown initialisation option: %s. Should be 'random' or 'exp'." % init
+        if init == 'random':
+            self.U = np.random.exponential(scale=1.0 / self.lambdaU)
+            self.V = np.random.exponential(scale=1.0 / self.lambdaV)
+        else:
+            self.U, self.V = 1.0 / self.lambdaU, 1.0 / self.lambdaV
+        self.tau = (self.alpha_s() - 1.) / self.beta_s()
+
+    _push = bnmf_gibbs_optimised._push
+    alpha_s = bnmf_gibbs_optimised.alpha_s
+    beta_s = bnmf_gibbs_optimised.beta_s
+    _params = bnmf_gibbs_optimised._params
+    tauU, muU, tauV, muV = (bnmf_gibbs_optimised.tauU, bnmf_gibbs_optimised.muU,
+                            bnmf_gibbs_optimised.tauV, bnmf_gibbs_optimised.muV)
+
+    def run(self, iterations, minimum_TN=0.):
+        eng = self._push()
+        self._init_trace_lists()
+        tr = self._run_loop(eng, iterations, minimum_TN=minimum_TN)
+        self.all_tau = tr[:, 0].copy()
+        self.U, self.V = self._down(eng.U.fac), self._down(eng.V.fac)
+        if iterations > 0:
+            self.tau = float(tr[-1, 0])
+        return
+
+    def predict(self, M_pred):
+        return _metrics_from_sums(self._sums_for(M_pred, self.U, self.V))
+
+    def quality(self, metric):
+        assert metric in QUALITY, 'Unrecognised metric for model quality: %s.' % metric
+        if metric == 'MSE':
+            return _metrics_from_sums(self._sums_for(None, self.U, self.V))['MSE']
+        elif metric == 'ELBO':
+            return 0.
+        return self._quality_from_ll(metric, self.log_likelihood())
+
+    def log_likelihood(self):
+        return self.size_Omega / 2. * (math.log(self.tau) - math.log(2 * math.pi)) \
+            - self.tau / 2. * float(self._sums_for(None, self.U, self.V)[0])
+
+
+# =====================================================================================================
+class bnmf_vb_optimised(_TwoFactorBase):
+    """Variational Bayes for BNMF (reference code/models/bnmf_vb_optimised.py)."""
+    _mode = 'vb'
+    _STATE = ('expU', 'varU', 'muU', 'tauU', 'expV', 'varV', 'muV', 'tauV')
+
+    def initialise(self, init='exp', tauUV={}):
+        self.tauU = tauUV['tauU'] if 'tauU' in tauUV else np.ones((self.I, self.K))
+        self.tauV = tauUV['tauV'] if 'tauV' in tauUV else np.ones((self.J, self.K))
+        assert init in ['exp', 'random'], "Unrecognised init option for F,G: %s." % init
+        self.muU, self.muV = 1. / self.lambdaU, 1. / self.lambdaV
+        if init == 'random':
+            self.muU = np.random.exponential(scale=1.0 / self.lambdaU)
+            self.muV = np.random.exponential(scale=1.0 / self.lambdaV)
+        self.expU, self.varU = np.zeros((self.I, self.K)), np.zeros((self.I, self.K))
+        self.expV, self.varV = np.zeros((self.J, self.K)), np.zeros((self.J, self.K))
+        for k in range(0, self.K):
+            self.update_exp_U(k)
+        for k in range(0, self.K):
+            self.update_exp_V(k)
+        self.update_tau()
+        self.update_exp_tau()
+
+    def train(self, iterations, init_UV='random'):
+        self.initialise(init=init_UV)      # the reference passes init_UV= to a signature without it (:157-159)
+        self.run(iterations=iterations)
+
+    def _push(self):
+        eng = self._engine()
+        for f, s in ((eng.U, 'U'), (eng.V, 'V')):
+            self._up(f.fac, getattr(self, 'exp' + s)), self._up(f.var, getattr(self, 'var' + s))
+            self._up(f.mu, getattr(self, 'mu' + s)), self._up(f.tauf, getattr(self, 'tau' + s))
+            self._up(f.lam, getattr(self, 'lambda' + s))
+        self._set_scalars(eng, {S_TAU: float(getattr(self, 'exptau', 1.0)), S_LOGTAU: float(getattr(self, 'explogtau', 0.0)),
+                                  S_BETA_S: float(getattr(self, 'beta_s', 1.0))})
+        return eng
+
+    def _pull(self, eng, names=None):
+        for f, s in ((eng.U, 'U'), (eng.V, 'V')):
+            for attr, t in (('exp', f.fac), ('var', f.var), ('mu', f.mu), ('tau', f.tauf)):
+                if names is None or attr + s in names:
+                    setattr(self, attr + s, self._down(t))
+
+    def run(self, iterations):
+        eng = self._push()
+        self._init_trace_lists()
+        tr = self._run_loop(eng, iterations)
+        self.all_exp_tau = [float(v) for v in tr[:, 0]]
+        self.all_elbo = [float(v) for v in tr[:, 4]]
+        self._pull(eng)
+        if iterations > 0:
+            sc = eng.scalars.cpu().numpy()
+            self.exptau, self.explogtau = float(sc[S_TAU]), float(sc[S_LOGTAU])
+            self.alpha_s, self.beta_s = self.alpha + self.size_Omega / 2.0, float(sc[S_BETA_S])
+        if self.verbose:
+            for it in range(iterations):
+                print("Iteration %s. ELBO: %s. MSE: %s. R^2: %s. Rp: %s." % (it + 1, tr[it, 4], tr[it, 1], tr[it, 2], tr[it, 3]))
+        return
+
+    # ---- white-box pieces (reference :163-215) ---------------------------------------------------------------
+    def _refreshed_scalars(self, update_tau):
+        eng = self._push()
+        eng.refresh_scalars(update_tau=update_tau)
+        return eng.scalars.cpu().numpy()
+
+    def elbo(self):
+        return float(self._refreshed_scalars(False)[S_ELBO])
+
+    def exp_square_diff(self):
+        return float(self._refreshed_scalars(False)[S_ESD])
+
+    def update_tau(self):
+        self.alpha_s = self.alpha + self.size_Omega / 2.0
+        self.beta_s = self.beta + 0.5 * self.exp_square_diff()
+
+    def update_exp_tau(self):
+        from scipy.special import psi
+        self.exptau = float(self.alpha_s) / float(self.beta_s)
+        self.explogtau = float(psi(float(self.alpha_s))) - math.log(float(self.beta_s))
+
+    def _update_params(self, side, k):
+        eng = self._push()
+        eng.stats(side)
+        eng.solve(side, order=[k], apply=False, use_iter=False)
+        s = 'U' if side == 0 else 'V'
+        f = eng.U if side == 0 else eng.V
+        getattr(self, 'tau' + s)[:, k] = self._down(f.tauf)[:, k]
+        getattr(self, 'mu' + s)[:, k] = self._down(f.mu)[:, k]
+
+    def update_U(self, k):
+        self._update_params(0, k)
+
+    def update_V(self, k):
+        self._update_params(1, k)
+
+    def _update_exp(self, s, k):
+        from .distributions import TN_vector_expectation, TN_vector_variance
+        mu, tau = getattr(self, 'mu' + s)[:, k], getattr(self, 'tau' + s)[:, k]
+        getattr(self, 'exp' + s)[:, k] = TN_vector_expectation(mu, tau)
+        getattr(self, 'var' + s)[:, k] = TN_vector_variance(mu, tau)
+
+    def update_exp_U(self, k):
+        self._update_exp('U', k)
+
+    def update_exp_V(self, k):
+        self._update_exp('V', k)
+
+    def predict(self, M_pred):
+        return _metrics_from_sums(self._sums_for(M_pred, self.expU, self.expV))
+
+    def quality(self, metric):
+        metric = 'ELBO' if metric == 'elbo' else metric      # BASELINE.json spells it lower case
+        assert metric in QUALITY, 'Unrecognised metric for model quality: %s.' % metric
+        if metric == 'MSE':
+            return _metrics_from_sums(self._sums_for(None, self.expU, self.expV))['MSE']
+        elif metric == 'ELBO':
+            return self.elbo()
+        return self._quality_from_ll(metric, self.log_likelihood())
+
+    def log_likelihood(self):
+        return self.size_Omega / 2. * (self.explogtau - math.log(2 * math.pi)) \
+            - self.exptau / 2. * float(self._sums_for(None, self.expU, self.expV)[0])
+
+
+# BASELINE.json's names for the same classes
+BNMF_Gibbs = bnmf_gibbs_optimised
+BNMF_VB = bnmf_vb_optimised

@@ -1,0 +1,229 @@
+// extern "C" surface of libbnmtf_b200 (declared in include/bnmtf_b200.h) + layout kernels.
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+#include "../../include/bnmtf_b200.h"
+
+namespace bnmtf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
+// ---- forward declarations of the launchers in the other translation units -----------------------------
+int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int, int, double*, cudaStream_t);
+int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
+int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
+int launch_pad_factor(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
+int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, double*, double*, cudaStream_t);
+int launch_vb_factor_terms(const double*, const double*, const double*, const double*, const double*, long long, double*, int, cudaStream_t);
+int launch_reduce8(const double*, int, double*, cudaStream_t);
+int launch_dense_metrics(const double*, const double*, const double*, long long, double*, int, double*, cudaStream_t);
+int launch_reduce1(const double*, long long, double*, cudaStream_t);
+int launch_tn_moments(const double*, const double*, long long, double*, double*, cudaStream_t);
+int launch_tn_draw(const double*, const double*, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
+int launch_gamma_draw(double, double, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
+int launch_exponential_draw(const double*, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
+
+int launch_row_solve(const RowSolveArgs&, cudaStream_t);
+
+int launch_finish(const FinishArgs&, cudaStream_t);
+
+// ---- layout kernels -------------------------------------------------------------------------------------
+// one warp per (row, 32-column word): copy R into the padded layout and ballot the mask into a word
+__global__ void k_pack_dataset(const double* __restrict__ Rin, const double* __restrict__ Min, long long rows,
+                               long long cols, long long ld, double* __restrict__ Rout, uint32_t* __restrict__ bits) {
+  const long long wpr = ld >> 5;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= rows * wpr) return;
+  const long long row = gw / wpr, w = gw - row * wpr;
+  const long long j = w * 32 + lane;
+  double r = 0.0;
+  bool m = false;
+  if (j < cols) {
+    m = Min[row * cols + j] != 0.0;
+    if (Rin) r = Rin[row * cols + j];
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, m);
+  if (Rout) Rout[row * ld + j] = r;
+  if (lane == 0) bits[row * wpr + w] = word;
+}
+
+// 32x32 tile transpose of the fp64 matrix (through shared memory) and of the bit mask (through ballots)
+__global__ void __launch_bounds__(1024) k_transpose_dataset(const double* __restrict__ R, const uint32_t* __restrict__ bits,
+                                                          long long rows, long long cols, long long ld,
+                                                          double* __restrict__ RT, uint32_t* __restrict__ bitsT,
+                                                          long long ldT) {
+  __shared__ double tile[32][33];
+  __shared__ uint32_t words[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;  // source tile origin
+  const long long wpr = ld >> 5, wprT = ldT >> 5;
+  {
+    const long long r = r0 + ty, c = c0 + tx;
+    tile[ty][tx] = (r < rows && c < ld) ? R[r * ld + c] : 0.0;
+    if (tx == 0) words[ty] = (r < rows && c0 < ld) ? bits[r * wpr + (c0 >> 5)] : 0u;
+  }
+  __syncthreads();
+  {
+    // destination row = source column c0 + ty, destination column = source row r0 + tx
+    const long long dr = c0 + ty, dc = r0 + tx;
+    if (dr < cols && dc < ldT) RT[dr * ldT + dc] = (dc < rows) ? tile[tx][ty] : 0.0;
+    const uint32_t bit = (words[tx] >> ty) & 1u;
+    const uint32_t word = __ballot_sync(0xffffffffu, bit != 0u);
+    if (tx == 0 && dr < cols && r0 < ldT) bitsT[dr * wprT + (r0 >> 5)] = word;
+  }
+}
+
+}  // namespace bnmtf
+
+using namespace bnmtf;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int bnmtf_version(void) { return 100; }
+const char* bnmtf_last_error(void) { return g_err; }
+int64_t bnmtf_ld_for(int64_t cols) { return round_up64(cols, 64); }
+int bnmtf_kp_for(int K) { return 8 * tiles_for(K); }
+int64_t bnmtf_gram_len(int K) { const int nt = tiles_for(K); return (int64_t)nt * (nt + 1) / 2 * 64; }
+
+static int check_k(int K) {
+  if (K < 1 || K > 63) { set_error("K=%d out of range (1..63)", K); return -2; }
+  return 0;
+}
+
+int bnmtf_pack_dataset_f64(const double* R_in, const double* M_in, int64_t rows, int64_t cols, int64_t ld,
+                           double* R_out, uint32_t* bits_out, void* stream) {
+  if (rows <= 0 || cols <= 0 || ld < cols || ld % 64) { set_error("pack_dataset: bad shape"); return -2; }
+  const long long warps = rows * (ld / 32);
+  const long long blocks = (warps * 32 + 255) / 256;
+  k_pack_dataset<<<(unsigned)blocks, 256, 0, ST(stream)>>>(R_in, M_in, rows, cols, ld, R_out, bits_out);
+  return check_launch("pack_dataset");
+}
+
+int bnmtf_pack_mask_f64(const double* M_in, int64_t rows, int64_t cols, int64_t ld, uint32_t* bits_out, void* stream) {
+  return bnmtf_pack_dataset_f64(nullptr, M_in, rows, cols, ld, nullptr, bits_out, stream);
+}
+
+int bnmtf_transpose_dataset_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t cols, int64_t ld,
+                                double* RT, uint32_t* bitsT, int64_t ldT, void* stream) {
+  if (ld % 64 || ldT % 64 || ldT < rows || ld < cols) { set_error("transpose_dataset: bad shape"); return -2; }
+  // cover the whole padded source (rows up to ldT, cols up to ld) so that every padding word is written
+  dim3 grid((unsigned)(ld / 32), (unsigned)(ldT / 32));
+  k_transpose_dataset<<<grid, dim3(32, 32), 0, ST(stream)>>>(R, bits, rows, cols, ld, RT, bitsT, ldT);
+  return check_launch("transpose_dataset");
+}
+
+int bnmtf_pad_factor_f64(const double* X, const double* Var, int64_t n, int K, int64_t n_alloc, double* Xp, double* Vp,
+                         void* stream) {
+  if (check_k(K)) return -2;
+  return launch_pad_factor(X, Var, (int)n, K, (int)n_alloc, Xp, Vp, ST(stream));
+}
+
+int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, int K,
+                       int nseg, double* RXpart, void* stream) {
+  if (check_k(K)) return -2;
+  return launch_stats_rx(R, bits, (int)rows, (int)ld, Xp, K, nseg, RXpart, ST(stream));
+}
+
+int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp, int K,
+                         int polarity, int nseg, double* Gpart, double* SVpart, void* stream) {
+  if (check_k(K)) return -2;
+  if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram: Vp and SVpart must be given together"); return -2; }
+  return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, ST(stream));
+}
+
+int bnmtf_gram_full_f64(const double* Xp, const double* Vp, int64_t n, int K, int64_t dummy_row, double* Gfull,
+                        double* scratch, void* stream) {
+  if (check_k(K)) return -2;
+  return launch_gram_full(Xp, Vp, (int)n, K, (int)dummy_row, Gfull, scratch, ST(stream));
+}
+
+int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, int polarity, const double* RXpart,
+                       const double* Gpart, const double* SVpart, const double* Gfull, double* fac, double* var,
+                       double* mu, double* tauf, const double* lambda, const double* scalars, const int* order,
+                       int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
+                       double* sterm, double* extra, void* stream) {
+  if (check_k(K)) return -2;
+  if (mode < 0 || mode > 2) { set_error("row_solve: bad mode %d", mode); return -2; }
+  if (mode == BNMTF_MODE_VB && (!var || !SVpart)) { set_error("row_solve: VB needs var and SVpart"); return -2; }
+  if (!polarity && !Gfull) { set_error("row_solve: polarity 0 needs Gfull"); return -2; }
+  RowSolveArgs a;
+  a.mode = mode; a.rows = (int)rows; a.K = K; a.nseg_rx = nseg_rx; a.nseg_g = nseg_g; a.polarity = polarity;
+  a.n_order = n_order; a.apply = apply; a.RXpart = RXpart; a.Gpart = Gpart; a.SVpart = SVpart; a.Gfull = Gfull;
+  a.fac = fac; a.var = var; a.mu = mu; a.tauf = tauf; a.lambda = lambda; a.scalars = scalars; a.order = order;
+  a.min_tn = min_tn; a.seed = seed; a.iter = reinterpret_cast<const unsigned long long*>(iter); a.salt = salt;
+  a.sterm = sterm; a.extra = extra;
+  return launch_row_solve(a, ST(stream));
+}
+
+int bnmtf_masked_metrics_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Ap,
+                             const double* Bp, int K, int nseg, double* partials, double* out8, void* stream) {
+  if (check_k(K)) return -2;
+  return launch_masked_metrics(R, bits, (int)rows, (int)ld, Ap, Bp, K, nseg, partials, out8, ST(stream));
+}
+
+int bnmtf_vb_factor_terms_f64(const double* ex, const double* var, const double* mu, const double* tauf,
+                              const double* lambda, int64_t n, double* partials, int nblocks, void* stream) {
+  return launch_vb_factor_terms(ex, var, mu, tauf, lambda, n, partials, nblocks, ST(stream));
+}
+
+int bnmtf_dense_metrics_f64(const double* R, const double* P, const double* M, int64_t n, double* partials, int nblocks,
+                            double* out8, void* stream) {
+  if (nblocks < 1) { set_error("dense_metrics: nblocks < 1"); return -2; }
+  return launch_dense_metrics(R, P, M, n, partials, nblocks, out8, ST(stream));
+}
+
+int bnmtf_reduce8_f64(const double* partials, int n, double* out8, void* stream) {
+  return launch_reduce8(partials, n, out8, ST(stream));
+}
+int bnmtf_reduce1_f64(const double* x, int64_t n, double* out, void* stream) {
+  return launch_reduce1(x, n, out, ST(stream));
+}
+
+int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_alpha_s, double lgamma_alpha,
+                          double lgamma_alpha_s, int64_t n_factor_elems, const double* m8, const double* ex1,
+                          const double* el8, double* scalars, double* trace, uint64_t* iter, int trace_cap,
+                          uint64_t seed, int update_tau, void* stream) {
+  FinishArgs a;
+  a.mode = mode; a.alpha = alpha; a.beta = beta; a.digamma_alpha_s = digamma_alpha_s; a.lgamma_alpha = lgamma_alpha;
+  a.lgamma_alpha_s = lgamma_alpha_s; a.n_factor_elems = (int)n_factor_elems; a.m8 = m8; a.ex1 = ex1; a.el8 = el8;
+  a.scalars = scalars; a.trace = trace; a.iter = reinterpret_cast<unsigned long long*>(iter); a.trace_cap = trace_cap;
+  a.seed = seed; a.update_tau = update_tau;
+  if (mode == BNMTF_MODE_VB && (!ex1 || !el8)) { set_error("finish_sweep: VB needs ex1 and el8"); return -2; }
+  return launch_finish(a, ST(stream));
+}
+
+int bnmtf_tn_moments_f64(const double* mu, const double* tau, int64_t n, double* ex, double* var, void* stream) {
+  return launch_tn_moments(mu, tau, n, ex, var, ST(stream));
+}
+int bnmtf_tn_draw_f64(const double* mu, const double* tau, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
+                      void* stream) {
+  return launch_tn_draw(mu, tau, n, seed, stream_id, out, ST(stream));
+}
+int bnmtf_gamma_draw_f64(double shape, double rate, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
+                         void* stream) {
+  return launch_gamma_draw(shape, rate, n, seed, stream_id, out, ST(stream));
+}
+int bnmtf_exponential_draw_f64(const double* lambda, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
+                               void* stream) {
+  return launch_exponential_draw(lambda, n, seed, stream_id, out, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+// Layer 2 for the two-factor model R ~ U V^T: per-row sequential column updates from the row statistics,
+// the masked prediction metrics, the noise-precision update and the small elementwise helpers.
+#include "common.cuh"
+
+namespace bnmtf {
+
+// ---------------------------------------------------------------------------------------------------
+// padded factor buffers
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_pad_factor(const double* __restrict__ X, const double* __restrict__ Var, int n, int K, int KP,
+                             int n_alloc, double* __restrict__ Xp, double* __restrict__ Vp) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n_alloc * KP) return;
+  const int j = (int)(i / KP), k = (int)(i - (size_t)j * KP);
+  double x = 0.0, v = 0.0;
+  if (j < n) {
+    if (k < K) { x = X[(size_t)j * K + k]; if (Var) v = Var[(size_t)j * K + k]; }
+    else if (k == K) x = 1.0;
+  }
+  Xp[i] = x;
+  if (Vp) Vp[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_bnmf_row_solve: one warp per row.
+//   G_obs = polarity ? sum_seg Gpart : Gfull - sum_seg Gpart      (K x K, symmetric, in shared memory)
+//   for k in order:   s   = RX_k - sum_{k' != k} G_obs[k][k'] u_k'          (the reference's masked row sum)
+//                     b   = G_obs[k][k] (+ sum_obs Var_k for VB)
+//                     tau_k = tau * b ;  mu_k = 1/tau_k * (-lambda_k + tau * s)
+//                     u_k <- draw | (mean, variance) | max(mu,0,min_tn)
+// which is bnmf_gibbs_optimised.py:134-137,167-171 / bnmf_vb_optimised.py:132-134,189-204 / nmf_icm.py:126-130
+// evaluated for one row with the other factor fixed.  The K updates of a row are sequential (Gauss-Seidel) as
+// in the reference; different rows are independent.
+// ---------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
+  constexpr int KP = 8 * NT;
+  constexpr int GS = KP + 1;
+  constexpr int NTP = NT * (NT + 1) / 2;
+  constexpr int CPL = (KP + 31) / 32;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= a.rows) return;
+  double* G = smem + (size_t)warp * (KP * GS);
+  const int K = a.K;
+
+  // Gram tiles -> full symmetric matrix
+  for (int i = lane; i < NTP * 64; i += 32) {
+    const int p = i >> 6, rc = i & 63, r = rc >> 3, c = rc & 7;
+    int ta = 0, rem = p;
+    while (rem >= NT - ta) { rem -= NT - ta; ++ta; }
+    const int tb = ta + rem;
+    double s = 0.0;
+    for (int sgm = 0; sgm < a.nseg_g; ++sgm) s += a.Gpart[((size_t)sgm * a.rows + row) * (NTP * 64) + i];
+    const double v = a.polarity ? s : a.Gfull[i] - s;
+    const int kr = 8 * ta + r, kc = 8 * tb + c;
+    G[kr * GS + kc] = v;
+    if (ta != tb) G[kc * GS + kr] = v;
+  }
+  double rx[CPL], sv[CPL], u[CPL], vr[CPL];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane + 32 * q;
+    rx[q] = sv[q] = u[q] = vr[q] = 0.0;
+    if (c < KP) {
+      for (int sgm = 0; sgm < a.nseg_rx; ++sgm) rx[q] += a.RXpart[((size_t)sgm * a.rows + row) * KP + c];
+      if (a.mode == MODE_VB) {
+        double s = 0.0;
+        for (int sgm = 0; sgm < a.nseg_g; ++sgm) s += a.SVpart[((size_t)sgm * a.rows + row) * KP + c];
+        sv[q] = a.polarity ? s : a.Gfull[NTP * 64 + c] - s;
+      }
+    }
+    if (c < K) {
+      u[q] = a.fac[(size_t)row * K + c];
+      if (a.mode == MODE_VB) vr[q] = a.var[(size_t)row * K + c];
+    }
+  }
+  __syncwarp();
+  const double tau = a.scalars[S_TAU];
+  const unsigned long long it = a.iter ? *a.iter : 0ull;
+
+  for (int o = 0; o < a.n_order; ++o) {
+    const int k = a.order ? a.order[o] : o;
+    double part = 0.0;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      if (c < K && c != k) part += G[k * GS + c] * u[q];
+    }
+    const double dot = warp_sum(part);
+    double rxk = rx[0], svk = sv[0];
+#pragma unroll
+    for (int q = 1; q < CPL; ++q) if ((k >> 5) == q) { rxk = rx[q]; svk = sv[q]; }
+    rxk = __shfl_sync(0xffffffffu, rxk, k & 31);
+    svk = __shfl_sync(0xffffffffu, svk, k & 31);
+    const double s = rxk - dot;
+    const double gkk = G[k * GS + k];
+    const double b = (a.mode == MODE_VB) ? gkk + svk : gkk;
+    const double lam = a.lambda[(size_t)row * K + k];
+    const double tau_k = tau * b;
+    const double mu_k = (1.0 / tau_k) * (-lam + tau * s);
+    double val = 0.0, vv = 0.0;
+    if (a.apply) {
+      if (a.mode == MODE_GIBBS) {
+        Philox rng(a.seed, it * 16ull + a.salt, (unsigned long long)row * K + k);
+        val = tn_draw(mu_k, tau_k, rng);
+      } else if (a.mode == MODE_VB) {
+        tn_moments(mu_k, tau_k, val, vv);
+      } else {
+        val = (mu_k != mu_k) ? mu_k : fmax(mu_k, 0.0);   // numpy.maximum propagates NaN (nmf_icm.py:129)
+        val = (val != val) ? val : fmax(val, a.min_tn);
+      }
+#pragma unroll
+      for (int q = 0; q < CPL; ++q)
+        if (lane + 32 * q == k) { u[q] = val; vr[q] = vv; }
+    }
+    if (lane == 0) {
+      const size_t idx = (size_t)row * K + k;
+      if (a.apply) { a.fac[idx] = val; if (a.mode == MODE_VB) a.var[idx] = vv; }
+      if (a.mu) a.mu[idx] = mu_k;
+      if (a.tauf) a.tauf[idx] = tau_k;
+      if (a.sterm) a.sterm[idx] = s;
+    }
+  }
+  if (a.extra) {
+    double e = 0.0;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      if (c < K) e += vr[q] * (G[c * GS + c] + sv[q]) + u[q] * u[q] * sv[q];
+    }
+    e = warp_sum(e);
+    if (lane == 0) a.extra[row] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_masked_metrics: partial sums over the set bits of `bits` of  e^2, p, p^2, r*p, r, r^2, 1  with
+// p = A_i . B_j (predict / predict_while_running, bnmf_gibbs_optimised.py:199-223).  The prediction tile is a
+// DMMA product of padded factor rows; a warp owns 16 rows and walks 32 columns at a time (4 column tiles
+// permuted so that each lane reads 64 contiguous bytes of R).
+// ---------------------------------------------------------------------------------------------------
+template <int KS>  // number of 4-wide k steps = ceil(K/4), templated for register arrays
+__global__ void __launch_bounds__(256) k_masked_metrics(const double* __restrict__ R, const uint32_t* __restrict__ bits,
+                                                       int rows, int ld, const double* __restrict__ Ap,
+                                                       const double* __restrict__ Bp, int K, int KP, int seg_cols,
+                                                       double* __restrict__ partials) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * 128 + warp * 16;
+  const int c_begin = blockIdx.y * seg_cols, c_end = min(ld, c_begin + seg_cols);
+  const int wpr = ld >> 5;
+  double sums[7] = {0, 0, 0, 0, 0, 0, 0};
+  double af[2][KS];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = min(row0 + 8 * r + g, rows - 1);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int k = 4 * ks + t;
+      af[r][ks] = (k < K) ? Ap[(size_t)row * KP + k] : 0.0;
+    }
+  }
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    uint32_t mw[2];
+    const double* rp[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + 8 * r + g;
+      const int rc = min(row, rows - 1);
+      mw[r] = (row < rows) ? bits[(size_t)rc * wpr + (c0 >> 5)] : 0u;
+      rp[r] = R + (size_t)rc * ld + c0 + 8 * t;
+    }
+    const uint32_t any = __ballot_sync(0xffffffffu, (mw[0] | mw[1]) != 0u);
+    if (!any) continue;
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu) {
+      // B fragment column g of tile uu  <->  actual column c0 + 8*(g>>1) + 2*uu + (g&1)
+      const double* br = Bp + (size_t)(c0 + 8 * (g >> 1) + 2 * uu + (g & 1)) * KP + t;
+      double p[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double bf = (4 * ks + t < K) ? br[4 * ks] : 0.0;
+        dmma884(p[0][0], p[0][1], af[0][ks], bf);
+        dmma884(p[1][0], p[1][1], af[1][ks], bf);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double2 rv = *reinterpret_cast<const double2*>(rp[r] + 2 * uu);
+        const uint32_t two = (mw[r] >> (8 * t + 2 * uu)) & 3u;
+        const double rr[2] = {rv.x, rv.y};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if ((two >> i) & 1u) {
+            const double e = rr[i] - p[r][i];
+            sums[0] += e * e; sums[1] += p[r][i]; sums[2] += p[r][i] * p[r][i]; sums[3] += rr[i] * p[r][i];
+            sums[4] += rr[i]; sums[5] += rr[i] * rr[i]; sums[6] += 1.0;
+          }
+        }
+      }
+    }
+  }
+  __shared__ double red[8][8];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const double s = warp_sum(sums[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = s;
+  }
+}
+
+// deterministic sum of `n` partial vectors of width 8 -> out[8]
+__global__ void k_reduce8(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double red[256][8];
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += 256)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s[c] += partials[(size_t)i * 8 + c];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) red[threadIdx.x][c] = s[c];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) red[threadIdx.x][c] += red[threadIdx.x + o][c];
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) out[threadIdx.x] = red[0][threadIdx.x];
+}
+
+// generic deterministic sum of a vector
+__global__ void k_reduce1(const double* __restrict__ x, long long n, double* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 256) s += x[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// sums over entries with M != 0 of {e^2, p, p^2, r p, r, r^2, 1} for dense host-layout matrices
+// (compute_MSE / compute_R2 / compute_Rp helpers, bnmf_gibbs_optimised.py:208-223)
+__global__ void __launch_bounds__(256) k_dense_metrics(const double* __restrict__ R, const double* __restrict__ P,
+                                                      const double* __restrict__ M, long long n,
+                                                      double* __restrict__ partials) {
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double m = M[i];
+    if (m != 0.0) {
+      const double r = R[i], p = P[i], e = r - p;
+      s[0] += m * e * e; s[1] += m * p; s[2] += m * p * p; s[3] += m * r * p; s[4] += m * r; s[5] += m * r * r; s[6] += m;
+    }
+  }
+  __shared__ double red[8][8];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const double v = warp_sum(s[i]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double v = 0.0;
+    if (threadIdx.x < 7) for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// VB: factor-side ELBO terms of one factor matrix (bnmf_vb_optimised.py:166-167,172-177), as block partials:
+//   [0] sum log(lambda) - lambda*exp   [1] -0.5 sum log tau + sum log(0.5 erfc(-mu sqrt(tau)/sqrt2)) + sum tau/2 (var + (exp-mu)^2)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vb_factor_terms(const double* __restrict__ ex, const double* __restrict__ var,
+                                                        const double* __restrict__ mu, const double* __restrict__ tauf,
+                                                        const double* __restrict__ lambda, long long n,
+                                                        double* __restrict__ partials) {
+  double s0 = 0.0, s1 = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double l = lambda[i], e = ex[i], v = var[i], m = mu[i], t = tauf[i];
+    s0 += log(l) - l * e;
+    const double d = e - m;
+    s1 += -0.5 * log(t) + log(0.5 * erfc(-m * sqrt(t) * kInvSqrt2)) + t * 0.5 * (v + d * d);
+  }
+  __shared__ double red[8][2];
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+  }
+  if (threadIdx.x >= 2 && threadIdx.x < 8) partials[(size_t)blockIdx.x * 8 + threadIdx.x] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_bnmf_finish: end of a sweep.  m8 = reduced metric sums over the training mask; ex1 = reduced extra term
+// (VB), el8 = reduced factor ELBO terms (VB, U then V added).  Updates tau (Gibbs: Gamma draw,
+// bnmf_gibbs_optimised.py:144,161-165; VB: :181-183,213-215; ICM: nmf_icm.py:137) and appends one trace row.
+// ---------------------------------------------------------------------------------------------------
+__device__ double gamma_draw_dev(double shape, double rate, Philox& rng) {
+  // Marsaglia & Tsang (2000); shape < 1 boosted by U^(1/shape)
+  double boost = 1.0;
+  if (shape < 1.0) { double u0, u1; rng.uniform2(u0, u1); boost = pow(u0, 1.0 / shape); shape += 1.0; }
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int tries = 0; tries < 1000; ++tries) {
+    double u0, u1; rng.uniform2(u0, u1);
+    const double x = normcdfinv(u0);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (log(u1) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v / rate;
+  }
+  return boost * d / rate;
+}
+
+__global__ void k_bnmf_finish(FinishArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* S = a.scalars;
+  const double n = a.m8[6], se2 = a.m8[0], sp = a.m8[1], sp2 = a.m8[2], srp = a.m8[3], sr = a.m8[4], sr2 = a.m8[5];
+  const double mean_r = sr / n, mean_p = sp / n;
+  const double ss_tot = sr2 - sr * mean_r;
+  const double cov = srp - sr * mean_p;
+  const double var_p = sp2 - sp * mean_p;
+  S[S_SUM_E2] = se2; S[S_SUM_R] = sr; S[S_SUM_R2] = sr2; S[S_OMEGA] = n;
+  S[S_MSE] = se2 / n;
+  S[S_R2] = (ss_tot != 0.0) ? 1.0 - se2 / ss_tot : INFINITY;
+  S[S_RP] = cov / (sqrt(ss_tot) * sqrt(var_p));
+  const unsigned long long it = *a.iter;
+  const double alpha_s = a.alpha + 0.5 * n;
+  S[S_ALPHA_S] = alpha_s;
+  double elbo = 0.0;
+  if (a.mode == MODE_VB) {
+    const double esd = se2 + a.ex1[0];
+    S[S_ESD] = esd;
+    if (a.update_tau) {
+      const double beta_s = a.beta + 0.5 * esd;
+      S[S_BETA_S] = beta_s;
+      S[S_TAU] = alpha_s / beta_s;
+      S[S_LOGTAU] = a.digamma_alpha_s - log(beta_s);
+    }
+    const double beta_s = S[S_BETA_S], et = S[S_TAU], elt = S[S_LOGTAU];
+    elbo = n / 2.0 * (elt - kLog2Pi) - et / 2.0 * esd + a.el8[0]
+         + a.alpha * log(a.beta) - a.lgamma_alpha + (a.alpha - 1.0) * elt - a.beta * et
+         - alpha_s * log(beta_s) + a.lgamma_alpha_s - (alpha_s - 1.0) * elt + beta_s * et
+         + a.el8[1] + a.n_factor_elems / 2.0 * kLog2Pi;
+    S[S_ELBO] = elbo;
+  } else if (a.update_tau) {
+    const double beta_s = a.beta + 0.5 * se2;
+    S[S_BETA_S] = beta_s;
+    if (a.mode == MODE_GIBBS) {
+      Philox rng(a.seed, it * 16ull + 15ull, 0ull);
+      S[S_TAU] = gamma_draw_dev(alpha_s, beta_s, rng);
+    } else {
+      S[S_TAU] = (alpha_s - 1.0) / beta_s;
+    }
+  }
+  if (a.trace && it < (unsigned long long)a.trace_cap) {
+    double* tr = a.trace + it * kTraceWidth;
+    tr[0] = S[S_TAU]; tr[1] = S[S_MSE]; tr[2] = S[S_R2]; tr[3] = S[S_RP]; tr[4] = elbo; tr[5] = se2; tr[6] = S[S_ESD];
+    tr[7] = S[S_LOGTAU];
+  }
+  *a.iter = it + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// elementwise distribution kernels (code/models/distributions/*.py)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_tn_moments(const double* __restrict__ mu, const double* __restrict__ tau, long long n,
+                             double* __restrict__ ex, double* __restrict__ var) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double e, v;
+  tn_moments(mu[i], tau[i], e, v);
+  if (ex) ex[i] = e;
+  if (var) var[i] = v;
+}
+
+__global__ void k_tn_draw(const double* __restrict__ mu, const double* __restrict__ tau, long long n,
+                          unsigned long long seed, unsigned long long stream, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox rng(seed, stream, (unsigned long long)i);
+  out[i] = tn_draw(mu[i], tau[i], rng);
+}
+
+__global__ void k_gamma_draw(double shape, double rate, long long n, unsigned long long seed, unsigned long long stream,
+                             double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox rng(seed, stream, (unsigned long long)i);
+  out[i] = gamma_draw_dev(shape, rate, rng);
+}
+
+__global__ void k_exponential_draw(const double* __restrict__ lambda, long long n, unsigned long long seed,
+                                   unsigned long long stream, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox rng(seed, stream, (unsigned long long)i);
+  double u0, u1; rng.uniform2(u0, u1);
+  out[i] = -log(u0) / lambda[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------
+int launch_pad_factor(const double* X, const double* Var, int n, int K, int n_alloc, double* Xp, double* Vp,
+                      cudaStream_t st) {
+  const int KP = 8 * tiles_for(K);
+  const size_t total = (size_t)n_alloc * KP;
+  k_pad_factor<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, Var, n, K, KP, n_alloc, Xp, Vp);
+  return check_launch("pad_factor");
+}
+
+int launch_row_solve(const RowSolveArgs& a, cudaStream_t st) {
+  const int nt = tiles_for(a.K);
+  const int KP = 8 * nt;
+  const size_t per_warp = (size_t)KP * (KP + 1) * sizeof(double);
+  int warps = (int)(40 * 1024 / per_warp);
+  if (warps > 4) warps = 4;
+  if (warps < 1) warps = 1;
+  const size_t smem = per_warp * warps;
+  const int grid = (a.rows + warps - 1) / warps;
+  switch (nt) {
+#define BNMTF_RS(N) case N: k_bnmf_row_solve<N><<<grid, warps * 32, smem, st>>>(a); break;
+    BNMTF_RS(1) BNMTF_RS(2) BNMTF_RS(3) BNMTF_RS(4) BNMTF_RS(5) BNMTF_RS(6) BNMTF_RS(7) BNMTF_RS(8)
+#undef BNMTF_RS
+    default: set_error("row_solve: K=%d out of range", a.K); return -2;
+  }
+  return check_launch("row_solve");
+}
+
+// partials must hold (ceil(rows/128) * nseg) * 8 doubles; out8 receives the reduced sums.
+int launch_masked_metrics(const double* R, const uint32_t* bits, int rows, int ld, const double* Ap, const double* Bp,
+                          int K, int nseg, double* partials, double* out8, cudaStream_t st) {
+  const int KP = 8 * tiles_for(K);
+  const int ks = (K + 3) / 4;
+  const int seg_cols = round_up((ld + nseg - 1) / nseg, 32);
+  dim3 grid((rows + 127) / 128, nseg);
+  switch (ks) {
+#define BNMTF_MM(N) case N: k_masked_metrics<N><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials); break;
+    BNMTF_MM(1) BNMTF_MM(2) BNMTF_MM(3) BNMTF_MM(4) BNMTF_MM(5) BNMTF_MM(6) BNMTF_MM(7) BNMTF_MM(8)
+    BNMTF_MM(9) BNMTF_MM(10) BNMTF_MM(11) BNMTF_MM(12) BNMTF_MM(13) BNMTF_MM(14) BNMTF_MM(15) BNMTF_MM(16)
+#undef BNMTF_MM
+    default: set_error("masked_metrics: K=%d out of range", K); return -2;
+  }
+  k_reduce8<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out8);
+  return check_launch("masked_metrics");
+}
+
+int launch_vb_factor_terms(const double* ex, const double* var, const double* mu, const double* tauf,
+                           const double* lambda, long long n, double* partials, int nblocks, cudaStream_t st) {
+  k_vb_factor_terms<<<nblocks, 256, 0, st>>>(ex, var, mu, tauf, lambda, n, partials);
+  return check_launch("vb_factor_terms");
+}
+
+int launch_dense_metrics(const double* R, const double* P, const double* M, long long n, double* partials, int nblocks,
+                         double* out8, cudaStream_t st) {
+  k_dense_metrics<<<nblocks, 256, 0, st>>>(R, P, M, n, partials);
+  k_reduce8<<<1, 256, 0, st>>>(partials, nblocks, out8);
+  return check_launch("dense_metrics");
+}
+
+int launch_reduce8(const double* partials, int n, double* out8, cudaStream_t st) {
+  k_reduce8<<<1, 256, 0, st>>>(partials, n, out8);
+  return check_launch("reduce8");
+}
+
+int launch_reduce1(const double* x, long long n, double* out, cudaStream_t st) {
+  k_reduce1<<<1, 256, 0, st>>>(x, n, out);
+  return check_launch("reduce1");
+}
+
+int launch_finish(const FinishArgs& a, cudaStream_t st) {
+  k_bnmf_finish<<<1, 32, 0, st>>>(a);
+  return check_launch("bnmf_finish");
+}
+
+int launch_tn_moments(const double* mu, const double* tau, long long n, double* ex, double* var, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_tn_moments<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mu, tau, n, ex, var);
+  return check_launch("tn_moments");
+}
+int launch_tn_draw(const double* mu, const double* tau, long long n, unsigned long long seed, unsigned long long stream,
+                   double* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_tn_draw<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mu, tau, n, seed, stream, out);
+  return check_launch("tn_draw");
+}
+int launch_gamma_draw(double shape, double rate, long long n, unsigned long long seed, unsigned long long stream,
+                      double* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_gamma_draw<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shape, rate, n, seed, stream, out);
+  return check_launch("gamma_draw");
+}
+int launch_exponential_draw(const double* lambda, long long n, unsigned long long seed, unsigned long long stream,
+                            double* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_exponential_draw<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lambda, n, seed, stream, out);
+  return check_launch("exponential_draw");
+}
+
+}  // namespace bnmtf

@@ -1,0 +1,129 @@
+/* libbnmtf_b200 -- C ABI of the B200 (sm_100a) engine for the BNMF / BNMTF update sweep.
+ *
+ * The reference (ThomasBrouwer/BNMTF) is pure Python and has no FFI of its own; its boundary is the duck-typed
+ * model-class protocol.  The Python classes in bnmtf_b200/ implement that protocol and
+ * reach the device only through the functions below (ctypes), so this header is what a maintainer of the
+ * reference would bind to replace the bodies of run()/update_*()/predict().
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (the library never allocates or frees caller memory
+ *     and keeps no state besides a thread-local error string);
+ *   - every function enqueues its work on `stream` (a cudaStream_t passed as void*) and returns 0, or a negative
+ *     code with the message available from bnmtf_last_error(); no hidden synchronisation;
+ *   - all arithmetic is IEEE double.
+ *
+ * Data layout
+ *   dataset   R    : rows x ld doubles, row-major, ld = bnmtf_ld_for(cols) (multiple of 64), padding = 0
+ *             bits : rows x (ld/32) uint32 words, bit (j & 31) of word (j >> 5) set <=> entry (i,j) observed,
+ *                    padding bits clear.  The column phase uses a second copy of both, transposed.
+ *   factor    X    : n x K doubles, row-major, contiguous (what numpy / torch hold)
+ *   padded    Xp   : (ld_n + 8) x KP doubles with KP = 8*ceil((K+1)/8); Xp[j][k<K] = X[j][k], Xp[j][K] = 1 for
+ *                    j < n, everything else 0 (bnmtf_pad_factor_f64 builds it).  ld_n = bnmtf_ld_for(n).
+ *   statistics RXpart : nseg x rows x KP            masked R times X            (bnmtf_stats_rx_f64)
+ *              Gpart  : nseg x rows x NTP*64        packed upper 8x8 tiles of the per-row masked Gram,
+ *                                                   NTP = NT(NT+1)/2, NT = KP/8 (bnmtf_stats_gram_f64)
+ *              SVpart : nseg x rows x KP            masked sums of the factor variances (VB only)
+ *              Gfull  : NTP*64 + KP                 unmasked totals                 (bnmtf_gram_full_f64)
+ *   scalars   : 16 doubles per model instance, slots BNMTF_S_* below; iter: one uint64 sweep counter
+ */
+#ifndef BNMTF_B200_H
+#define BNMTF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNMTF_MODE_GIBBS 0
+#define BNMTF_MODE_VB 1
+#define BNMTF_MODE_ICM 2
+
+#define BNMTF_S_TAU 0      /* Gibbs/ICM: tau; VB: E[tau] */
+#define BNMTF_S_LOGTAU 1   /* VB: E[log tau] */
+#define BNMTF_S_ALPHA_S 2
+#define BNMTF_S_BETA_S 3
+#define BNMTF_S_SUM_E2 4
+#define BNMTF_S_ESD 5      /* VB: exp_square_diff */
+#define BNMTF_S_MSE 6
+#define BNMTF_S_R2 7
+#define BNMTF_S_RP 8
+#define BNMTF_S_ELBO 9
+#define BNMTF_S_SUM_R 10
+#define BNMTF_S_SUM_R2 11
+#define BNMTF_S_OMEGA 12
+#define BNMTF_S_COUNT 16
+#define BNMTF_TRACE_WIDTH 8 /* tau, MSE, R^2, Rp, ELBO, sum_e2, exp_square_diff, E[log tau] per sweep */
+
+int bnmtf_version(void);
+const char* bnmtf_last_error(void);
+int64_t bnmtf_ld_for(int64_t cols);
+int bnmtf_kp_for(int K);            /* padded factor width KP */
+int64_t bnmtf_gram_len(int K);      /* NTP*64 doubles per row */
+
+/* ---- layout --------------------------------------------------------------------------------------- */
+/* R_in, M_in: rows x cols contiguous doubles (M is the reference's 0/1 float mask).  Replaces the float mask
+ * products M*(...) of every reference update (e.g. bnmf_gibbs_optimised.py:164-177) by a bit mask. */
+int bnmtf_pack_dataset_f64(const double* R_in, const double* M_in, int64_t rows, int64_t cols, int64_t ld,
+                           double* R_out, uint32_t* bits_out, void* stream);
+int bnmtf_pack_mask_f64(const double* M_in, int64_t rows, int64_t cols, int64_t ld, uint32_t* bits_out, void* stream);
+/* (R, bits): rows x ld  ->  (RT, bitsT): cols x ldT with ldT = bnmtf_ld_for(rows) */
+int bnmtf_transpose_dataset_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t cols, int64_t ld,
+                                double* RT, uint32_t* bitsT, int64_t ldT, void* stream);
+int bnmtf_pad_factor_f64(const double* X, const double* Var /*or NULL*/, int64_t n, int K, int64_t n_alloc,
+                         double* Xp, double* Vp /*or NULL*/, void* stream);
+
+/* ---- layer 1: masked row statistics (the streaming passes over R) ------------------------------------- */
+int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, int K,
+                       int nseg, double* RXpart, void* stream);
+/* polarity 0: accumulate over the MISSING entries of each row (cheap when most entries are observed; the solver
+ * subtracts from Gfull), 1: over the OBSERVED entries. */
+int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp /*or NULL*/,
+                         int K, int polarity, int nseg, double* Gpart, double* SVpart /*or NULL*/, void* stream);
+/* scratch: >= 64 * (bnmtf_gram_len(K) + KP) doubles */
+int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t n, int K, int64_t dummy_row,
+                        double* Gfull, double* scratch, void* stream);
+
+/* ---- layer 2: two-factor model ------------------------------------------------------------------------ */
+/* All K (or the listed) column updates of one factor for every row, from the row statistics.  Replaces the
+ * k-loops of bnmf_gibbs_optimised.run (:134-142), bnmf_vb_optimised.run (:132-138) and nmf_icm.run (:126-135).
+ *   order/n_order : columns to update, in sequence (NULL -> 0..n_order-1)
+ *   apply         : 0 = only write mu/tauf/sterm for the CURRENT state (white-box tauU()/muU()/update_U())
+ *   fac,var       : n x K, updated in place when apply (var only for VB)
+ *   mu,tauf,sterm : optional n x K outputs (conditional mean, precision, masked-sum term)
+ *   extra         : optional rows doubles (VB): this row's share of exp_square_diff's variance term
+ *   iter,salt,seed: Philox stream = (*iter)*16 + salt; index = row*K + k */
+int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, int polarity,
+                       const double* RXpart, const double* Gpart, const double* SVpart, const double* Gfull,
+                       double* fac, double* var, double* mu, double* tauf, const double* lambda,
+                       const double* scalars, const int* order, int n_order, int apply, double min_tn,
+                       uint64_t seed, const uint64_t* iter, uint64_t salt, double* sterm, double* extra, void* stream);
+/* Sums over the set bits of `bits` of {e^2, p, p^2, r p, r, r^2, 1}, p = A_i.B_j  ->  out8 (predict(),
+ * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8. */
+int bnmtf_masked_metrics_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Ap,
+                             const double* Bp, int K, int nseg, double* partials, double* out8, void* stream);
+/* Same seven sums for dense contiguous R, P (prediction) and 0/1 (or weight) mask M of n entries each: the
+ * compute_MSE / compute_R2 / compute_Rp helpers.  partials: >= nblocks*8 doubles. */
+int bnmtf_dense_metrics_f64(const double* R, const double* P, const double* M, int64_t n, double* partials, int nblocks,
+                            double* out8, void* stream);
+int bnmtf_vb_factor_terms_f64(const double* ex, const double* var, const double* mu, const double* tauf,
+                              const double* lambda, int64_t n, double* partials, int nblocks, void* stream);
+int bnmtf_reduce8_f64(const double* partials, int n, double* out8, void* stream);
+int bnmtf_reduce1_f64(const double* x, int64_t n, double* out, void* stream);
+/* End of a sweep: metrics -> scalars, tau update (Gibbs draw / VB expectation / ICM mode), trace row, ++*iter. */
+int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_alpha_s, double lgamma_alpha,
+                          double lgamma_alpha_s, int64_t n_factor_elems, const double* m8, const double* ex1,
+                          const double* el8, double* scalars, double* trace, uint64_t* iter, int trace_cap,
+                          uint64_t seed, int update_tau, void* stream);
+
+/* ---- distributions (code/models/distributions/*.py) ---------------------------------------------------- */
+int bnmtf_tn_moments_f64(const double* mu, const double* tau, int64_t n, double* ex, double* var, void* stream);
+int bnmtf_tn_draw_f64(const double* mu, const double* tau, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
+                      void* stream);
+int bnmtf_gamma_draw_f64(double shape, double rate, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
+                         void* stream);
+int bnmtf_exponential_draw_f64(const double* lambda, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

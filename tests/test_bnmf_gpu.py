@@ -1,0 +1,152 @@
+"""GPU parity of the two-factor models against the golden fixtures (generated from the reference itself) and
+against the CPU oracle on the same seeded inputs.  Everything here goes through the ctypes C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def close(a, b, rtol=RTOL, what=""):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * 1e-3 * scale, err_msg=what)
+
+
+def priors2(g):
+    lam = float(g["lambda"])
+    return {"alpha": 1.0, "beta": 1.0, "lambdaU": lam, "lambdaV": lam}
+
+
+@pytest.fixture(scope="module")
+def models():
+    import bnmtf_b200
+    return bnmtf_b200
+
+
+def vb_from_golden(models, g):
+    m = models.bnmf_vb_optimised(g["R"], g["M"], int(g["K"]), priors2(g))
+    m.initialise("exp")
+    m.muU, m.muV = g["init_muU"].copy(), g["init_muV"].copy()
+    m.tauU, m.tauV = g["init_tauU"].copy(), g["init_tauV"].copy()
+    for k in range(int(g["K"])):
+        m.update_exp_U(k)
+    for k in range(int(g["K"])):
+        m.update_exp_V(k)
+    m.update_tau()
+    m.update_exp_tau()
+    return m
+
+
+@pytest.mark.parametrize("name", ["toy_bnmf_vb", "gdsc_bnmf_vb"])
+def test_vb_initialise_matches_reference(models, golden, name):
+    g = golden(name)
+    m = vb_from_golden(models, g)
+    close(m.expU, g["init_expU"]), close(m.varU, g["init_varU"]), close(m.expV, g["init_expV"]), close(m.varV, g["init_varV"])
+    close(m.exptau, g["init_exptau"]), close(m.explogtau, g["init_explogtau"])
+    close(m.elbo(), g["init_elbo"])
+
+
+@pytest.mark.parametrize("name", ["toy_bnmf_vb", "gdsc_bnmf_vb"])
+def test_vb_trajectory_matches_reference(models, golden, name):
+    """Factors, ELBO, MSE/R^2/Rp and E[tau] trajectories within 1e-9 relative of the reference's run()."""
+    g = golden(name)
+    m = vb_from_golden(models, g)
+    its = int(g["its"])
+    m.run(its)
+    close(m.all_performances["MSE"], g["trace_MSE"], what="MSE trace")
+    close(m.all_performances["R^2"], g["trace_R^2"], what="R2 trace")
+    close(m.all_performances["Rp"], g["trace_Rp"], what="Rp trace")
+    close(m.all_exp_tau, g["trace_exptau"], what="exptau trace")
+    ok = np.isfinite(g["trace_elbo"])
+    close(np.asarray(m.all_elbo)[ok], g["trace_elbo"][ok], what="ELBO trace")
+    for k in ("expU", "varU", "muU", "tauU", "expV", "varV", "muV", "tauV"):
+        close(getattr(m, k), g["final_" + k], what=k)
+    close(m.quality("AIC"), g["trace_AIC"][-1]), close(m.quality("BIC"), g["trace_BIC"][-1])
+    close(m.quality("loglikelihood"), g["trace_loglik"][-1]), close(m.quality("ELBO"), g["trace_elbo"][-1])
+    close(m.predict(g["M"])["MSE"], g["trace_MSE"][-1])
+
+
+def test_vb_run_twice_equals_run_once(models, golden):
+    g = golden("toy_bnmf_vb")
+    a, b = vb_from_golden(models, g), vb_from_golden(models, g)
+    a.run(6)
+    b.run(2), b.run(4)
+    close(a.expU, b.expU, rtol=1e-13), close(a.exptau, b.exptau, rtol=1e-13)
+
+
+def test_icm_trajectory_matches_reference(models, golden):
+    g = golden("toy_nmf_icm")
+    m = models.nmf_icm(g["R"], g["M"], int(g["K"]), priors2(g))
+    m.initialise("exp")
+    m.U, m.V = g["init_U"].copy(), g["init_V"].copy()
+    m.tau = (m.alpha_s() - 1.0) / m.beta_s()
+    close(m.tau, g["init_tau"])
+    m.run(int(g["its"]), minimum_TN=float(g["minimum_TN"]))
+    close(m.all_performances["MSE"], g["trace_MSE"]), close(m.all_tau, g["trace_tau"])
+    close(m.U, g["final_U"]), close(m.V, g["final_V"])
+    close(m.quality("loglikelihood"), g["loglik"]), close(m.quality("AIC"), g["AIC"]), close(m.quality("BIC"), g["BIC"])
+
+
+def test_gibbs_conditionals_match_reference(models, golden):
+    g = golden("toy_bnmf_gibbs")
+    K = int(g["K"])
+    m = models.bnmf_gibbs_optimised(g["R"], g["M"], K, priors2(g))
+    m.initialise("exp")
+    m.U, m.V = g["init_U"].copy(), g["init_V"].copy()
+    m.tau = m.alpha_s() / m.beta_s()
+    close(m.tau, g["init_tau"]), close(m.beta_s(), g["beta_s"]), close(m.alpha_s(), g["alpha_s"])
+    for k in range(K):
+        tU = m.tauU(k)
+        close(tU, g["tauU"][:, k]), close(m.muU(tU, k), g["muU"][:, k])
+        tV = m.tauV(k)
+        close(tV, g["tauV"][:, k]), close(m.muV(tV, k), g["muV"][:, k])
+
+
+def test_gibbs_chain_matches_reference_in_distribution(models, golden):
+    """Matched burn-in / thinning; posterior-mean MSE and E[tau] inside the reference's chain-to-chain band."""
+    g = golden("toy_bnmf_gibbs")
+    K = int(g["K"])
+    m = models.bnmf_gibbs_optimised(g["R"], g["M"], K, priors2(g), seed=11)
+    m.initialise("exp")
+    m.U, m.V = g["init_U"].copy(), g["init_V"].copy()
+    m.tau = m.alpha_s() / m.beta_s()
+    its, burn, thin = int(g["chain_its"]), int(g["chain_burn_in"]), int(g["chain_thinning"])
+    all_U, all_V, all_tau = m.run(its)
+    assert all_U.shape == (its, 100, K) and (all_U >= 0).all() and (all_V >= 0).all()
+    ref_mse, ref_tau = g["chains_MSE_tau"][:, 0], g["chains_MSE_tau"][:, 1]
+    mse = m.quality("MSE", burn, thin)
+    assert abs(mse - ref_mse.mean()) <= max(5 * ref_mse.std(), 0.05 * ref_mse.mean())
+    exp_tau = m.approx_expectation(burn, thin)[2]
+    assert abs(exp_tau - ref_tau.mean()) <= max(5 * ref_tau.std(), 0.05 * ref_tau.mean())
+    # the MSE trace converges like the reference's (same order of magnitude at matched iterations)
+    assert m.all_performances["MSE"][-1] == pytest.approx(float(g["chain_trace_MSE"][-1]), rel=0.25)
+    # a second run continues the chain with fresh random numbers
+    t_before = m.tau
+    m.run(3)
+    assert m.tau != t_before
+
+
+def test_tn_moments_and_draws_device(golden):
+    from scipy.stats import ks_2samp, kstest, truncnorm
+    from bnmtf_b200 import distributions as D
+    g = golden("distributions")
+    close(D.TN_vector_expectation(g["mus"], g["taus"]), g["exp"])
+    close(D.TN_vector_variance(g["mus"], g["taus"]), g["var"])
+    assert D.TN_expectation(-2000.0, 1.0) == pytest.approx(1.0 / 2000.0, rel=1e-14)
+    assert D.TN_draw(1.0, 0.0) == 0.0
+    for (mu, tau), ref_draws in zip(g["draw_cases"], g["draws"]):
+        ours = np.array(D.TN_vector_draw(np.full(20000, mu), np.full(20000, tau), seed=5))
+        assert (ours >= 0).all()
+        sigma = 1.0 / np.sqrt(tau)
+        assert kstest(ours, truncnorm((0 - mu) / sigma, np.inf, loc=mu, scale=sigma).cdf).pvalue > 1e-3, (mu, tau)
+        assert ks_2samp(ours, ref_draws).pvalue > 1e-3, (mu, tau)
+    # far tail (rejection branch): a = 12
+    ours = np.array(D.TN_vector_draw(np.full(20000, -12.0), np.full(20000, 1.0), seed=6))
+    assert kstest(ours, truncnorm(12.0, np.inf, loc=-12.0, scale=1.0).cdf).pvalue > 1e-3
+    gd = D.gamma_draws(3601.0, 5000.0, 20000, seed=7)
+    from scipy.stats import gamma as sgamma
+    assert kstest(gd, sgamma(3601.0, scale=1.0 / 5000.0).cdf).pvalue > 1e-3
+    gd = D.gamma_draws(0.5, 2.0, 20000, seed=8)
+    assert kstest(gd, sgamma(0.5, scale=0.5).cdf).pvalue > 1e-3
