@@ -40,6 +40,15 @@ _PLAIN = {"bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "
 
 _lib = None
 
+# kernels launched per entry point (for bench.py's gpu_launches count)
+KERNELS_PER_CALL = {"bnmtf_pack_dataset_f64": 1, "bnmtf_pack_mask_f64": 1, "bnmtf_transpose_dataset_f64": 1,
+                    "bnmtf_pad_factor_f64": 1, "bnmtf_stats_rx_f64": 1, "bnmtf_stats_gram_f64": 1,
+                    "bnmtf_gram_full_f64": 2, "bnmf_row_solve_f64": 1, "bnmtf_masked_metrics_f64": 2,
+                    "bnmtf_dense_metrics_f64": 2, "bnmtf_vb_factor_terms_f64": 1, "bnmtf_reduce8_f64": 1,
+                    "bnmtf_reduce1_f64": 1, "bnmf_finish_sweep_f64": 1, "bnmtf_tn_moments_f64": 1,
+                    "bnmtf_tn_draw_f64": 1, "bnmtf_gamma_draw_f64": 1, "bnmtf_exponential_draw_f64": 1}
+launch_count = [0]
+
 
 class BnmtfError(RuntimeError):
     pass
@@ -70,4 +79,5 @@ def call(name, *args):
         return rc
     if rc != 0:
         raise BnmtfError("%s failed (%d): %s" % (name, rc, lib.bnmtf_last_error().decode()))
+    launch_count[0] += KERNELS_PER_CALL.get(name, 1)
     return 0

@@ -65,6 +65,25 @@ class _TwoFactorBase(object):
         self._device_arg, self._seed, self._eng = device, seed, None
         self.verbose = False
 
+    @classmethod
+    def from_dataset(cls, dataset, K, priors, seed=None):
+        """Build a model on an engine.Dataset that already lives on the GPU (matrices too large for, or never
+        present in, host memory).  R and M stay None on the host; everything else behaves as usual."""
+        self = cls.__new__(cls)
+        self.R = self.M = None
+        self.K = K
+        (self.I, self.J) = (dataset.I, dataset.J)
+        self.size_Omega = float(dataset.n_obs)
+        self.alpha, self.beta = float(priors['alpha']), float(priors['beta'])
+        self.lambdaU, self.lambdaV = np.array(priors['lambdaU'], dtype=float), np.array(priors['lambdaV'], dtype=float)
+        if self.lambdaU.shape == ():
+            self.lambdaU = self.lambdaU * np.ones((self.I, self.K))
+        if self.lambdaV.shape == ():
+            self.lambdaV = self.lambdaV * np.ones((self.J, self.K))
+        self._device_arg, self._seed, self.verbose = dataset.device, seed, False
+        self._eng = BNMFEngine(dataset, K, cls._mode, self.alpha, self.beta, seed=0 if seed is None else seed)
+        return self
+
     def check_empty_rows_columns(self):
         sums_columns = self.M.sum(axis=0)
         sums_rows = self.M.sum(axis=1)

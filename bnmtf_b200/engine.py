@@ -274,6 +274,43 @@ class BNMFEngine:
             self._vb_terms()
         self.finish(update_tau=True, record=True)
 
+    def profile_sweep(self, reps=3):
+        """Per-kernel CUDA-event timings (ms, mean over reps) of the two streaming passes and the solver, for the
+        roofline block of bench.py.  Runs real sweeps (the state advances)."""
+        names = ("stats_rx", "stats_gram", "row_solve", "masked_metrics")
+        acc = {n: 0.0 for n in names}
+        count = {n: 0 for n in names}
+
+        def timed(name, fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            acc[name] += e0.elapsed_time(e1)
+            count[name] += 1
+        for _ in range(reps):
+            for side in (0, 1):
+                me, other, R, bits, rows, ld = self._sides(side)
+                nrx, ng, _ = self.nseg[side]
+                other.pad()
+                if self.polarity == 0:
+                    _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
+                              _ptr(self.Gfull), _ptr(self.gscratch), _stream())
+                timed("stats_rx", lambda: _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp),
+                                                    self.K, nrx, _ptr(self.RXpart), _stream()))
+                timed("stats_gram", lambda: _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp),
+                                                      _ptr(other.Vp), self.K, self.polarity, ng, _ptr(self.Gpart),
+                                                      _ptr(self.SVpart), _stream()))
+                timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1))
+            self.V.pad()
+            timed("masked_metrics", lambda: self._metrics_padded(self.ds.bits))
+            if self.vb:
+                _lib.call("bnmtf_reduce1_f64", _ptr(self.extra), self.ds.J, _ptr(self.ex1), _stream())
+                self._vb_terms()
+            self.finish(update_tau=True, record=False)
+        return {n: acc[n] / max(1, count[n]) for n in names}
+
     def alloc_trace(self, iterations):
         self.trace_cap = int(iterations)
         self.trace = torch.zeros((max(1, self.trace_cap), 8), dtype=torch.float64, device=self.ds.device)
