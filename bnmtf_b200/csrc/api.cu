@@ -29,7 +29,7 @@ int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_pad_factor(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
-int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, double*, double*, cudaStream_t);
+int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, const double*, double*, double*, cudaStream_t);
 int launch_vb_factor_terms(const double*, const double*, const double*, const double*, const double*, long long, double*, int, cudaStream_t);
 int launch_reduce8(const double*, int, double*, cudaStream_t);
 int launch_dense_metrics(const double*, const double*, const double*, long long, double*, int, double*, cudaStream_t);
@@ -174,9 +174,10 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
 }
 
 int bnmtf_masked_metrics_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Ap,
-                             const double* Bp, int K, int nseg, double* partials, double* out8, void* stream) {
+                             const double* Bp, int K, int nseg, const double* statics3, double* partials, double* out8,
+                             void* stream) {
   if (check_k(K)) return -2;
-  return launch_masked_metrics(R, bits, (int)rows, (int)ld, Ap, Bp, K, nseg, partials, out8, ST(stream));
+  return launch_masked_metrics(R, bits, (int)rows, (int)ld, Ap, Bp, K, nseg, statics3, partials, out8, ST(stream));
 }
 
 int bnmtf_vb_factor_terms_f64(const double* ex, const double* var, const double* mu, const double* tauf,

@@ -136,65 +136,105 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_masked_metrics: partial sums over the set bits of `bits` of  e^2, p, p^2, r*p, r, r^2, 1  with
+// k_masked_metrics: partial sums over the set bits of `bits` of  e^2, p, p^2 (and, FULL, r*p, r, r^2, 1)  with
 // p = A_i . B_j (predict / predict_while_running, bnmf_gibbs_optimised.py:199-223).  The prediction tile is a
 // DMMA product of padded factor rows; a warp owns 16 rows and walks 32 columns at a time (4 column tiles
-// permuted so that each lane reads 64 contiguous bytes of R).
+// permuted so that each lane reads 64 contiguous bytes of R).  The B chunk is staged k-major in shared memory
+// (row stride = 4 mod 16 doubles -> conflict-free fragment reads); R is register double-buffered.
+// For the training mask the r-only sums are static, and sum r*p = (sum r^2 + sum p^2 - sum e^2)/2.
 // ---------------------------------------------------------------------------------------------------
-template <int KS>  // number of 4-wide k steps = ceil(K/4), templated for register arrays
+template <int KS, bool FULL>  // KS = ceil(K/4) k-steps
 __global__ void __launch_bounds__(256) k_masked_metrics(const double* __restrict__ R, const uint32_t* __restrict__ bits,
                                                        int rows, int ld, const double* __restrict__ Ap,
                                                        const double* __restrict__ Bp, int K, int KP, int seg_cols,
                                                        double* __restrict__ partials) {
+  constexpr int CHM = KS <= 8 ? 128 : 64;
+  constexpr int CS = CHM + 4;
+  __shared__ double bs[4 * KS * CS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * 128 + warp * 16;
   const int c_begin = blockIdx.y * seg_cols, c_end = min(ld, c_begin + seg_cols);
   const int wpr = ld >> 5;
   double sums[7] = {0, 0, 0, 0, 0, 0, 0};
   double af[2][KS];
+  const double* rp[2];
+  const uint32_t* mp[2];
+  bool live[2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    const int row = min(row0 + 8 * r + g, rows - 1);
+    const int row = row0 + 8 * r + g;
+    const int rc = min(row, rows - 1);
+    live[r] = row < rows;
+    rp[r] = R + (size_t)rc * ld + 8 * t;
+    mp[r] = bits + (size_t)rc * wpr;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const int k = 4 * ks + t;
-      af[r][ks] = (k < K) ? Ap[(size_t)row * KP + k] : 0.0;
+      af[r][ks] = (k < K) ? Ap[(size_t)rc * KP + k] : 0.0;
     }
   }
-  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-    uint32_t mw[2];
-    const double* rp[2];
+  double2 nxt[2][4];
+  if (c_begin < c_end) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int row = row0 + 8 * r + g;
-      const int rc = min(row, rows - 1);
-      mw[r] = (row < rows) ? bits[(size_t)rc * wpr + (c0 >> 5)] : 0u;
-      rp[r] = R + (size_t)rc * ld + c0 + 8 * t;
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) nxt[r][uu] = *reinterpret_cast<const double2*>(rp[r] + c_begin + 2 * uu);
+  }
+  for (int c0 = c_begin; c0 < c_end; c0 += CHM) {
+    const int ncol = min(CHM, c_end - c0);   // multiple of 32
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncol * 4 * KS; i += 256) {
+      const int col = i / (4 * KS), k = i - col * (4 * KS);
+      const int rho = (col & ~31) + 8 * ((col >> 1) & 3) + 2 * ((col >> 3) & 3) + (col & 1);
+      bs[k * CS + rho] = (k < K) ? Bp[(size_t)(c0 + col) * KP + k] : 0.0;
     }
-    const uint32_t any = __ballot_sync(0xffffffffu, (mw[0] | mw[1]) != 0u);
-    if (!any) continue;
+    __syncthreads();
+    for (int q = 0; q < (ncol >> 5); ++q) {
+      const int cq = c0 + 32 * q;
+      double2 cur[2][4];
 #pragma unroll
-    for (int uu = 0; uu < 4; ++uu) {
-      // B fragment column g of tile uu  <->  actual column c0 + 8*(g>>1) + 2*uu + (g&1)
-      const double* br = Bp + (size_t)(c0 + 8 * (g >> 1) + 2 * uu + (g & 1)) * KP + t;
-      double p[2][2] = {{0, 0}, {0, 0}};
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const double bf = (4 * ks + t < K) ? br[4 * ks] : 0.0;
-        dmma884(p[0][0], p[0][1], af[0][ks], bf);
-        dmma884(p[1][0], p[1][1], af[1][ks], bf);
+        for (int uu = 0; uu < 4; ++uu) cur[r][uu] = nxt[r][uu];
+      if (cq + 32 < c_end) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) nxt[r][uu] = *reinterpret_cast<const double2*>(rp[r] + cq + 32 + 2 * uu);
       }
+      uint32_t mw[2];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const double2 rv = *reinterpret_cast<const double2*>(rp[r] + 2 * uu);
-        const uint32_t two = (mw[r] >> (8 * t + 2 * uu)) & 3u;
-        const double rr[2] = {rv.x, rv.y};
+      for (int r = 0; r < 2; ++r) mw[r] = live[r] ? mp[r][cq >> 5] : 0u;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if ((two >> i) & 1u) {
-            const double e = rr[i] - p[r][i];
-            sums[0] += e * e; sums[1] += p[r][i]; sums[2] += p[r][i] * p[r][i]; sums[3] += rr[i] * p[r][i];
-            sums[4] += rr[i]; sums[5] += rr[i] * rr[i]; sums[6] += 1.0;
+      for (int uu = 0; uu < 4; ++uu) {
+        // B fragment column g of tile uu <-> actual column cq + 8*(g>>1) + 2*uu + (g&1) = staged slot 32q + 8uu + g
+        const double* br = bs + t * CS + 32 * q + 8 * uu + g;
+        double p[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const double bf = br[4 * ks * CS];
+          dmma884(p[0][0], p[0][1], af[0][ks], bf);
+          dmma884(p[1][0], p[1][1], af[1][ks], bf);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t two = (mw[r] >> (8 * t + 2 * uu)) & 3u;
+          const double rr[2] = {cur[r][uu].x, cur[r][uu].y};
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const bool on = (two >> i) & 1u;
+            const double pm = on ? p[r][i] : 0.0;
+            const double em = on ? rr[i] - p[r][i] : 0.0;
+            sums[0] = fma(em, em, sums[0]);
+            sums[1] += pm;
+            sums[2] = fma(pm, pm, sums[2]);
+            if (FULL) {
+              const double rm = on ? rr[i] : 0.0;
+              sums[3] = fma(rm, pm, sums[3]);
+              sums[4] += rm;
+              sums[5] = fma(rm, rm, sums[5]);
+              sums[6] += on ? 1.0 : 0.0;
+            }
           }
         }
       }
@@ -203,14 +243,23 @@ __global__ void __launch_bounds__(256) k_masked_metrics(const double* __restrict
   __shared__ double red[8][8];
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    const double s = warp_sum(sums[i]);
-    if (lane == 0) red[warp][i] = s;
+    const double v = warp_sum(sums[i]);
+    if (lane == 0) red[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 7) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = s;
+  if (threadIdx.x < 8) {
+    double v = 0.0;
+    if (threadIdx.x < 7) for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
+  }
+}
+
+// lean mode: complete the 7-vector from the static sums of the training mask {sum r, sum r^2, |Omega|}
+__global__ void k_fill_static_sums(double* __restrict__ out8, const double* __restrict__ statics3) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double e2 = out8[0], p2 = out8[2], r = statics3[0], r2 = statics3[1], n = statics3[2];
+    out8[3] = 0.5 * (r2 + p2 - e2);
+    out8[4] = r; out8[5] = r2; out8[6] = n;
   }
 }
 
@@ -438,21 +487,25 @@ int launch_row_solve(const RowSolveArgs& a, cudaStream_t st) {
   return check_launch("row_solve");
 }
 
-// partials must hold (ceil(rows/128) * nseg) * 8 doubles; out8 receives the reduced sums.
+// partials must hold (ceil(rows/128) * nseg) * 8 doubles; out8 receives the reduced sums.  statics3 != NULL selects
+// the lean kernel (training mask: {sum r, sum r^2, |Omega|} known).
 int launch_masked_metrics(const double* R, const uint32_t* bits, int rows, int ld, const double* Ap, const double* Bp,
-                          int K, int nseg, double* partials, double* out8, cudaStream_t st) {
+                          int K, int nseg, const double* statics3, double* partials, double* out8, cudaStream_t st) {
   const int KP = 8 * tiles_for(K);
   const int ks = (K + 3) / 4;
-  const int seg_cols = round_up((ld + nseg - 1) / nseg, 32);
+  const int chm = ks <= 8 ? 128 : 64;
+  const int seg_cols = round_up((ld + nseg - 1) / nseg, chm);
   dim3 grid((rows + 127) / 128, nseg);
   switch (ks) {
-#define BNMTF_MM(N) case N: k_masked_metrics<N><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials); break;
+#define BNMTF_MM(N) case N: if (statics3) k_masked_metrics<N, false><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials); \
+                            else k_masked_metrics<N, true><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials); break;
     BNMTF_MM(1) BNMTF_MM(2) BNMTF_MM(3) BNMTF_MM(4) BNMTF_MM(5) BNMTF_MM(6) BNMTF_MM(7) BNMTF_MM(8)
     BNMTF_MM(9) BNMTF_MM(10) BNMTF_MM(11) BNMTF_MM(12) BNMTF_MM(13) BNMTF_MM(14) BNMTF_MM(15) BNMTF_MM(16)
 #undef BNMTF_MM
     default: set_error("masked_metrics: K=%d out of range", K); return -2;
   }
   k_reduce8<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out8);
+  if (statics3) k_fill_static_sums<<<1, 32, 0, st>>>(out8, statics3);
   return check_launch("masked_metrics");
 }
 

@@ -27,11 +27,11 @@ namespace bnmtf {
 // 2 row-groups x NT DMMAs per 4 columns.
 // ---------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256) k_stats_rx(const double* __restrict__ R, const uint32_t* __restrict__ bits,
+__global__ void __launch_bounds__(256, 3) k_stats_rx(const double* __restrict__ R, const uint32_t* __restrict__ bits,
                                                  int rows, int ld, const double* __restrict__ Xp, int seg_cols,
                                                  double* __restrict__ out) {
   constexpr int KP = 8 * NT;
-  constexpr int CH = 64;
+  constexpr int CH = NT <= 4 ? 128 : 64;   // columns of X staged per barrier pair (<= 34 KB of shared memory)
   constexpr int XS = KP + 1;  // odd stride: the 4 t-groups of a half warp land on disjoint 8-bank groups
   __shared__ double xs[CH * XS];
 
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) k_stats_rx(const double* __restrict__ R, 
   const int c_end = min(ld, c_begin + seg_cols);
   const int wpr = ld >> 5;
   const int ra = min(row0 + g, rows - 1), rb = min(row0 + 8 + g, rows - 1);
-  const double* Ra = R + (size_t)ra * ld;
-  const double* Rb = R + (size_t)rb * ld;
+  const double* Ra = R + (size_t)ra * ld + 4 * t;
+  const double* Rb = R + (size_t)rb * ld + 4 * t;
   const uint32_t* Ma = bits + (size_t)ra * wpr;
   const uint32_t* Mb = bits + (size_t)rb * wpr;
 
@@ -53,41 +53,56 @@ __global__ void __launch_bounds__(256) k_stats_rx(const double* __restrict__ R, 
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[r][n][0] = acc[r][n][1] = 0.0;
 
+  // register double buffer: the 16-column step after the current one is always in flight
+  double2 nxt[4];
+  if (c_begin < c_end) {
+    nxt[0] = *reinterpret_cast<const double2*>(Ra + c_begin);
+    nxt[1] = *reinterpret_cast<const double2*>(Ra + c_begin + 2);
+    nxt[2] = *reinterpret_cast<const double2*>(Rb + c_begin);
+    nxt[3] = *reinterpret_cast<const double2*>(Rb + c_begin + 2);
+  }
   for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+    const int ncol = min(CH, c_end - c0);   // multiple of 64
     __syncthreads();
-    for (int i = threadIdx.x; i < CH * KP; i += 256) {
+    for (int i = threadIdx.x; i < ncol * KP; i += 256) {
       int j = i / KP, k = i - j * KP;
       xs[j * XS + k] = Xp[(size_t)(c0 + j) * KP + k];
     }
     __syncthreads();
-    const uint64_t ma = *reinterpret_cast<const uint64_t*>(Ma + (c0 >> 5));
-    const uint64_t mb = *reinterpret_cast<const uint64_t*>(Mb + (c0 >> 5));
+    for (int h = 0; h < ncol; h += 64) {
+      const uint64_t ma = *reinterpret_cast<const uint64_t*>(Ma + ((c0 + h) >> 5));
+      const uint64_t mb = *reinterpret_cast<const uint64_t*>(Mb + ((c0 + h) >> 5));
 #pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-      const int j0 = c0 + 16 * s4 + 4 * t;
-      const double2 a01 = *reinterpret_cast<const double2*>(Ra + j0);
-      const double2 a23 = *reinterpret_cast<const double2*>(Ra + j0 + 2);
-      const double2 b01 = *reinterpret_cast<const double2*>(Rb + j0);
-      const double2 b23 = *reinterpret_cast<const double2*>(Rb + j0 + 2);
-      const uint32_t na = (uint32_t)(ma >> (16 * s4 + 4 * t)) & 0xFu;
-      const uint32_t nb = (uint32_t)(mb >> (16 * s4 + 4 * t)) & 0xFu;
-      double av[4] = {a01.x, a01.y, a23.x, a23.y};
-      double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+      for (int st = 0; st < 4; ++st) {
+        const double2 a01 = nxt[0], a23 = nxt[1], b01 = nxt[2], b23 = nxt[3];
+        const int jn = c0 + h + 16 * (st + 1);
+        if (jn < c_end) {
+          nxt[0] = *reinterpret_cast<const double2*>(Ra + jn);
+          nxt[1] = *reinterpret_cast<const double2*>(Ra + jn + 2);
+          nxt[2] = *reinterpret_cast<const double2*>(Rb + jn);
+          nxt[3] = *reinterpret_cast<const double2*>(Rb + jn + 2);
+        }
+        const int sh = 16 * st + 4 * t;
+        const uint32_t na = (uint32_t)(ma >> sh) & 0xFu;
+        const uint32_t nb = (uint32_t)(mb >> sh) & 0xFu;
+        double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        double bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        av[s] = ((na >> s) & 1u) ? av[s] : 0.0;
-        bv[s] = ((nb >> s) & 1u) ? bv[s] : 0.0;
-      }
-      // inner index of step s, lane t  <->  column 16*s4 + 4*t + s of the chunk (any bijection works as long
-      // as A and B use the same one; this one gives every lane 32 contiguous bytes of its row)
+        for (int q = 0; q < 4; ++q) {
+          av[q] = ((na >> q) & 1u) ? av[q] : 0.0;
+          bv[q] = ((nb >> q) & 1u) ? bv[q] : 0.0;
+        }
+        // inner index of step q, lane t  <->  column 16*st + 4*t + q of the 64-column block (any bijection works
+        // as long as A and B use the same one; this one gives every lane 32 contiguous bytes of its row)
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const double* xr = xs + (16 * s4 + 4 * t + s) * XS + g;
+        for (int q = 0; q < 4; ++q) {
+          const double* xr = xs + (h + 16 * st + 4 * t + q) * XS + g;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          const double bf = xr[8 * n];
-          dmma884(acc[0][n][0], acc[0][n][1], av[s], bf);
-          dmma884(acc[1][n][0], acc[1][n][1], bv[s], bf);
+          for (int n = 0; n < NT; ++n) {
+            const double bf = xr[8 * n];
+            dmma884(acc[0][n][0], acc[0][n][1], av[q], bf);
+            dmma884(acc[1][n][0], acc[1][n][1], bv[q], bf);
+          }
         }
       }
     }

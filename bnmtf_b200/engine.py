@@ -143,11 +143,13 @@ class BNMFEngine:
         # segment counts: enough CTAs to fill 148 SMs when the matrix has few rows
         self.nseg = {}
         for side, (rows, ld) in enumerate(((I, dataset.ldJ), (J, dataset.ldI))):
+            # CTAs per launch: aim for >= 6 waves of resident CTAs (148 SMs x 3 resp. 2 CTAs) so that the tail
+            # wave costs little; segments are column ranges whose partial results the solver adds up in order
             rb = (rows + 127) // 128
-            nrx = max(1, min(ld // 64, -(-296 // rb)))
+            nrx = max(1, min(ld // 128, -(-2664 // rb)))
             gb = (rows + 7) // 8
             ng = max(1, min(-(-(ld // 32) // 32), -(-592 // gb)))
-            nm = max(1, min(ld // 32, -(-296 // rb)))
+            nm = max(1, min(ld // 128, -(-1776 // rb)))
             self.nseg[side] = (nrx, ng, nm)
         mrx = max(self.nseg[0][0] * I, self.nseg[1][0] * J)
         mg = max(self.nseg[0][1] * I, self.nseg[1][1] * J)
@@ -162,14 +164,22 @@ class BNMFEngine:
         self.el8 = f64(8)
         self.m8 = f64(8)
         self.mpart = f64(((I + 127) // 128) * self.nseg[0][2] * 8)
+        self.m8 = f64(8)
         self.nb_terms = 64
         self.elpart = f64(2 * self.nb_terms * 8) if self.vb else None
         self.sterm = None
         self.order_dev = None
         self.alpha_s = None
         self.shard = shard          # set by parallel.ShardedBNMF: (rank, world, row ranges, comm hooks)
-        if dataset.n_obs is not None:
-            self._set_omega(dataset.n_obs)
+        # static sums of the training mask {sum r, sum r^2, |Omega|}: one full-mode metrics pass with zero factors
+        self.statics = f64(3)
+        _lib.call("bnmtf_masked_metrics_f64", _ptr(dataset.R), _ptr(dataset.bits), I, dataset.ldJ, _ptr(self.U.Xp),
+                  _ptr(self.V.Xp), self.K, self.nseg[0][2], 0, _ptr(self.mpart), _ptr(self.m8), _stream())
+        self.statics.copy_(self.m8[4:7])
+        if dataset.n_obs is None:
+            dataset.n_obs = float(self.statics[2].item())
+            self.polarity = 0 if dataset.n_obs >= 0.5 * I * J else 1
+        self._set_omega(dataset.n_obs)
 
     # ---- constants depending on |Omega| ---------------------------------------------------------------
     def _set_omega(self, n_obs):
@@ -229,8 +239,9 @@ class BNMFEngine:
 
     def _metrics_padded(self, bits):
         ds = self.ds
+        statics = _ptr(self.statics) if bits is ds.bits else 0
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(bits), ds.I, ds.ldJ, _ptr(self.U.Xp), _ptr(self.V.Xp),
-                  self.K, self.nseg[0][2], _ptr(self.mpart), _ptr(self.m8), _stream())
+                  self.K, self.nseg[0][2], statics, _ptr(self.mpart), _ptr(self.m8), _stream())
 
     def _vb_terms(self):
         nb = self.nb_terms

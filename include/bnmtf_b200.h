@@ -97,9 +97,12 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
                        const double* scalars, const int* order, int n_order, int apply, double min_tn,
                        uint64_t seed, const uint64_t* iter, uint64_t salt, double* sterm, double* extra, void* stream);
 /* Sums over the set bits of `bits` of {e^2, p, p^2, r p, r, r^2, 1}, p = A_i.B_j  ->  out8 (predict(),
- * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8. */
+ * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8.
+ * statics3 = {sum r, sum r^2, count} of this mask if already known (training mask; selects the lean kernel that
+ * only accumulates e^2, p, p^2), else NULL. */
 int bnmtf_masked_metrics_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Ap,
-                             const double* Bp, int K, int nseg, double* partials, double* out8, void* stream);
+                             const double* Bp, int K, int nseg, const double* statics3, double* partials, double* out8,
+                             void* stream);
 /* Same seven sums for dense contiguous R, P (prediction) and 0/1 (or weight) mask M of n entries each: the
  * compute_MSE / compute_R2 / compute_Rp helpers.  partials: >= nblocks*8 doubles. */
 int bnmtf_dense_metrics_f64(const double* R, const double* P, const double* M, int64_t n, double* partials, int nblocks,
