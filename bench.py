@@ -179,7 +179,7 @@ def main():
 
     if world > 1:
         from bnmtf_b200 import parallel
-        return parallel.bench_sharded(args, rank, world, device, make_synthetic, ClockSampler, measured_peaks)
+        return parallel.bench_sharded(args, rank, world, device, ClockSampler, measured_peaks)
 
     R, bits, n_obs = make_synthetic(I, J, K, device)
     ds = engine.Dataset.from_device(R, bits, I, J, n_obs=n_obs)

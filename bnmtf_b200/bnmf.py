@@ -38,7 +38,7 @@ def _metrics_from_sums(s):
 class _TwoFactorBase(object):
     _mode = None
 
-    def __init__(self, R, M, K, priors, device=None, seed=None):
+    def __init__(self, R, M, K, priors, device=None, seed=None, distributed=False):
         self.R = np.array(R, dtype=float)
         self.M = np.array(M, dtype=float)
         self.K = K
@@ -63,6 +63,7 @@ class _TwoFactorBase(object):
         assert self.lambdaV.shape == (self.J, self.K), "Prior matrix lambdaV has the wrong shape: %s instead of (%s, %s)." % (self.lambdaV.shape, self.J, self.K)
 
         self._device_arg, self._seed, self._eng = device, seed, None
+        self._distributed = distributed   # True: shard rows of R / R^T over the ranks of torch.distributed
         self.verbose = False
 
     @classmethod
@@ -81,6 +82,7 @@ class _TwoFactorBase(object):
         if self.lambdaV.shape == ():
             self.lambdaV = self.lambdaV * np.ones((self.J, self.K))
         self._device_arg, self._seed, self.verbose = dataset.device, seed, False
+        self._distributed = dataset.world > 1
         self._eng = BNMFEngine(dataset, K, cls._mode, self.alpha, self.beta, seed=0 if seed is None else seed)
         return self
 
@@ -96,18 +98,24 @@ class _TwoFactorBase(object):
     def _engine(self):
         if self._eng is None:
             dev = require_cuda(self._device_arg)
-            ds = Dataset.from_host(self.R, self.M, dev)
+            world, rank = 1, 0
+            if self._distributed:
+                import torch.distributed as dist
+                world, rank = dist.get_world_size(), dist.get_rank()
+            ds = Dataset.from_host(self.R, self.M, dev, world, rank)
+            # every rank must use the same Philox seed: draw it from numpy's (seeded) stream or pass seed=
             seed = self._seed if self._seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
             self._eng = BNMFEngine(ds, self.K, self._mode, self.alpha, self.beta, seed=seed)
         return self._eng
 
     @staticmethod
     def _up(dst, src):
-        dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64)), non_blocking=False)
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        dst[:src.shape[0]].copy_(torch.from_numpy(src), non_blocking=False)
 
     @staticmethod
-    def _down(src):
-        return src.detach().cpu().numpy().copy()
+    def _down(src, n=None):
+        return (src if n is None else src[:n]).detach().cpu().numpy().copy()
 
     def _set_scalars(self, eng, kv):
         s = eng.scalars.cpu().numpy()
@@ -215,11 +223,11 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
         self._init_trace_lists()
 
         def keep(it):
-            all_U[it].copy_(eng.U.fac), all_V[it].copy_(eng.V.fac)
+            all_U[it].copy_(eng.U.fac[:self.I]), all_V[it].copy_(eng.V.fac[:self.J])
         tr = self._run_loop(eng, iterations, per_iteration=keep)
         self.all_U, self.all_V = self._down(all_U), self._down(all_V)
         self.all_tau = tr[:, 0].copy()
-        self.U, self.V = self._down(eng.U.fac), self._down(eng.V.fac)
+        self.U, self.V = self._down(eng.U.fac, self.I), self._down(eng.V.fac, self.J)
         if iterations > 0:
             self.tau = float(tr[-1, 0])
         if self.verbose:
@@ -239,7 +247,8 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
         eng.stats(side)
         eng.solve(side, order=[k], apply=False, want_sterm=True, use_iter=False)
         me = eng.U if side == 0 else eng.V
-        return self._down(me.tauf)[:, k], self._down(eng.sterm[:me.n])[:, k]
+        eng.gather_params()
+        return self._down(me.tauf, me.n)[:, k], self._down(eng.sterm, me.n)[:, k]
 
     def tauU(self, k):
         return self._params(0, k)[0]
@@ -318,7 +327,7 @@ class nmf_icm(_TwoFactorBase):
         self._init_trace_lists()
         tr = self._run_loop(eng, iterations, minimum_TN=minimum_TN)
         self.all_tau = tr[:, 0].copy()
-        self.U, self.V = self._down(eng.U.fac), self._down(eng.V.fac)
+        self.U, self.V = self._down(eng.U.fac, self.I), self._down(eng.V.fac, self.J)
         if iterations > 0:
             self.tau = float(tr[-1, 0])
         return
@@ -380,7 +389,7 @@ class bnmf_vb_optimised(_TwoFactorBase):
         for f, s in ((eng.U, 'U'), (eng.V, 'V')):
             for attr, t in (('exp', f.fac), ('var', f.var), ('mu', f.mu), ('tau', f.tauf)):
                 if names is None or attr + s in names:
-                    setattr(self, attr + s, self._down(t))
+                    setattr(self, attr + s, self._down(t, f.n))
 
     def run(self, iterations):
         eng = self._push()
@@ -388,6 +397,7 @@ class bnmf_vb_optimised(_TwoFactorBase):
         tr = self._run_loop(eng, iterations)
         self.all_exp_tau = [float(v) for v in tr[:, 0]]
         self.all_elbo = [float(v) for v in tr[:, 4]]
+        eng.gather_params()
         self._pull(eng)
         if iterations > 0:
             sc = eng.scalars.cpu().numpy()
@@ -425,8 +435,8 @@ class bnmf_vb_optimised(_TwoFactorBase):
         eng.solve(side, order=[k], apply=False, use_iter=False)
         s = 'U' if side == 0 else 'V'
         f = eng.U if side == 0 else eng.V
-        getattr(self, 'tau' + s)[:, k] = self._down(f.tauf)[:, k]
-        getattr(self, 'mu' + s)[:, k] = self._down(f.mu)[:, k]
+        getattr(self, 'tau' + s)[:, k] = self._down(f.tauf, f.n)[:, k]
+        getattr(self, 'mu' + s)[:, k] = self._down(f.mu, f.n)[:, k]
 
     def update_U(self, k):
         self._update_params(0, k)

@@ -159,7 +159,7 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
                        const double* Gpart, const double* SVpart, const double* Gfull, double* fac, double* var,
                        double* mu, double* tauf, const double* lambda, const double* scalars, const int* order,
                        int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
-                       double* sterm, double* extra, void* stream) {
+                       int64_t row_offset, double* sterm, double* extra, void* stream) {
   if (check_k(K)) return -2;
   if (mode < 0 || mode > 2) { set_error("row_solve: bad mode %d", mode); return -2; }
   if (mode == BNMTF_MODE_VB && (!var || !SVpart)) { set_error("row_solve: VB needs var and SVpart"); return -2; }
@@ -169,7 +169,7 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
   a.n_order = n_order; a.apply = apply; a.RXpart = RXpart; a.Gpart = Gpart; a.SVpart = SVpart; a.Gfull = Gfull;
   a.fac = fac; a.var = var; a.mu = mu; a.tauf = tauf; a.lambda = lambda; a.scalars = scalars; a.order = order;
   a.min_tn = min_tn; a.seed = seed; a.iter = reinterpret_cast<const unsigned long long*>(iter); a.salt = salt;
-  a.sterm = sterm; a.extra = extra;
+  a.sterm = sterm; a.extra = extra; a.row_offset = row_offset;
   return launch_row_solve(a, ST(stream));
 }
 

@@ -49,6 +49,7 @@ struct RowSolveArgs {
   double* fac; double* var; double* mu; double* tauf; const double* lambda;
   const double* scalars; const int* order; double min_tn;
   unsigned long long seed; const unsigned long long* iter; unsigned long long salt;
+  long long row_offset;  // global index of local row 0 (row-sharded runs): keeps the Philox stream shard-invariant
   double* sterm;   // optional: the masked-sum term s (rows x K), for the white-box muU()/muV() API
   double* extra;   // optional (VB): per-row sum_k [ var_k (g_kk + sv_k) + u_k^2 sv_k ] for exp_square_diff
 };

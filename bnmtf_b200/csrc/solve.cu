@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
     double val = 0.0, vv = 0.0;
     if (a.apply) {
       if (a.mode == MODE_GIBBS) {
-        Philox rng(a.seed, it * 16ull + a.salt, (unsigned long long)row * K + k);
+        Philox rng(a.seed, it * 16ull + a.salt, (unsigned long long)(a.row_offset + row) * K + k);
         val = tn_draw(mu_k, tau_k, rng);
       } else if (a.mode == MODE_VB) {
         tn_moments(mu_k, tau_k, val, vv);

@@ -1,10 +1,14 @@
 """Device-side state and sweep driver for the two-factor model (R ~ U V^T).
 
-PyTorch is used for exactly three things here: allocating fp64/int32 device buffers, host<->device copies, and
-the current CUDA stream.  Every arithmetic step is a call into libbnmtf_b200.so through ctypes (bnmtf_b200/_lib.py).
-"""
-import math
+PyTorch is used for exactly four things here: allocating fp64/int32 device buffers, host<->device copies, the
+current CUDA stream, and (row-sharded runs) torch.distributed collectives over NCCL.  Every arithmetic step is a
+call into libbnmtf_b200.so through ctypes (bnmtf_b200/_lib.py).
 
+Multi-GPU layout ("dual R / R^T"): rank p owns rows [lo_I, lo_I+cnt_I) of R for the U phase and rows
+[lo_J, lo_J+cnt_J) of R^T for the V phase; U and V are replicated.  Rows are conditionally independent inside a
+phase, so each rank runs the same kernels on its shard and the only exchanges per sweep are an all-gather of the new
+factor rows after each phase and one all-reduce of the metric / ELBO partial sums.
+"""
 import numpy as np
 import torch
 
@@ -22,8 +26,11 @@ def require_cuda(device=None):
     return torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
 
 
-def _ptr(t):
-    return 0 if t is None else t.data_ptr()
+def _ptr(t, row=0):
+    """Device address of tensor t (optionally of its row `row`); 0 for None."""
+    if t is None:
+        return 0
+    return t.data_ptr() + (row * t.stride(0) * t.element_size() if row else 0)
 
 
 def _stream():
@@ -43,41 +50,90 @@ def gram_len(K):
     return nt * (nt + 1) // 2 * 64
 
 
-class Dataset:
-    """R and its observation mask on the device, in both orientations (row phase: I x ld(J); column phase:
-    J x ld(I)), masks as bit words.  Rows [row_lo,row_hi) / columns [col_lo,col_hi) select the shard this rank
-    owns when the matrix is split across GPUs (parallel.py); by default everything."""
+class Partition:
+    """Contiguous equal-size row shards: rank p owns [lo(p), lo(p)+cnt(p)); the last shards may be short or empty."""
 
-    def __init__(self, I, J, device):
+    def __init__(self, n, world=1, rank=0):
+        self.n, self.world, self.rank = int(n), int(world), int(rank)
+        self.S = -(-self.n // self.world)
+        self.n_pad = self.S * self.world
+
+    def lo(self, rank=None):
+        return min(self.n, (self.rank if rank is None else rank) * self.S)
+
+    def cnt(self, rank=None):
+        return max(0, min(self.S, self.n - self.lo(rank)))
+
+
+class Comm:
+    """The two exchanges of a sharded sweep.  world == 1: no-ops."""
+
+    def __init__(self, world=1, rank=0, group=None):
+        self.world, self.rank, self.group = world, rank, group
+
+    def gather_rows(self, full, part):
+        """full: (part.n_pad, ...) tensor whose rows [rank*S, rank*S+S) hold this rank's fresh values -> all ranks'."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        S = part.S
+        mine = full[self.rank * S:(self.rank + 1) * S].clone()
+        dist.all_gather_into_tensor(full[:part.n_pad], mine, group=self.group)
+
+    def allreduce(self, t):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.group)
+
+
+class Dataset:
+    """This rank's shards of R and of its observation mask on the device, in both orientations (row phase:
+    cnt_I x ld(J); column phase: cnt_J x ld(I)), masks as bit words."""
+
+    def __init__(self, I, J, device, world=1, rank=0):
         self.I, self.J, self.device = int(I), int(J), device
         self.ldJ, self.ldI = ld_for(J), ld_for(I)
+        self.partI, self.partJ = Partition(I, world, rank), Partition(J, world, rank)
+        self.world, self.rank = world, rank
         self.R = self.bits = self.RT = self.bitsT = None
-        self.n_obs = None
+        self.n_obs = None          # global |Omega|
+
+    def _pack(self, R, M, rows, cols, ld):
+        out = torch.zeros((max(rows, 1), ld), dtype=torch.float64, device=self.device)
+        bits = torch.zeros((max(rows, 1), ld // 32), dtype=torch.int32, device=self.device)
+        if rows > 0:
+            Rd = torch.from_numpy(np.ascontiguousarray(R, dtype=np.float64)).to(self.device)
+            Md = torch.from_numpy(np.ascontiguousarray(M, dtype=np.float64)).to(self.device)
+            _lib.call("bnmtf_pack_dataset_f64", _ptr(Rd), _ptr(Md), rows, cols, ld, _ptr(out), _ptr(bits), _stream())
+        return out, bits
 
     @classmethod
-    def from_host(cls, R, M, device=None):
+    def from_host(cls, R, M, device=None, world=1, rank=0):
         device = require_cuda(device)
-        R = np.ascontiguousarray(R, dtype=np.float64)
-        M = np.ascontiguousarray(M, dtype=np.float64)
+        R = np.asarray(R, dtype=np.float64)
+        M = np.asarray(M, dtype=np.float64)
         I, J = R.shape
-        ds = cls(I, J, device)
-        Rd = torch.from_numpy(R).to(device)
-        Md = torch.from_numpy(M).to(device)
-        ds.R = torch.empty((I, ds.ldJ), dtype=torch.float64, device=device)
-        ds.bits = torch.empty((I, ds.ldJ // 32), dtype=torch.int32, device=device)
-        _lib.call("bnmtf_pack_dataset_f64", _ptr(Rd), _ptr(Md), I, J, ds.ldJ, _ptr(ds.R), _ptr(ds.bits), _stream())
-        ds._make_transpose()
+        ds = cls(I, J, device, world, rank)
+        lo, cnt = ds.partI.lo(), ds.partI.cnt()
+        ds.R, ds.bits = ds._pack(R[lo:lo + cnt], M[lo:lo + cnt], cnt, J, ds.ldJ)
+        if world == 1:
+            ds._make_transpose()
+        else:
+            lo, cnt = ds.partJ.lo(), ds.partJ.cnt()
+            ds.RT, ds.bitsT = ds._pack(R[:, lo:lo + cnt].T, M[:, lo:lo + cnt].T, cnt, I, ds.ldI)
         ds.n_obs = float(M.sum())
         return ds
 
     @classmethod
-    def from_device(cls, R_padded, bits, I, J, RT_padded=None, bitsT=None, n_obs=None):
-        """Adopt already-resident buffers in the library's layout (synthetic benchmark data is generated
-        directly on the GPU: a 65536 x 32768 fp64 matrix never exists on the host)."""
-        ds = cls(I, J, R_padded.device)
-        assert R_padded.shape == (I, ds.ldJ) and bits.shape == (I, ds.ldJ // 32)
+    def from_device(cls, R_padded, bits, I, J, RT_padded=None, bitsT=None, n_obs=None, world=1, rank=0):
+        """Adopt already-resident shards in the library's layout (synthetic benchmark data is generated directly
+        on the GPU: a 65536 x 32768 fp64 matrix never exists on the host)."""
+        ds = cls(I, J, R_padded.device, world, rank)
+        assert R_padded.shape[1] == ds.ldJ and bits.shape[1] == ds.ldJ // 32
         ds.R, ds.bits = R_padded, bits
         if RT_padded is None:
+            assert world == 1
             ds._make_transpose()
         else:
             ds.RT, ds.bitsT = RT_padded, bitsT
@@ -92,23 +148,23 @@ class Dataset:
                   _ptr(self.RT), _ptr(self.bitsT), self.ldI, _stream())
 
     def pack_mask(self, M):
-        """Bit-pack another I x J 0/1 mask (predict(M_pred))."""
-        Md = torch.from_numpy(np.ascontiguousarray(M, dtype=np.float64)).to(self.device)
-        bits = torch.empty((self.I, self.ldJ // 32), dtype=torch.int32, device=self.device)
-        _lib.call("bnmtf_pack_mask_f64", _ptr(Md), self.I, self.J, self.ldJ, _ptr(bits), _stream())
-        return bits
+        """Bit-pack this rank's rows of another I x J 0/1 mask (predict(M_pred))."""
+        lo, cnt = self.partI.lo(), self.partI.cnt()
+        return self._pack(np.zeros((cnt, self.J)), np.asarray(M, dtype=np.float64)[lo:lo + cnt], cnt, self.J, self.ldJ)[1]
 
 
 class Factor:
-    """One factor matrix (n x K) with its variational / conditional parameters and its padded image."""
+    """One factor matrix (n x K, replicated on every rank) with its variational / conditional parameters and its
+    padded image.  Arrays have part.n_pad rows so that equal-size shards can be all-gathered in place."""
 
-    def __init__(self, n, K, device, vb):
-        self.n, self.K = n, K
-        z = lambda: torch.zeros((n, K), dtype=torch.float64, device=device)
+    def __init__(self, part, K, device, vb):
+        self.part, self.n, self.K = part, part.n, K
+        z = lambda: torch.zeros((part.n_pad, K), dtype=torch.float64, device=device)
         self.fac, self.lam = z(), z()
+        self.lam.fill_(1.0)
         self.mu, self.tauf = z(), z()
         self.var = z() if vb else None
-        self.n_alloc = ld_for(n) + 8
+        self.n_alloc = ld_for(self.n) + 8
         KP = kp_for(K)
         self.Xp = torch.zeros((self.n_alloc, KP), dtype=torch.float64, device=device)
         self.Vp = torch.zeros((self.n_alloc, KP), dtype=torch.float64, device=device) if vb else None
@@ -121,15 +177,16 @@ class Factor:
 class BNMFEngine:
     """All device work of bnmf_gibbs_optimised / bnmf_vb_optimised / nmf_icm for one (R, M, K)."""
 
-    def __init__(self, dataset, K, mode, alpha, beta, seed=0, trace_cap=0, shard=None):
+    def __init__(self, dataset, K, mode, alpha, beta, seed=0, comm=None):
         self.ds, self.K, self.mode = dataset, int(K), mode
         self.m = MODE[mode]
         self.vb = mode == "vb"
         self.alpha, self.beta, self.seed = float(alpha), float(beta), int(seed) & (2 ** 64 - 1)
+        self.comm = comm if comm is not None else Comm(dataset.world, dataset.rank)
         dev = dataset.device
         I, J = dataset.I, dataset.J
-        self.U = Factor(I, K, dev, self.vb)
-        self.V = Factor(J, K, dev, self.vb)
+        self.U = Factor(dataset.partI, K, dev, self.vb)
+        self.V = Factor(dataset.partJ, K, dev, self.vb)
         self.scalars = torch.zeros(16, dtype=torch.float64, device=dev)
         self.iter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.iter_scratch = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -137,48 +194,49 @@ class BNMFEngine:
         self.trace_cap = 0
         self.trace_base = 0         # value of the (never reset) sweep counter when the current trace was allocated
         self.sweeps_done = 0        # host mirror of self.iter; also the Philox stream id, so it only ever grows
-        self.polarity = 0 if dataset.n_obs is None or dataset.n_obs >= 0.5 * I * J else 1
         KP, GL = kp_for(K), gram_len(K)
-        nmax = max(I, J)
-        # segment counts: enough CTAs to fill 148 SMs when the matrix has few rows
+        # local row ranges of the two phases
+        self.loc = {0: (dataset.partI.lo(), dataset.partI.cnt()), 1: (dataset.partJ.lo(), dataset.partJ.cnt())}
+        # CTAs per launch: aim for >= 6 waves of resident CTAs (148 SMs x 3 resp. 2 CTAs) so that the tail wave
+        # costs little; segments are column ranges whose partial results the solver adds up in order
         self.nseg = {}
-        for side, (rows, ld) in enumerate(((I, dataset.ldJ), (J, dataset.ldI))):
-            # CTAs per launch: aim for >= 6 waves of resident CTAs (148 SMs x 3 resp. 2 CTAs) so that the tail
-            # wave costs little; segments are column ranges whose partial results the solver adds up in order
+        for side, ld in ((0, dataset.ldJ), (1, dataset.ldI)):
+            rows = max(1, self.loc[side][1])
             rb = (rows + 127) // 128
             nrx = max(1, min(ld // 128, -(-2664 // rb)))
             gb = (rows + 7) // 8
             ng = max(1, min(-(-(ld // 32) // 32), -(-592 // gb)))
             nm = max(1, min(ld // 128, -(-1776 // rb)))
             self.nseg[side] = (nrx, ng, nm)
-        mrx = max(self.nseg[0][0] * I, self.nseg[1][0] * J)
-        mg = max(self.nseg[0][1] * I, self.nseg[1][1] * J)
+        rI, rJ = max(1, self.loc[0][1]), max(1, self.loc[1][1])
+        mrx = max(self.nseg[0][0] * rI, self.nseg[1][0] * rJ)
+        mg = max(self.nseg[0][1] * rI, self.nseg[1][1] * rJ)
         f64 = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
         self.RXpart = f64(mrx, KP)
         self.Gpart = f64(mg, GL)
         self.SVpart = f64(mg, KP) if self.vb else None
         self.Gfull = f64(GL + KP)
         self.gscratch = f64(64 * (GL + KP))
-        self.extra = f64(nmax) if self.vb else None
-        self.ex1 = f64(1)
-        self.el8 = f64(8)
-        self.m8 = f64(8)
-        self.mpart = f64(((I + 127) // 128) * self.nseg[0][2] * 8)
-        self.m8 = f64(8)
+        self.extra = f64(max(rI, rJ)) if self.vb else None
+        self.red = f64(24)          # [0:8] metric sums, [8:16] factor ELBO terms, [16] VB extra term
+        self.m8, self.el8, self.ex1 = self.red[0:8], self.red[8:16], self.red[16:17]
+        self.mpart = f64(((rI + 127) // 128) * self.nseg[0][2] * 8)
         self.nb_terms = 64
         self.elpart = f64(2 * self.nb_terms * 8) if self.vb else None
         self.sterm = None
         self.order_dev = None
-        self.alpha_s = None
-        self.shard = shard          # set by parallel.ShardedBNMF: (rank, world, row ranges, comm hooks)
-        # static sums of the training mask {sum r, sum r^2, |Omega|}: one full-mode metrics pass with zero factors
+        # static sums of the training mask {sum r, sum r^2, |Omega|} over THIS rank's rows: one full-mode pass, p = 0
         self.statics = f64(3)
-        _lib.call("bnmtf_masked_metrics_f64", _ptr(dataset.R), _ptr(dataset.bits), I, dataset.ldJ, _ptr(self.U.Xp),
-                  _ptr(self.V.Xp), self.K, self.nseg[0][2], 0, _ptr(self.mpart), _ptr(self.m8), _stream())
-        self.statics.copy_(self.m8[4:7])
+        if self.loc[0][1] > 0:
+            _lib.call("bnmtf_masked_metrics_f64", _ptr(dataset.R), _ptr(dataset.bits), self.loc[0][1], dataset.ldJ,
+                      _ptr(self.U.Xp), _ptr(self.V.Xp), self.K, self.nseg[0][2], 0, _ptr(self.mpart), _ptr(self.m8),
+                      _stream())
+            self.statics.copy_(self.m8[4:7])
         if dataset.n_obs is None:
-            dataset.n_obs = float(self.statics[2].item())
-            self.polarity = 0 if dataset.n_obs >= 0.5 * I * J else 1
+            tot = self.statics[2:3].clone()
+            self.comm.allreduce(tot)
+            dataset.n_obs = float(tot.item())
+        self.polarity = 0 if dataset.n_obs >= 0.5 * I * J else 1
         self._set_omega(dataset.n_obs)
 
     # ---- constants depending on |Omega| ---------------------------------------------------------------
@@ -193,15 +251,19 @@ class BNMFEngine:
     # ---- pieces ---------------------------------------------------------------------------------------
     def _sides(self, side):
         ds = self.ds
+        lo, cnt = self.loc[side]
         if side == 0:
-            return self.U, self.V, ds.R, ds.bits, ds.I, ds.ldJ
-        return self.V, self.U, ds.RT, ds.bitsT, ds.J, ds.ldI
+            return self.U, self.V, ds.R, ds.bits, cnt, ds.ldJ, lo
+        return self.V, self.U, ds.RT, ds.bitsT, cnt, ds.ldI, lo
 
     def stats(self, side, need_rx=True):
-        """Layer-1 passes for one phase: statistics of the rows of R (side 0) / R^T (side 1) w.r.t. the other factor."""
-        me, other, R, bits, rows, ld = self._sides(side)
+        """Layer-1 passes for one phase: statistics of this rank's rows of R (side 0) / R^T (side 1) w.r.t. the
+        other factor."""
+        me, other, R, bits, rows, ld, lo = self._sides(side)
         nrx, ng, _ = self.nseg[side]
         other.pad()
+        if rows == 0:
+            return
         if self.polarity == 0:
             _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
                       _ptr(self.Gfull), _ptr(self.gscratch), _stream())
@@ -212,8 +274,8 @@ class BNMFEngine:
                   self.polarity, ng, _ptr(self.Gpart), _ptr(self.SVpart), _stream())
 
     def solve(self, side, order=None, n_order=None, apply=True, minimum_TN=0.0, want_sterm=False, want_extra=False,
-              use_iter=True):
-        me, other, R, bits, rows, ld = self._sides(side)
+              use_iter=True, gather=True):
+        me, other, R, bits, rows, ld, lo = self._sides(side)
         nrx, ng, _ = self.nseg[side]
         order_ptr = 0
         if order is not None:
@@ -221,34 +283,67 @@ class BNMFEngine:
             order_ptr, n_order = _ptr(self.order_dev), len(order)
         elif n_order is None:
             n_order = self.K
-        if want_sterm and (self.sterm is None or self.sterm.shape[0] < rows):
-            self.sterm = torch.zeros((max(self.ds.I, self.ds.J), self.K), dtype=torch.float64, device=self.ds.device)
-        _lib.call("bnmf_row_solve_f64", self.m, rows, self.K, nrx, ng, self.polarity,
-                  _ptr(self.RXpart), _ptr(self.Gpart), _ptr(self.SVpart), _ptr(self.Gfull),
-                  _ptr(me.fac), _ptr(me.var), _ptr(me.mu), _ptr(me.tauf), _ptr(me.lam),
-                  _ptr(self.scalars), order_ptr, n_order, 1 if apply else 0, float(minimum_TN),
-                  self.seed, _ptr(self.iter if use_iter else self.iter_scratch), side,
-                  _ptr(self.sterm) if want_sterm else 0, _ptr(self.extra) if want_extra else 0, _stream())
+        if want_sterm and self.sterm is None:
+            self.sterm = torch.zeros((max(self.U.part.n_pad, self.V.part.n_pad), self.K), dtype=torch.float64,
+                                     device=self.ds.device)
+        if rows > 0:
+            _lib.call("bnmf_row_solve_f64", self.m, rows, self.K, nrx, ng, self.polarity,
+                      _ptr(self.RXpart), _ptr(self.Gpart), _ptr(self.SVpart), _ptr(self.Gfull),
+                      _ptr(me.fac, lo), _ptr(me.var, lo), _ptr(me.mu, lo), _ptr(me.tauf, lo), _ptr(me.lam, lo),
+                      _ptr(self.scalars), order_ptr, n_order, 1 if apply else 0, float(minimum_TN),
+                      self.seed, _ptr(self.iter if use_iter else self.iter_scratch), side, lo,
+                      _ptr(self.sterm, lo) if want_sterm else 0, _ptr(self.extra) if want_extra else 0, _stream())
+        if gather and self.comm.world > 1:
+            if apply:
+                self.comm.gather_rows(me.fac, me.part)
+                if self.vb:
+                    self.comm.gather_rows(me.var, me.part)
+            else:
+                self.comm.gather_rows(me.mu, me.part), self.comm.gather_rows(me.tauf, me.part)
+                if want_sterm:
+                    self.comm.gather_rows(self.sterm, me.part)
+
+    def gather_params(self):
+        """mu / tau of both factors are only exchanged when the host asks for them (end of run())."""
+        if self.comm.world > 1:
+            for f in (self.U, self.V):
+                self.comm.gather_rows(f.mu, f.part), self.comm.gather_rows(f.tauf, f.part)
 
     def metrics(self, bits=None):
-        """Masked sums over `bits` (default: the training mask) with the current factors -> self.m8."""
-        ds = self.ds
+        """Masked sums over `bits` (default: the training mask) with the current factors -> self.m8 (global)."""
         self.U.pad()
         self.V.pad()
-        self._metrics_padded(ds.bits if bits is None else bits)
+        self._metrics_padded(self.ds.bits if bits is None else bits)
+        self.comm.allreduce(self.m8)
 
     def _metrics_padded(self, bits):
+        """Local partial sums over this rank's rows of R -> self.m8 (not yet all-reduced)."""
         ds = self.ds
+        lo, rows = self.loc[0]
+        if rows == 0:
+            self.m8.zero_()
+            return
         statics = _ptr(self.statics) if bits is ds.bits else 0
-        _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(bits), ds.I, ds.ldJ, _ptr(self.U.Xp), _ptr(self.V.Xp),
+        _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(bits), rows, ds.ldJ, _ptr(self.U.Xp, lo), _ptr(self.V.Xp),
                   self.K, self.nseg[0][2], statics, _ptr(self.mpart), _ptr(self.m8), _stream())
 
     def _vb_terms(self):
+        """Local partial sums of the factor-side ELBO terms over this rank's rows of U and V -> self.el8."""
         nb = self.nb_terms
+        self.elpart.zero_()
         for i, f in enumerate((self.U, self.V)):
-            _lib.call("bnmtf_vb_factor_terms_f64", _ptr(f.fac), _ptr(f.var), _ptr(f.mu), _ptr(f.tauf), _ptr(f.lam),
-                      f.n * f.K, self.elpart[i * nb * 8:].data_ptr(), nb, _stream())
+            lo, cnt = self.loc[i]
+            if cnt > 0:
+                _lib.call("bnmtf_vb_factor_terms_f64", _ptr(f.fac, lo), _ptr(f.var, lo), _ptr(f.mu, lo), _ptr(f.tauf, lo),
+                          _ptr(f.lam, lo), cnt * f.K, self.elpart[i * nb * 8:].data_ptr(), nb, _stream())
         _lib.call("bnmtf_reduce8_f64", _ptr(self.elpart), 2 * nb, _ptr(self.el8), _stream())
+
+    def _vb_extra(self):
+        rows = self.loc[1][1]
+        if rows > 0:
+            _lib.call("bnmtf_reduce1_f64", _ptr(self.extra), rows, _ptr(self.ex1), _stream())
+        else:
+            self.ex1.zero_()
 
     def finish(self, update_tau=True, record=True):
         # the kernel writes trace row number *iter; rebase the pointer so that row trace_base is row 0
@@ -263,12 +358,16 @@ class BNMFEngine:
     def refresh_scalars(self, update_tau=True):
         """Recompute metrics / exp_square_diff / ELBO (and optionally tau) for the CURRENT state without advancing
         the sweep counter: initialise(), exp_square_diff(), elbo(), quality() of the white-box API."""
+        self.red.zero_()
         if self.vb:
             self.stats(1, need_rx=False)
-            self.solve(1, n_order=0, apply=False, want_extra=True, use_iter=False)
-            _lib.call("bnmtf_reduce1_f64", _ptr(self.extra), self.ds.J, _ptr(self.ex1), _stream())
+            self.solve(1, n_order=0, apply=False, want_extra=True, use_iter=False, gather=False)
+            self._vb_extra()
             self._vb_terms()
-        self.metrics()
+        self.U.pad()
+        self.V.pad()
+        self._metrics_padded(self.ds.bits)
+        self.comm.allreduce(self.red)
         self.finish(update_tau=update_tau, record=False)
 
     # ---- the sweep ------------------------------------------------------------------------------------
@@ -281,8 +380,9 @@ class BNMFEngine:
         self.V.pad()                      # U's padded image is current (made for the column phase)
         self._metrics_padded(self.ds.bits)
         if self.vb:
-            _lib.call("bnmtf_reduce1_f64", _ptr(self.extra), self.ds.J, _ptr(self.ex1), _stream())
+            self._vb_extra()
             self._vb_terms()
+        self.comm.allreduce(self.red)     # one exchange for metric sums, ELBO terms and the VB extra term
         self.finish(update_tau=True, record=True)
 
     def profile_sweep(self, reps=3):
@@ -302,7 +402,7 @@ class BNMFEngine:
             count[name] += 1
         for _ in range(reps):
             for side in (0, 1):
-                me, other, R, bits, rows, ld = self._sides(side)
+                me, other, R, bits, rows, ld, lo = self._sides(side)
                 nrx, ng, _ = self.nseg[side]
                 other.pad()
                 if self.polarity == 0:
@@ -313,12 +413,14 @@ class BNMFEngine:
                 timed("stats_gram", lambda: _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp),
                                                       _ptr(other.Vp), self.K, self.polarity, ng, _ptr(self.Gpart),
                                                       _ptr(self.SVpart), _stream()))
-                timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1))
+                timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1, gather=False))
+                self.solve(side, n_order=0, apply=True, gather=True)   # exchange only (no column is updated)
             self.V.pad()
             timed("masked_metrics", lambda: self._metrics_padded(self.ds.bits))
             if self.vb:
-                _lib.call("bnmtf_reduce1_f64", _ptr(self.extra), self.ds.J, _ptr(self.ex1), _stream())
+                self._vb_extra()
                 self._vb_terms()
+            self.comm.allreduce(self.red)
             self.finish(update_tau=True, record=False)
         return {n: acc[n] / max(1, count[n]) for n in names}
 

@@ -90,12 +90,14 @@ int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t 
  *   fac,var       : n x K, updated in place when apply (var only for VB)
  *   mu,tauf,sterm : optional n x K outputs (conditional mean, precision, masked-sum term)
  *   extra         : optional rows doubles (VB): this row's share of exp_square_diff's variance term
- *   iter,salt,seed: Philox stream = (*iter)*16 + salt; index = row*K + k */
+ *   iter,salt,seed: Philox stream = (*iter)*16 + salt; index = (row_offset+row)*K + k
+ *   row_offset    : global index of row 0 of the arrays passed (0 unless the rows are sharded across GPUs) */
 int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, int polarity,
                        const double* RXpart, const double* Gpart, const double* SVpart, const double* Gfull,
                        double* fac, double* var, double* mu, double* tauf, const double* lambda,
                        const double* scalars, const int* order, int n_order, int apply, double min_tn,
-                       uint64_t seed, const uint64_t* iter, uint64_t salt, double* sterm, double* extra, void* stream);
+                       uint64_t seed, const uint64_t* iter, uint64_t salt, int64_t row_offset, double* sterm,
+                       double* extra, void* stream);
 /* Sums over the set bits of `bits` of {e^2, p, p^2, r p, r, r^2, 1}, p = A_i.B_j  ->  out8 (predict(),
  * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8.
  * statics3 = {sum r, sum r^2, count} of this mask if already known (training mask; selects the lean kernel that
