@@ -40,6 +40,12 @@ int launch_gamma_draw(double, double, long long, unsigned long long, unsigned lo
 int launch_exponential_draw(const double*, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
 
 int launch_row_solve(const RowSolveArgs&, cudaStream_t);
+int launch_np_build_pred(const double*, const double*, int, int, int, int, double*, cudaStream_t);
+int launch_np_row_update(const double*, const uint32_t*, double*, int, int, int, double*, const double*, int, cudaStream_t);
+int launch_np_s_update(const double*, const uint32_t*, double*, int, int, int, const double*, int, int, const double*, int,
+                       int, double*, double*, int, cudaStream_t);
+int launch_np_metrics(const double*, const uint32_t*, const double*, int, int, int, double*, int, cudaStream_t);
+int launch_small_matmul(const double*, const double*, int, int, int, int, double*, cudaStream_t);
 
 int launch_finish(const FinishArgs&, cudaStream_t);
 
@@ -209,6 +215,30 @@ int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_al
   a.seed = seed; a.update_tau = update_tau;
   if (mode == BNMTF_MODE_VB && (!ex1 || !el8)) { set_error("finish_sweep: VB needs ex1 and el8"); return -2; }
   return launch_finish(a, ST(stream));
+}
+
+int bnmtf_np_build_pred_f64(const double* A, const double* B, int64_t rows, int64_t cols, int64_t ld, int K, double* P,
+                            void* stream) {
+  return launch_np_build_pred(A, B, (int)rows, (int)cols, (int)ld, K, P, ST(stream));
+}
+int bnmtf_np_row_update_f64(const double* R, const uint32_t* bits, double* P, int64_t rows, int64_t cols, int64_t ld,
+                            double* A, const double* B, int K, void* stream) {
+  return launch_np_row_update(R, bits, P, (int)rows, (int)cols, (int)ld, A, B, K, ST(stream));
+}
+int bnmtf_np_s_update_f64(const double* R, const uint32_t* bits, double* P, int64_t rows, int64_t cols, int64_t ld,
+                          const double* F, int K, int k, const double* G, int L, int l, double* S, double* partials,
+                          int nparts, void* stream) {
+  if (nparts < 1) { set_error("np_s_update: nparts < 1"); return -2; }
+  return launch_np_s_update(R, bits, P, (int)rows, (int)cols, (int)ld, F, K, k, G, L, l, S, partials, nparts, ST(stream));
+}
+int bnmtf_np_metrics_f64(const double* R, const uint32_t* bits, const double* P, int64_t rows, int64_t cols, int64_t ld,
+                         double* partials, int nparts, double* out8, void* stream) {
+  int rc = launch_np_metrics(R, bits, P, (int)rows, (int)cols, (int)ld, partials, nparts, ST(stream));
+  if (rc) return rc;
+  return launch_reduce8(partials, nparts, out8, ST(stream));
+}
+int bnmtf_small_matmul_f64(const double* A, const double* B, int64_t n, int p, int q, int transB, double* C, void* stream) {
+  return launch_small_matmul(A, B, (int)n, p, q, transB, C, ST(stream));
 }
 
 int bnmtf_tn_moments_f64(const double* mu, const double* tau, int64_t n, double* ex, double* var, void* stream) {

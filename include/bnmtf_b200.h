@@ -119,6 +119,25 @@ int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_al
                           const double* el8, double* scalars, double* trace, uint64_t* iter, int trace_cap,
                           uint64_t seed, int update_tau, void* stream);
 
+/* ---- non-probabilistic multiplicative updates (nmf_np.py:114-118, nmtf_np.py:155-174) ------------------------ */
+/* P (rows x ld scratch) = A B^T with A rows x K, B cols x K; padding columns of P are set to 1. */
+int bnmtf_np_build_pred_f64(const double* A, const double* B, int64_t rows, int64_t cols, int64_t ld, int K, double* P,
+                            void* stream);
+/* for every row: for k = 0..K-1: A_ik *= sum_j m r/p B_jk / sum_j m B_jk, P kept current (NMF.update_U/V;
+ * NMTF.update_F/G with B = G S^T resp. F S). */
+int bnmtf_np_row_update_f64(const double* R, const uint32_t* bits, double* P, int64_t rows, int64_t cols, int64_t ld,
+                            double* A, const double* B, int K, void* stream);
+/* NMTF.update_S(k,l) on P = F S G^T; partials: >= 2*nparts + 1 doubles of scratch. */
+int bnmtf_np_s_update_f64(const double* R, const uint32_t* bits, double* P, int64_t rows, int64_t cols, int64_t ld,
+                          const double* F, int K, int k, const double* G, int L, int l, double* S, double* partials,
+                          int nparts, void* stream);
+/* out8 = sums over observed entries of {e^2, p, p^2, r p, r, r^2, 1, r log(r/p) - r + p} for an explicit P
+ * (predict / compute_I_div, nmf_np.py:122-148).  partials: >= 8*nparts doubles. */
+int bnmtf_np_metrics_f64(const double* R, const uint32_t* bits, const double* P, int64_t rows, int64_t cols, int64_t ld,
+                         double* partials, int nparts, double* out8, void* stream);
+/* C (n x q) = A (n x p) B (p x q), or A B^T with B (q x p) when transB: factor-sized products (S G^T, F S, ...). */
+int bnmtf_small_matmul_f64(const double* A, const double* B, int64_t n, int p, int q, int transB, double* C, void* stream);
+
 /* ---- distributions (code/models/distributions/*.py) ---------------------------------------------------- */
 int bnmtf_tn_moments_f64(const double* mu, const double* tau, int64_t n, double* ex, double* var, void* stream);
 int bnmtf_tn_draw_f64(const double* mu, const double* tau, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
