@@ -30,6 +30,10 @@ SIGNATURES = {
     "bnmtf_reduce8_f64": [c_p, c_i, c_p, c_p],
     "bnmtf_reduce1_f64": [c_p, c_i64, c_p, c_p],
     "bnmf_finish_sweep_f64": [c_i, c_d, c_d, c_d, c_d, c_d, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_u64, c_i, c_p],
+    "bnmtf_nmtf_transform_f64": [c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "bnmtf_nmtf_sq_f64": [c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
+    "bnmtf_coord_solve_f64": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_u64, c_p, c_u64, c_p],
+    "bnmtf_nmtf_extra_f64": [c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "bnmtf_np_build_pred_f64": [c_p, c_p, c_i64, c_i64, c_i64, c_i, c_p, c_p],
     "bnmtf_np_row_update_f64": [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i, c_p],
     "bnmtf_np_s_update_f64": [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p],
@@ -52,7 +56,8 @@ KERNELS_PER_CALL = {"bnmtf_pack_dataset_f64": 1, "bnmtf_pack_mask_f64": 1, "bnmt
                     "bnmtf_dense_metrics_f64": 2, "bnmtf_vb_factor_terms_f64": 1, "bnmtf_reduce8_f64": 1,
                     "bnmtf_reduce1_f64": 1, "bnmf_finish_sweep_f64": 1, "bnmtf_tn_moments_f64": 1, "bnmtf_np_build_pred_f64": 1,
                     "bnmtf_np_row_update_f64": 1, "bnmtf_np_s_update_f64": 2, "bnmtf_np_metrics_f64": 2,
-                    "bnmtf_small_matmul_f64": 1,
+                    "bnmtf_small_matmul_f64": 1, "bnmtf_nmtf_transform_f64": 1, "bnmtf_nmtf_sq_f64": 2,
+                    "bnmtf_coord_solve_f64": 1, "bnmtf_nmtf_extra_f64": 1,
                     "bnmtf_tn_draw_f64": 1, "bnmtf_gamma_draw_f64": 1, "bnmtf_exponential_draw_f64": 1}
 launch_count = [0]
 

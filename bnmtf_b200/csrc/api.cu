@@ -46,6 +46,10 @@ int launch_np_s_update(const double*, const uint32_t*, double*, int, int, int, c
                        int, double*, double*, int, cudaStream_t);
 int launch_np_metrics(const double*, const uint32_t*, const double*, int, int, int, double*, int, cudaStream_t);
 int launch_small_matmul(const double*, const double*, int, int, int, int, double*, cudaStream_t);
+int launch_nmtf_transform(const TransformArgs&, cudaStream_t);
+int launch_nmtf_sq(const SqArgs&, int, double*, cudaStream_t);
+int launch_coord_solve(const CoordArgs&, cudaStream_t);
+int launch_nmtf_extra(const ExtraArgs&, cudaStream_t);
 
 int launch_finish(const FinishArgs&, cudaStream_t);
 
@@ -239,6 +243,47 @@ int bnmtf_np_metrics_f64(const double* R, const uint32_t* bits, const double* P,
 }
 int bnmtf_small_matmul_f64(const double* A, const double* B, int64_t n, int p, int q, int transB, double* C, void* stream) {
   return launch_small_matmul(A, B, (int)n, p, q, transB, C, ST(stream));
+}
+
+int bnmtf_nmtf_transform_f64(int64_t rows, int Ks, int Lo, int polarity, int vb, const double* RXo, const double* Go,
+                             const double* SVo, const double* Gfull_o, const double* Smat, const double* varS,
+                             double* RXs, double* Gs, double* SVs, void* stream) {
+  if (check_k(Ks) || check_k(Lo)) return -2;
+  if (vb && (!SVo || !varS || !SVs)) { set_error("nmtf_transform: VB needs SVo, varS, SVs"); return -2; }
+  TransformArgs a;
+  a.rows = (int)rows; a.Ks = Ks; a.Lo = Lo; a.polarity = polarity; a.vb = vb; a.RXo = RXo; a.Go = Go; a.SVo = SVo;
+  a.Gfull_o = Gfull_o; a.Smat = Smat; a.varS = varS; a.RXs = RXs; a.Gs = Gs; a.SVs = SVs;
+  return launch_nmtf_transform(a, ST(stream));
+}
+int bnmtf_nmtf_sq_f64(int64_t rows, int K, int L, int polarity, int vb, const double* RXo, const double* Go,
+                      const double* SVo, const double* Gfull_o, const double* F, const double* varF, double* partial,
+                      int nparts, double* out, void* stream) {
+  if (check_k(K) || check_k(L)) return -2;
+  SqArgs a;
+  a.rows = (int)rows; a.K = K; a.L = L; a.polarity = polarity; a.vb = vb; a.RXo = RXo; a.Go = Go; a.SVo = SVo;
+  a.Gfull_o = Gfull_o; a.F = F; a.varF = varF; a.partial = partial;
+  return launch_nmtf_sq(a, nparts, out, ST(stream));
+}
+int bnmtf_coord_solve_f64(int mode, int D, const double* H, const double* prec, const double* rhs, const double* lambda,
+                          double* x, double* var, double* mu, double* tauf, const double* scalars, const int* order,
+                          int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
+                          void* stream) {
+  if (D < 1 || D > 4096) { set_error("coord_solve: D=%d out of range", D); return -2; }
+  if (mode == BNMTF_MODE_VB && !var) { set_error("coord_solve: VB needs var"); return -2; }
+  CoordArgs a;
+  a.mode = mode; a.D = D; a.n_order = n_order; a.apply = apply; a.H = H; a.prec = prec; a.rhs = rhs; a.lambda = lambda;
+  a.x = x; a.var = var; a.mu = mu; a.tauf = tauf; a.scalars = scalars; a.order = order; a.min_tn = min_tn; a.seed = seed;
+  a.iter = reinterpret_cast<const unsigned long long*>(iter); a.salt = salt;
+  return launch_coord_solve(a, ST(stream));
+}
+int bnmtf_nmtf_extra_f64(int64_t rows, int K, int L, int polarity, const double* Go, const double* SVo,
+                         const double* Gfull_o, const double* G, const double* varG, const double* S, const double* varS,
+                         double* extra, void* stream) {
+  if (check_k(K) || check_k(L)) return -2;
+  ExtraArgs a;
+  a.rows = (int)rows; a.K = K; a.L = L; a.polarity = polarity; a.Go = Go; a.SVo = SVo; a.Gfull_o = Gfull_o; a.G = G;
+  a.varG = varG; a.S = S; a.varS = varS; a.extra = extra;
+  return launch_nmtf_extra(a, ST(stream));
 }
 
 int bnmtf_tn_moments_f64(const double* mu, const double* tau, int64_t n, double* ex, double* var, void* stream) {

@@ -61,6 +61,37 @@ struct FinishArgs {
   unsigned long long seed; int update_tau;
 };
 
+// ---- tri-factorisation argument blocks (nmtf.cu) ----------------------------------------------------------
+struct TransformArgs {
+  int rows, Ks, Lo, polarity, vb;
+  const double* RXo; const double* Go; const double* SVo; const double* Gfull_o;   // statistics w.r.t. the other factor
+  const double* Smat; const double* varS;                                           // Ks x Lo
+  double* RXs; double* Gs; double* SVs;                                             // outputs, self dimension
+};
+
+struct SqArgs {
+  int rows, K, L, polarity, vb;
+  const double* RXo; const double* Go; const double* SVo; const double* Gfull_o;   // row statistics w.r.t. G
+  const double* F; const double* varF;                                              // rows x K
+  double* partial;                                                                  // gridDim.x x (D*D + 2D)
+};
+
+struct CoordArgs {
+  int mode, D, n_order, apply;
+  const double* H; const double* prec; const double* rhs; const double* lambda;
+  double* x; double* var; double* mu; double* tauf;
+  const double* scalars; const int* order; double min_tn;
+  unsigned long long seed; const unsigned long long* iter; unsigned long long salt;
+};
+
+struct ExtraArgs {
+  int rows, K, L, polarity;
+  const double* Go; const double* SVo; const double* Gfull_o;     // column statistics w.r.t. F (dimension K)
+  const double* G; const double* varG;                            // rows x L
+  const double* S; const double* varS;                            // K x L
+  double* extra;                                                  // rows
+};
+
 #ifdef __CUDACC__
 // fp64 tensor-pipe MMA: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l>>2][l&3], B[l&3][l>>2],
 // and C[l>>2][2*(l&3) + {0,1}].  On B200 this runs at the full fp64 rate (measured 37.1 TFLOP/s) while each

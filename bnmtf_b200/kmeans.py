@@ -1,0 +1,110 @@
+"""K-means with missing values, used for init_FG='kmeans' (host-side port of the behaviour of
+code/models/kmeans/kmeans.py:6-205; one-off initialisation, outside the update sweep -- SURVEY.md section 8f #2).
+
+Semantics kept: centroids drawn with python's `random.uniform` between the per-coordinate min and max of the
+observed values (same call order, so a seeded run picks the same centroids); distance = mean squared difference
+over the coordinates observed in both the point and the centroid (None / infinite when there is no overlap, ties go
+to the lowest cluster index); centroid = per-coordinate mean of the observed values of its points (coordinate masked
+out when none is observed); an empty cluster takes the point currently furthest from its centroid ('singleton');
+stop when no assignment changes or after 200 iterations; result = one-hot assignment matrix.
+"""
+import random
+
+import numpy as np
+
+MAX_ITERATIONS = 200
+
+
+class KMeans(object):
+    def __init__(self, X, M, K, resolve_empty='singleton'):
+        self.X = np.array(X, dtype=float)
+        self.M = np.array(M, dtype=float)
+        self.K = K
+        self.resolve_empty = resolve_empty
+        assert len(self.X.shape) == 2, "Input matrix X is not a two-dimensional array, but instead %s-dimensional." % len(self.X.shape)
+        assert self.X.shape == self.M.shape, "Input matrix X is not of the same size as the indicator matrix M: %s and %s respectively." % (self.X.shape, self.M.shape)
+        assert self.K > 0, "K should be greater than 0."
+        (self.no_points, self.no_coordinates) = self.X.shape
+        self.no_unique_points = len(set(tuple(row) for row in self.X.tolist()))
+        for i, c in enumerate(self.M.sum(axis=1)):
+            assert c != 0, "Fully unobserved row in X, row %s." % i
+        keep = self.M.sum(axis=0) != 0
+        if not keep.all():
+            self.X, self.M = self.X[:, keep], self.M[:, keep]
+            self.no_coordinates = self.X.shape[1]
+        self.distances = np.zeros(self.no_points)
+
+    def initialise(self, seed=None):
+        if seed is not None:
+            random.seed(seed)
+        obs = self.M != 0
+        self.mins = [self.X[obs[:, j], j].min() for j in range(self.no_coordinates)]
+        self.maxs = [self.X[obs[:, j], j].max() for j in range(self.no_coordinates)]
+        self.centroids = np.array([self.random_cluster_centroid() for _ in range(self.K)], dtype=float)
+        self.cluster_assignments = np.full(self.no_points, -1, dtype=int)
+        self.mask_centroids = np.ones((self.K, self.no_coordinates))
+
+    def random_cluster_centroid(self):
+        return [random.uniform(self.mins[c], self.maxs[c]) for c in range(self.no_coordinates)]
+
+    def cluster(self):
+        iteration = 1
+        change = True
+        while change:
+            iteration += 1
+            change = self.assignment()
+            self.update()
+            if iteration >= MAX_ITERATIONS:
+                break
+        self.create_matrix()
+
+    def _all_distances(self):
+        """no_points x K matrix of masked mean squared differences (inf where nothing overlaps)."""
+        both = self.M[:, None, :] * self.mask_centroids[None, :, :]
+        overlap = both.sum(axis=2)
+        sq = (both * (self.X[:, None, :] - self.centroids[None, :, :]) ** 2).sum(axis=2)
+        with np.errstate(all='ignore'):
+            return np.where(overlap > 0, sq / overlap, np.inf)
+
+    def assignment(self):
+        dist = self._all_distances()
+        new = dist.argmin(axis=1)                       # first minimum = lowest index on ties
+        best = dist[np.arange(self.no_points), new]
+        self.distances = np.where(np.isfinite(best), best, 0.0)
+        change = bool((new != self.cluster_assignments).any())
+        self.cluster_assignments = new
+        self.data_point_assignments = [list(np.nonzero(new == c)[0]) for c in range(self.K)]
+        return change
+
+    def update(self):
+        for c in range(self.K):
+            self.update_cluster(c)
+
+    def update_cluster(self, c):
+        members = self.data_point_assignments[c]
+        if len(members) == 0:
+            if self.no_unique_points >= self.K:
+                if self.resolve_empty == 'singleton':
+                    far = int(self.distances.argmax())
+                    old = int(self.cluster_assignments[far])
+                    self.centroids[c] = self.X[far]
+                    self.mask_centroids[c] = self.M[far]
+                    self.distances[far] = 0.0
+                    self.cluster_assignments[far] = c
+                    self.data_point_assignments[c] = [far]
+                    self.data_point_assignments[old].remove(far)
+                    self.update_cluster(old)
+                else:
+                    self.centroids[c] = self.random_cluster_centroid()
+                    self.mask_centroids[c] = np.ones(self.no_coordinates)
+            return
+        Xc, Mc = self.X[members], self.M[members]
+        counts = Mc.sum(axis=0)
+        with np.errstate(all='ignore'):
+            means = np.where(counts > 0, (Mc * Xc).sum(axis=0) / counts, 0.0)
+        self.centroids[c] = means
+        self.mask_centroids[c] = (counts > 0).astype(float)
+
+    def create_matrix(self):
+        self.clustering_results = np.zeros((self.no_points, self.K))
+        self.clustering_results[np.arange(self.no_points), self.cluster_assignments] = 1

@@ -119,6 +119,31 @@ int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_al
                           const double* el8, double* scalars, double* trace, uint64_t* iter, int trace_cap,
                           uint64_t seed, int update_tau, void* stream);
 
+/* ---- layer 2: tri-factorisation R ~ F S G^T (bnmtf_gibbs_optimised.py, bnmtf_vb_optimised.py, nmtf_icm.py) ---- */
+/* Row statistics w.r.t. the OTHER outer factor (dimension Lo, one segment: RXo rows x KPo, Go rows x gram_len(Lo),
+ * SVo rows x KPo, Gfull_o) -> statistics of the effective factor X = other * Smat^T (dimension Ks) in the layout
+ * bnmf_row_solve_f64 consumes with nseg 1, polarity 1.  Smat is Ks x Lo (S for the F phase, S^T for the G phase).
+ * Replaces tauF/muF, tauG/muG (bnmtf_gibbs_optimised.py:195-211) and update_F/update_G (bnmtf_vb_optimised.py:245-280). */
+int bnmtf_nmtf_transform_f64(int64_t rows, int Ks, int Lo, int polarity, int vb, const double* RXo, const double* Go,
+                             const double* SVo, const double* Gfull_o, const double* Smat, const double* varS,
+                             double* RXs, double* Gs, double* SVs, void* stream);
+/* Reduction over rows for the S phase: out = [H (D x D) | prec (D) | rhs (D)], D = K*L, index d = k*L + l.
+ * partial: nparts x (D*D + 2D) doubles of scratch. */
+int bnmtf_nmtf_sq_f64(int64_t rows, int K, int L, int polarity, int vb, const double* RXo, const double* Go,
+                      const double* SVo, const double* Gfull_o, const double* F, const double* varF, double* partial,
+                      int nparts, double* out, void* stream);
+/* The K*L sequential scalar updates of S on that system (tauS/muS + TN_draw | TN moments | TN_mode,
+ * bnmtf_gibbs_optimised.py:201-205, bnmtf_vb_optimised.py:257-268).  Philox stream = (*iter)*16 + salt, index = d. */
+int bnmtf_coord_solve_f64(int mode, int D, const double* H, const double* prec, const double* rhs, const double* lambda,
+                          double* x, double* var, double* mu, double* tauf, const double* scalars, const int* order,
+                          int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
+                          void* stream);
+/* Variance terms of exp_square_diff (bnmtf_vb_optimised.py:240-243) per column of R from the column statistics
+ * w.r.t. F; extra: rows doubles. */
+int bnmtf_nmtf_extra_f64(int64_t rows, int K, int L, int polarity, const double* Go, const double* SVo,
+                         const double* Gfull_o, const double* G, const double* varG, const double* S, const double* varS,
+                         double* extra, void* stream);
+
 /* ---- non-probabilistic multiplicative updates (nmf_np.py:114-118, nmtf_np.py:155-174) ------------------------ */
 /* P (rows x ld scratch) = A B^T with A rows x K, B cols x K; padding columns of P are set to 1. */
 int bnmtf_np_build_pred_f64(const double* A, const double* B, int64_t rows, int64_t cols, int64_t ld, int K, double* P,
