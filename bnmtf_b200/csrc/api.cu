@@ -28,6 +28,9 @@ int check_launch(const char* what) {
 int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int, int, double*, cudaStream_t);
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
+long long umma_workspace_bytes(int, int, long long);
+int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, double*, double*,
+                           void*, long long, cudaStream_t);
 int launch_pad_factor(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, const double*, double*, double*, cudaStream_t);
 int launch_vb_factor_terms(const double*, const double*, const double*, const double*, const double*, long long, double*, int, cudaStream_t);
@@ -157,6 +160,20 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram: Vp and SVpart must be given together"); return -2; }
   return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, ST(stream));
+}
+
+int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld) {
+  if (K < 1 || K > 63 || ld <= 0) return -1;
+  return umma_workspace_bytes(K, vb, ld);
+}
+
+int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp,
+                              const double* Vp, int K, int polarity, int nseg, int tile, double* Gpart, double* SVpart,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  if (check_k(K)) return -2;
+  if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram_umma: Vp and SVpart must be given together"); return -2; }
+  return launch_stats_gram_umma(bits, (int)rows, (int)ld, (int)cols, Xp, Vp, K, polarity, nseg, tile, Gpart, SVpart,
+                                workspace, workspace_bytes, ST(stream));
 }
 
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp, int64_t n, int K, int64_t dummy_row, double* Gfull,

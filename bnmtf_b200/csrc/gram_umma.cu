@@ -1,0 +1,517 @@
+// Layer 1, 5th-generation tensor-core path: the per-row masked Gram as an EXACT integer GEMM on tcgen05.
+//
+//   G_i[a][b] = sum_{j in S(i)} X_ja X_jb   (a <= b),      SV_i[k] = sum_{j in S(i)} Var_jk     (VB)
+//
+// is  W (rows x cols, 0/1: the selected set of each row)  times  P (cols x NC),  P_jc = X_ja X_jb | Var_jk.
+// W is exact in any format; P is turned into 56-bit fixed point per column (scale = power of two above the
+// column's largest magnitude) and cut into seven unsigned bytes, so that
+//
+//   sum_j W_ij P_jc  =  2^(e_c-55) * ( sum_s 256^s * sum_j W_ij d_s(j,c)  -  2^55 * |S(i)| )
+//
+// where every inner sum is an int32 accumulated by tcgen05.mma.kind::i8 (u8 x u8 -> s32) in tensor memory: no
+// rounding anywhere until the final conversion to double (one rounding of the exact fixed-point total), i.e. the
+// result is the correctly rounded sum of the quantised products -- at least as accurate as an fp64 accumulation
+// and independent of the order of summation.  (The 2^55 offset makes signed P representable with unsigned digits.)
+//
+// Kernel k_gram_umma: one CTA = 128 rows x one chunk of <= 73 P-columns (<= 511 digit columns = the whole tensor
+// memory of an SM as two accumulators of n_half columns) x one segment of the column range.
+//   warps 0-3  expand the mask bits of their 128 rows into the K-major, 64/128-byte-swizzled A tile (generic
+//              proxy stores + fence.proxy.async), count |S(i)|, and run the epilogue (tcgen05.ld -> fixed point
+//              -> double -> packed 8x8 Gram tiles the row solver consumes);
+//   warp 4     streams the digit tiles of P^T (N x K bytes, K-major) with TMA into the same stage;
+//   warp 5     owns tensor memory and issues the tcgen05.mma's (one elected thread), releasing each stage with
+//              tcgen05.commit.
+//
+// Replaces the fp64 DMMA kernel k_stats_gram for the statistics of bnmf_gibbs_optimised.py:167-177,
+// bnmf_vb_optimised.py:189-195 (see stats.cu for the role of the statistics).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace bnmtf {
+
+constexpr int UG_SLICES = 7;
+constexpr int UG_ROWS = 128;     // rows per CTA = UMMA M
+constexpr int UG_THREADS = 192;
+
+struct UmmaPlan {
+  int K, vb;
+  int ng;       // K(K+1)/2 Gram columns
+  int nc;       // ng (+K variance columns)
+  int nch;      // chunks
+  int cpc;      // P-columns per chunk
+  int n_half;   // UMMA N of each of the two accumulators (multiple of 16, <= 256)
+  int nb;       // digit rows per chunk in the staged B matrix = 2*n_half
+};
+
+__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb) {
+  UmmaPlan p;
+  p.K = K; p.vb = vb;
+  p.ng = K * (K + 1) / 2;
+  p.nc = p.ng + (vb ? K : 0);
+  const int cmax = 512 / UG_SLICES;                   // 73
+  p.nch = (p.nc + cmax - 1) / cmax;
+  p.cpc = (p.nc + p.nch - 1) / p.nch;
+  const int nd = p.cpc * UG_SLICES;
+  p.n_half = ((nd + 1) / 2 + 15) / 16 * 16;
+  p.nb = 2 * p.n_half;
+  return p;
+}
+
+// column c of P  ->  (a, b) with a <= b < K, or (k, -1) for a variance column
+__host__ __device__ inline void umma_col_pair(int c, int K, int ng, int& a, int& b) {
+  if (c >= ng) { a = c - ng; b = -1; return; }
+  int aa = 0, rem = c;
+  while (rem >= K - aa) { rem -= K - aa; ++aa; }
+  a = aa; b = aa + rem;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pre-pass 1: largest |P_jc| per column (bit patterns of non-negative doubles order like integers; NaN sorts last)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ug_colmax(const double* __restrict__ Xp, const double* __restrict__ Vp, int n,
+                                                  int KP, UmmaPlan pl, unsigned long long* __restrict__ colmax) {
+  extern __shared__ double xs[];           // [2][K][JT+1]
+  constexpr int JT = 64;
+  const int j0 = blockIdx.x * JT;
+  const int K = pl.K;
+  for (int i = threadIdx.x; i < JT * K; i += blockDim.x) {
+    const int jj = i / K, k = i - jj * K;
+    const int j = j0 + jj;
+    xs[k * (JT + 1) + jj] = (j < n) ? Xp[(size_t)j * KP + k] : 0.0;
+    if (pl.vb) xs[(K + k) * (JT + 1) + jj] = (j < n) ? Vp[(size_t)j * KP + k] : 0.0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < pl.nc; c += blockDim.x) {
+    int a, b;
+    umma_col_pair(c, K, pl.ng, a, b);
+    const double* xa = xs + (b < 0 ? (K + a) : a) * (JT + 1);
+    const double* xb = b < 0 ? nullptr : xs + b * (JT + 1);
+    unsigned long long m = 0ull;
+    for (int jj = 0; jj < JT; ++jj) {
+      const double p = xb ? xa[jj] * xb[jj] : xa[jj];
+      const unsigned long long u = (unsigned long long)__double_as_longlong(fabs(p));
+      m = u > m ? u : m;
+    }
+    atomicMax(colmax + c, m);
+  }
+}
+
+// scale of column c: P is stored as llrint(P * 2^(55-e)) with 2^e > max|P|;  cscale = 2^(e-55) (NaN if not finite)
+__global__ void k_ug_scales(const unsigned long long* __restrict__ colmax, int nc, double* __restrict__ cscale,
+                            int* __restrict__ cexp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double m = __longlong_as_double((long long)colmax[c]);
+  int e = 0;
+  double s;
+  if (!isfinite(m)) { s = __longlong_as_double(0x7ff8000000000000ll); }
+  else {
+    if (m > 0.0) { frexp(m, &e); }       // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
+    s = scalbn(1.0, e - 55);
+  }
+  cscale[c] = s;
+  cexp[c] = e;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pre-pass 2: the digit matrix  Bd[ch*nb + cl*7 + s][j] = byte s of ( llrint(P_jc 2^(55-e_c)) + 2^55 ),  0 for j >= n
+// CTA = 128 threads = 32 column groups of 4 consecutive j  x  4 interleaved P-column subsets.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ug_quantize(const double* __restrict__ Xp, const double* __restrict__ Vp, int n,
+                                                    int KP, long long ldb, UmmaPlan pl, const int* __restrict__ cexp,
+                                                    uint8_t* __restrict__ Bd) {
+  extern __shared__ double xs[];           // [2][K][JT+2]
+  constexpr int JT = 128, XS = JT + 2;
+  const int j0 = blockIdx.x * JT;
+  const int K = pl.K;
+  for (int i = threadIdx.x; i < JT * K; i += blockDim.x) {
+    const int jj = i / K, k = i - jj * K;
+    const int j = j0 + jj;
+    xs[k * XS + jj] = (j < n) ? Xp[(size_t)j * KP + k] : 0.0;
+    if (pl.vb) xs[(K + k) * XS + jj] = (j < n) ? Vp[(size_t)j * KP + k] : 0.0;
+  }
+  __syncthreads();
+  const int jg = (threadIdx.x & 31) * 4, sub = threadIdx.x >> 5;
+  for (int c = sub; c < pl.nch * pl.cpc; c += 4) {
+    const int ch = c / pl.cpc, cl = c - ch * pl.cpc;
+    uint32_t w[UG_SLICES];
+#pragma unroll
+    for (int s = 0; s < UG_SLICES; ++s) w[s] = 0u;
+    if (c < pl.nc) {
+      int a, b;
+      umma_col_pair(c, K, pl.ng, a, b);
+      const double* xa = xs + (b < 0 ? (K + a) : a) * XS + jg;
+      const double* xb = b < 0 ? nullptr : xs + b * XS + jg;
+      const int sh = 55 - cexp[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (j0 + jg + i < n) {
+          const double p = xb ? xa[i] * xb[i] : xa[i];
+          const long long q = llrint(scalbn(p, sh)) + (1ll << 55);
+#pragma unroll
+          for (int s = 0; s < UG_SLICES; ++s) w[s] |= (uint32_t)((q >> (8 * s)) & 0xff) << (8 * i);
+        }
+      }
+    }
+    uint8_t* dst = Bd + ((size_t)ch * pl.nb + (size_t)cl * UG_SLICES) * ldb + j0 + jg;
+    if (j0 + jg < ldb) {
+#pragma unroll
+      for (int s = 0; s < UG_SLICES; ++s) *reinterpret_cast<uint32_t*>(dst + (size_t)s * ldb) = w[s];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], u8 x u8 -> s32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t addr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO>>4 |
+// version 1 (Blackwell) | layout type (2 = 128B swizzle, 4 = 64B swizzle)
+template <int KT>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  constexpr uint64_t SBO = (8 * KT) >> 4;          // 8 rows of KT bytes per swizzle atom
+  constexpr uint64_t LAYOUT = KT == 128 ? 2 : 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (SBO << 32) | (1ull << 46) | (LAYOUT << 61);
+}
+
+struct UmmaGramArgs {
+  const uint32_t* bits; int rows, wpr, cols, polarity;
+  int ktiles, tiles_per_seg;
+  UmmaPlan pl;
+  const double* cscale;
+  double* Gout; double* SVout;
+  int KP, gl;       // padded factor width, doubles per Gram record (NTP*64)
+  int stages;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_constant__ CUtensorMap tmap, UmmaGramArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const UmmaPlan& pl = a.pl;
+  const int A_BYTES = UG_ROWS * KT, B_BYTES = pl.nb * KT, STAGE = A_BYTES + B_BYTES;
+  const int stages = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);   // full[stages], empty[stages], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  uint16_t* pair_tab = reinterpret_cast<uint16_t*>(tmem_slot + 2);              // [cpc] (a<<8 | b), b = 0xff: variance
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+#define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
+#define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(stages + (s)))
+#define ACCUM_BAR (bar_base + 8u * (uint32_t)(2 * stages))
+
+  const int rb = blockIdx.x, ch = blockIdx.y, seg = blockIdx.z;
+  const int kt_begin = seg * a.tiles_per_seg;
+  const int kt_end = min(a.ktiles, kt_begin + a.tiles_per_seg);
+  const int ntile = kt_end - kt_begin;                 // >= 1 by construction of the grid
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), 128 + 1); mbar_init(EMPTY_BAR(s), 1); }
+    mbar_init(ACCUM_BAR, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int cl = tid; cl < pl.cpc; cl += UG_THREADS) {
+    const int c = ch * pl.cpc + cl;
+    int pa = 0xff, pb = 0xfe;                          // 0xff/0xfe: column beyond nc (nothing to store)
+    if (c < pl.nc) { int x, y; umma_col_pair(c, pl.K, pl.ng, x, y); pa = x; pb = y < 0 ? 0xff : y; }
+    pair_tab[cl] = (uint16_t)((pa << 8) | pb);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================= mask expander, then epilogue: thread <-> row =================
+    const int row = rb * UG_ROWS + tid;
+    const bool live = row < a.rows;
+    const uint32_t* mrow = a.bits + (size_t)(live ? row : 0) * a.wpr;
+    constexpr int WPT = KT / 32;                       // mask words per tile
+    const uint32_t flip = a.polarity ? 0u : 0xffffffffu;
+    // byte offset of this row inside an A tile, and its swizzle key (16-byte chunk index XOR)
+    const uint32_t row_off = (uint32_t)(tid >> 3) * (8 * KT) + (uint32_t)(tid & 7) * KT;
+    const uint32_t key = KT == 128 ? (uint32_t)(tid & 7) : (uint32_t)((tid >> 1) & 3);
+    int cnt = 0;
+    uint32_t nxt[WPT];
+    {
+      const int w0 = kt_begin * WPT;
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) nxt[i] = (live && w0 + i < a.wpr) ? mrow[w0 + i] : 0u;
+    }
+    for (int it = 0; it < ntile; ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      uint32_t w[WPT];
+      const int wbase = (kt_begin + it) * WPT;
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        uint32_t v = nxt[i] ^ flip;
+        const int jb = (wbase + i) * 32;               // first column of this word
+        if (jb + 32 > a.cols) v = jb >= a.cols ? 0u : (v & ((1u << (a.cols - jb)) - 1u));
+        w[i] = live ? v : 0u;
+        cnt += __popc(w[i]);
+      }
+      if (it + 1 < ntile) {
+        const int wn = wbase + WPT;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) nxt[i] = (live && wn + i < a.wpr) ? mrow[wn + i] : 0u;
+      }
+      mbar_wait(EMPTY_BAR(s), ph ^ 1u);
+      const uint32_t abase = smem_base + (uint32_t)s * STAGE + row_off;
+#pragma unroll
+      for (int c16 = 0; c16 < KT / 16; ++c16) {
+        const uint32_t h = (w[c16 >> 1] >> (16 * (c16 & 1))) & 0xffffu;
+        const uint32_t y0 = ((h & 0xfu) * 0x00204081u) & 0x01010101u;
+        const uint32_t y1 = (((h >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+        const uint32_t y2 = (((h >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
+        const uint32_t y3 = ((h >> 12) * 0x00204081u) & 0x01010101u;
+        const uint32_t addr = abase + ((((uint32_t)c16) ^ key) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y0), "r"(y1), "r"(y2), "r"(y3) : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(FULL_BAR(s));
+    }
+
+    // ---- epilogue ----
+    mbar_wait(ACCUM_BAR, 0u);
+    tc_fence_after();
+    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    double* grow = a.Gout + ((size_t)seg * a.rows + (live ? row : 0)) * a.gl;
+    double* srow = a.SVout ? a.SVout + ((size_t)seg * a.rows + (live ? row : 0)) * a.KP : nullptr;
+    const int NT = a.KP >> 3;
+    for (int cl = 0; cl < pl.cpc; ++cl) {
+      uint32_t d[UG_SLICES];
+#pragma unroll
+      for (int s = 0; s < UG_SLICES; ++s) d[s] = tmem_ld1(tlane + (uint32_t)(cl * UG_SLICES + s));
+      tmem_ld_wait();
+      const uint32_t pr = pair_tab[cl];
+      const int pa = pr >> 8, pb = pr & 0xff;
+      if (!live || pb == 0xfe) continue;
+      const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
+      const long long hi = (long long)d[4] + ((long long)d[5] << 8) + (((long long)(int)d[6] - 128ll * cnt) << 16);
+      const double v = fma((double)hi, 4294967296.0, (double)lo) * a.cscale[ch * pl.cpc + cl];
+      if (pb == 0xff) {
+        if (srow) srow[pa] = v;
+      } else {
+        const int ta = pa >> 3, tb = pb >> 3;
+        const int p = ta * NT - ta * (ta - 1) / 2 + (tb - ta);
+        grow[p * 64 + (pa & 7) * 8 + (pb & 7)] = v;
+        if (ta == tb) grow[p * 64 + (pb & 7) * 8 + (pa & 7)] = v;
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ================= TMA producer of the digit tiles =================
+    if (lane == 0) {
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(EMPTY_BAR(s), ph ^ 1u);
+        mbar_expect_tx(FULL_BAR(s), (uint32_t)B_BYTES);
+        const uint32_t bdst = smem_base + (uint32_t)s * STAGE + A_BYTES;
+        const int x = (kt_begin + it) * KT;
+        tma_load_2d(bdst, &tmap, x, ch * pl.nb, FULL_BAR(s));
+        tma_load_2d(bdst + (uint32_t)pl.n_half * KT, &tmap, x, ch * pl.nb + pl.n_half, FULL_BAR(s));
+      }
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, N = n_half, M = 128
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(pl.n_half >> 3) << 17) | ((uint32_t)(UG_ROWS >> 4) << 24);
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(FULL_BAR(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + (uint32_t)s * STAGE;
+        const uint64_t ad = umma_desc<KT>(sa);
+        const uint64_t bd0 = umma_desc<KT>(sa + A_BYTES);
+        const uint64_t bd1 = umma_desc<KT>(sa + A_BYTES + (uint32_t)pl.n_half * KT);
+#pragma unroll
+        for (int kk = 0; kk < KT / 32; ++kk) {
+          const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+          umma_i8(tmem_base, ad + 2 * kk, bd0 + 2 * kk, idesc, acc);
+          umma_i8(tmem_base + (uint32_t)pl.n_half, ad + 2 * kk, bd1 + 2 * kk, idesc, acc);
+        }
+        umma_commit(EMPTY_BAR(s));
+      }
+      umma_commit(ACCUM_BAR);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+#undef FULL_BAR
+#undef EMPTY_BAR
+#undef ACCUM_BAR
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// workspace layout: colmax (nc u64) | cscale (nc f64) | cexp (nc i32, padded) | digits (nch*nb x ldb bytes, 1024-aligned)
+static size_t ws_digits_offset(const UmmaPlan& pl) {
+  size_t o = (size_t)pl.nc * 8 * 2 + (size_t)((pl.nc + 1) / 2 * 2) * 4;
+  return (o + 1023) / 1024 * 1024;
+}
+
+long long umma_workspace_bytes(int K, int vb, long long ld) {
+  const UmmaPlan pl = make_umma_plan(K, vb);
+  return (long long)ws_digits_offset(pl) + (long long)pl.nch * pl.nb * ld;
+}
+
+int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, const double* Xp, const double* Vp, int K,
+                           int polarity, int nseg, int kt, double* Gout, double* SVout, void* workspace,
+                           long long workspace_bytes, cudaStream_t st) {
+  if (rows <= 0 || ld <= 0 || ld % 64 || nseg <= 0 || cols <= 0 || cols > ld) { set_error("stats_gram_umma: bad shape"); return -2; }
+  if (kt != 64 && kt != 128) { set_error("stats_gram_umma: tile width must be 64 or 128"); return -2; }
+  if ((long long)ld * 255 >= 2147483647ll) { set_error("stats_gram_umma: more than 8.4M columns would overflow the int32 accumulators"); return -2; }
+  const int vb = Vp != nullptr;
+  const UmmaPlan pl = make_umma_plan(K, vb);
+  if (workspace_bytes < umma_workspace_bytes(K, vb, ld)) { set_error("stats_gram_umma: workspace too small"); return -2; }
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { set_error("stats_gram_umma: cuTensorMapEncodeTiled not available"); return -3; }
+
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  unsigned long long* colmax = reinterpret_cast<unsigned long long*>(ws);
+  double* cscale = reinterpret_cast<double*>(ws + (size_t)pl.nc * 8);
+  int* cexp = reinterpret_cast<int*>(ws + (size_t)pl.nc * 16);
+  uint8_t* Bd = ws + ws_digits_offset(pl);
+  const int KP = 8 * tiles_for(K);
+  const int nt = tiles_for(K);
+
+  cudaMemsetAsync(colmax, 0, (size_t)pl.nc * 8, st);
+  {
+    const size_t sm = (size_t)(vb ? 2 : 1) * K * 65 * sizeof(double);
+    k_ug_colmax<<<(cols + 63) / 64, 256, sm, st>>>(Xp, Vp, cols, KP, pl, colmax);
+    k_ug_scales<<<(pl.nc + 127) / 128, 128, 0, st>>>(colmax, pl.nc, cscale, cexp);
+    const size_t sq = (size_t)(vb ? 2 : 1) * K * 130 * sizeof(double);
+    if (sq > 48 * 1024) cudaFuncSetAttribute(k_ug_quantize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sq);
+    k_ug_quantize<<<(ld + 127) / 128, 128, sq, st>>>(Xp, Vp, cols, KP, (long long)ld, pl, cexp, Bd);
+  }
+  if (check_launch("stats_gram_umma prepass")) return -1;
+
+  CUtensorMap tmap;
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)pl.nch * pl.nb};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld};
+    const cuuint32_t box[2] = {(cuuint32_t)kt, (cuuint32_t)pl.n_half};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, Bd, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              kt == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("stats_gram_umma: cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
+  }
+
+  UmmaGramArgs a;
+  a.bits = bits; a.rows = rows; a.wpr = ld / 32; a.cols = cols; a.polarity = polarity;
+  a.ktiles = (ld + kt - 1) / kt;
+  a.tiles_per_seg = (a.ktiles + nseg - 1) / nseg;
+  const int nseg_eff = (a.ktiles + a.tiles_per_seg - 1) / a.tiles_per_seg;
+  if (nseg_eff != nseg) { set_error("stats_gram_umma: nseg=%d leaves empty segments (use <= %d)", nseg, nseg_eff); return -2; }
+  a.pl = pl; a.cscale = cscale; a.Gout = Gout; a.SVout = SVout; a.KP = KP; a.gl = nt * (nt + 1) / 2 * 64;
+  const int stage_bytes = (UG_ROWS + pl.nb) * kt;
+  const int tail = (2 * 16 + 1) * 8 + 16 + 2 * pl.cpc + 64;
+  int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
+  if (stages > 16) stages = 16;
+  if (stages < 2) { set_error("stats_gram_umma: stage does not fit"); return -2; }
+  a.stages = stages;
+  // >= half of the SM's shared memory: one CTA per SM, so the 512-column tensor-memory allocation never waits
+  size_t smem = (size_t)stages * stage_bytes + tail + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  dim3 grid((rows + UG_ROWS - 1) / UG_ROWS, pl.nch, nseg);
+  if (kt == 128) {
+    cudaFuncSetAttribute(k_gram_umma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_gram_umma<128><<<grid, UG_THREADS, smem, st>>>(tmap, a);
+  } else {
+    cudaFuncSetAttribute(k_gram_umma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_gram_umma<64><<<grid, UG_THREADS, smem, st>>>(tmap, a);
+  }
+  return check_launch("stats_gram_umma");
+}
+
+}  // namespace bnmtf

@@ -78,6 +78,16 @@ int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int6
  * subtracts from Gfull), 1: over the OBSERVED entries. */
 int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp /*or NULL*/,
                          int K, int polarity, int nseg, double* Gpart, double* SVpart /*or NULL*/, void* stream);
+/* The same statistics on the 5th-generation tensor cores (tcgen05.mma kind::i8 with tensor-memory accumulators):
+ * the products X_ja X_jb (and Var_jk) are cut into seven exact 8-bit digits of a 56-bit fixed-point value per
+ * column and multiplied with the 0/1 selection matrix of the rows, so the result is the exactly summed,
+ * once-rounded value.  cols = number of valid columns (<= ld); tile = 64 or 128 (bytes of the column range staged
+ * per pipeline stage); workspace: >= bnmtf_gram_umma_workspace_bytes(K, Vp != NULL, ld) bytes, 1024-byte aligned.
+ * Only the entries (a, b < K) of the packed tiles and the first K entries of SVpart are written. */
+int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld);
+int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp,
+                              const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, double* Gpart,
+                              double* SVpart /*or NULL*/, void* workspace, int64_t workspace_bytes, void* stream);
 /* scratch: >= 64 * (bnmtf_gram_len(K) + KP) doubles */
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t n, int K, int64_t dummy_row,
                         double* Gfull, double* scratch, void* stream);
