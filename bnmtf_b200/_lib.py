@@ -23,10 +23,14 @@ SIGNATURES = {
     "bnmtf_stats_gram_f64": [c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "bnmtf_gram_full_f64": [c_p, c_p, c_i64, c_i, c_i64, c_p, c_p, c_p],
     "bnmtf_gram_umma_workspace_bytes": [c_i, c_i, c_i64],
-    "bnmtf_stats_gram_umma_f64": [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i64, c_p],
+    "bnmtf_stats_gram_umma_f64": [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i64,
+                                  c_p],
     "bnmf_row_solve_f64": [c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                           c_i, c_i, c_d, c_u64, c_p, c_u64, c_i64, c_p, c_p, c_p],
-    "bnmtf_masked_metrics_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
+                           c_i, c_i, c_d, c_u64, c_p, c_u64, c_i64, c_p, c_p, c_p, c_p],
+    "bnmtf_masked_metrics_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "bnmtf_mstat_reduce_f64": [c_p, c_i64, c_p, c_p, c_p],
+    "bnmtf_metrics_from_sums_f64": [c_p, c_p, c_d, c_p, c_p, c_p],
+    "bnmtf_select_metrics_f64": [c_p, c_p, c_p, c_p],
     "bnmtf_dense_metrics_f64": [c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_p],
     "bnmtf_vb_factor_terms_f64": [c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p],
     "bnmtf_reduce8_f64": [c_p, c_i, c_p, c_p],
@@ -55,7 +59,8 @@ _lib = None
 
 # kernels launched per entry point (for bench.py's gpu_launches count)
 KERNELS_PER_CALL = {"bnmtf_pack_dataset_f64": 1, "bnmtf_pack_mask_f64": 1, "bnmtf_transpose_dataset_f64": 1,
-                    "bnmtf_pad_factor_f64": 1, "bnmtf_stats_rx_f64": 1, "bnmtf_stats_gram_f64": 1, "bnmtf_stats_gram_umma_f64": 4,
+                    "bnmtf_pad_factor_f64": 1, "bnmtf_stats_rx_f64": 1, "bnmtf_stats_gram_f64": 1, "bnmtf_stats_gram_umma_f64": 4, "bnmtf_mstat_reduce_f64": 2,
+                    "bnmtf_metrics_from_sums_f64": 1, "bnmtf_select_metrics_f64": 1,
                     "bnmtf_gram_full_f64": 2, "bnmf_row_solve_f64": 1, "bnmtf_masked_metrics_f64": 3,
                     "bnmtf_dense_metrics_f64": 2, "bnmtf_vb_factor_terms_f64": 1, "bnmtf_reduce8_f64": 1,
                     "bnmtf_reduce1_f64": 1, "bnmf_finish_sweep_f64": 1, "bnmtf_tn_moments_f64": 1, "bnmtf_np_build_pred_f64": 1,

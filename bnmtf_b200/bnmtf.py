@@ -59,7 +59,7 @@ class BNMTFEngine:
         self.elpart = f64(3 * self.nb_terms * 8)
         self.statics = f64(3)
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(ds.bits), I, ds.ldJ, _ptr(self.FS.Xp), _ptr(self.G.Xp),
-                  self.L, self.nseg_m, 0, _ptr(self.mpart), _ptr(self.m8), _stream())
+                  self.L, self.nseg_m, 0, _ptr(self.mpart), _ptr(self.m8), 0, _stream())
         self.statics.copy_(self.m8[4:7])
         if ds.n_obs is None:
             ds.n_obs = float(self.statics[2].item())
@@ -112,7 +112,7 @@ class BNMTFEngine:
                   _ptr(self.eff["SV"]) if self.vb else 0, 0, _ptr(me.fac), _ptr(me.var), _ptr(me.mu), _ptr(me.tauf),
                   _ptr(me.lam), _ptr(self.scalars), optr, n_order, 1 if apply else 0, float(minimum_TN), self.seed,
                   _ptr(self.iter if use_iter else self.iter_scratch), salt, 0,
-                  _ptr(self.sterm) if want_sterm else 0, 0, _stream())
+                  _ptr(self.sterm) if want_sterm else 0, 0, 0, _stream())
         del keep
 
     def phase_F(self, order=None, n_order=None, apply=True, minimum_TN=0.0, want_sterm=False, use_iter=True):
@@ -150,7 +150,7 @@ class BNMTFEngine:
         bits = ds.bits if bits is None else bits
         statics = _ptr(self.statics) if bits is ds.bits else 0
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(bits), ds.I, ds.ldJ, _ptr(self.FS.Xp), _ptr(self.G.Xp),
-                  self.L, self.nseg_m, statics, _ptr(self.mpart), _ptr(self.m8), _stream())
+                  self.L, self.nseg_m, statics, _ptr(self.mpart), _ptr(self.m8), 0, _stream())
 
     def vb_extra(self):
         """Variance terms of exp_square_diff; the column statistics must be current w.r.t. F."""

@@ -29,10 +29,13 @@ int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 long long umma_workspace_bytes(int, int, long long);
-int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, double*, double*,
-                           void*, long long, cudaStream_t);
+int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, int, int,
+                           double*, double*, void*, long long, cudaStream_t);
 int launch_pad_factor(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
-int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, const double*, double*, double*, cudaStream_t);
+int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, const double*, double*, double*, const int*, cudaStream_t);
+int launch_mstat_reduce(const double*, int, double*, double*, cudaStream_t);
+int launch_metrics_from_sums(const double*, const double*, double, double*, int*, cudaStream_t);
+int launch_select_metrics(const int*, const double*, double*, cudaStream_t);
 int launch_vb_factor_terms(const double*, const double*, const double*, const double*, const double*, long long, double*, int, cudaStream_t);
 int launch_reduce8(const double*, int, double*, cudaStream_t);
 int launch_dense_metrics(const double*, const double*, const double*, long long, double*, int, double*, cudaStream_t);
@@ -168,12 +171,12 @@ int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld) {
 }
 
 int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp,
-                              const double* Vp, int K, int polarity, int nseg, int tile, double* Gpart, double* SVpart,
-                              void* workspace, int64_t workspace_bytes, void* stream) {
+                              const double* Vp, int K, int polarity, int nseg, int tile, int sums, int max_stages,
+                              double* Gpart, double* SVpart, void* workspace, int64_t workspace_bytes, void* stream) {
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram_umma: Vp and SVpart must be given together"); return -2; }
-  return launch_stats_gram_umma(bits, (int)rows, (int)ld, (int)cols, Xp, Vp, K, polarity, nseg, tile, Gpart, SVpart,
-                                workspace, workspace_bytes, ST(stream));
+  return launch_stats_gram_umma(bits, (int)rows, (int)ld, (int)cols, Xp, Vp, K, polarity, nseg, tile, sums, max_stages,
+                                Gpart, SVpart, workspace, workspace_bytes, ST(stream));
 }
 
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp, int64_t n, int K, int64_t dummy_row, double* Gfull,
@@ -186,7 +189,7 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
                        const double* Gpart, const double* SVpart, const double* Gfull, double* fac, double* var,
                        double* mu, double* tauf, const double* lambda, const double* scalars, const int* order,
                        int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
-                       int64_t row_offset, double* sterm, double* extra, void* stream) {
+                       int64_t row_offset, double* sterm, double* extra, double* mstat, void* stream) {
   if (check_k(K)) return -2;
   if (mode < 0 || mode > 2) { set_error("row_solve: bad mode %d", mode); return -2; }
   if (mode == BNMTF_MODE_VB && (!var || !SVpart)) { set_error("row_solve: VB needs var and SVpart"); return -2; }
@@ -196,15 +199,29 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
   a.n_order = n_order; a.apply = apply; a.RXpart = RXpart; a.Gpart = Gpart; a.SVpart = SVpart; a.Gfull = Gfull;
   a.fac = fac; a.var = var; a.mu = mu; a.tauf = tauf; a.lambda = lambda; a.scalars = scalars; a.order = order;
   a.min_tn = min_tn; a.seed = seed; a.iter = reinterpret_cast<const unsigned long long*>(iter); a.salt = salt;
-  a.sterm = sterm; a.extra = extra; a.row_offset = row_offset;
+  a.sterm = sterm; a.extra = extra; a.mstat = mstat; a.row_offset = row_offset;
   return launch_row_solve(a, ST(stream));
 }
 
 int bnmtf_masked_metrics_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Ap,
                              const double* Bp, int K, int nseg, const double* statics3, double* partials, double* out8,
-                             void* stream) {
+                             const int* run_flag, void* stream) {
   if (check_k(K)) return -2;
-  return launch_masked_metrics(R, bits, (int)rows, (int)ld, Ap, Bp, K, nseg, statics3, partials, out8, ST(stream));
+  return launch_masked_metrics(R, bits, (int)rows, (int)ld, Ap, Bp, K, nseg, statics3, partials, out8, run_flag, ST(stream));
+}
+
+int bnmtf_mstat_reduce_f64(const double* mstat, int64_t rows, double* partial, double* out4, void* stream) {
+  if (rows <= 0) { set_error("mstat_reduce: no rows"); return -2; }
+  return launch_mstat_reduce(mstat, (int)rows, partial, out4, ST(stream));
+}
+
+int bnmtf_metrics_from_sums_f64(const double* sums4, const double* statics3, double guard, double* out8, int* direct_flag,
+                                void* stream) {
+  return launch_metrics_from_sums(sums4, statics3, guard, out8, direct_flag, ST(stream));
+}
+
+int bnmtf_select_metrics_f64(const int* flag, const double* direct8, double* out8, void* stream) {
+  return launch_select_metrics(flag, direct8, out8, ST(stream));
 }
 
 int bnmtf_vb_factor_terms_f64(const double* ex, const double* var, const double* mu, const double* tauf,

@@ -52,6 +52,7 @@ struct RowSolveArgs {
   long long row_offset;  // global index of local row 0 (row-sharded runs): keeps the Philox stream shard-invariant
   double* sterm;   // optional: the masked-sum term s (rows x K), for the white-box muU()/muV() API
   double* extra;   // optional (VB): per-row sum_k [ var_k (g_kk + sv_k) + u_k^2 sv_k ] for exp_square_diff
+  double* mstat;   // optional: rows x 4 {sum_obs r p, sum_obs p^2, sum_obs p, 0} of the row with its NEW factor values
 };
 
 struct FinishArgs {

@@ -34,20 +34,20 @@ constexpr int UG_ROWS = 128;     // rows per CTA = UMMA M
 constexpr int UG_THREADS = 192;
 
 struct UmmaPlan {
-  int K, vb;
+  int K, vb, sums;
   int ng;       // K(K+1)/2 Gram columns
-  int nc;       // ng (+K variance columns)
+  int nc;       // ng (+K variance columns) (+K plain columns X_jk: masked column sums, for the metrics)
   int nch;      // chunks
   int cpc;      // P-columns per chunk
   int n_half;   // UMMA N of each of the two accumulators (multiple of 16, <= 256)
   int nb;       // digit rows per chunk in the staged B matrix = 2*n_half
 };
 
-__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb) {
+__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums) {
   UmmaPlan p;
-  p.K = K; p.vb = vb;
+  p.K = K; p.vb = vb; p.sums = sums;
   p.ng = K * (K + 1) / 2;
-  p.nc = p.ng + (vb ? K : 0);
+  p.nc = p.ng + (vb ? K : 0) + (sums ? K : 0);
   const int cmax = 512 / UG_SLICES;                   // 73
   p.nch = (p.nc + cmax - 1) / cmax;
   p.cpc = (p.nc + p.nch - 1) / p.nch;
@@ -57,9 +57,14 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb) {
   return p;
 }
 
-// column c of P  ->  (a, b) with a <= b < K, or (k, -1) for a variance column
-__host__ __device__ inline void umma_col_pair(int c, int K, int ng, int& a, int& b) {
-  if (c >= ng) { a = c - ng; b = -1; return; }
+// column c of P  ->  (a, b) with a <= b < K: X_a X_b;  (k, -1): Var_k;  (k, -2): X_k
+__host__ __device__ inline void umma_col_pair(int c, const UmmaPlan& pl, int& a, int& b) {
+  const int K = pl.K, ng = pl.ng;
+  if (c >= ng) {
+    a = c - ng; b = -1;
+    if (!pl.vb || a >= K) { a -= pl.vb ? K : 0; b = -2; }
+    return;
+  }
   int aa = 0, rem = c;
   while (rem >= K - aa) { rem -= K - aa; ++aa; }
   a = aa; b = aa + rem;
@@ -83,8 +88,8 @@ __global__ void __launch_bounds__(256) k_ug_colmax(const double* __restrict__ Xp
   __syncthreads();
   for (int c = threadIdx.x; c < pl.nc; c += blockDim.x) {
     int a, b;
-    umma_col_pair(c, K, pl.ng, a, b);
-    const double* xa = xs + (b < 0 ? (K + a) : a) * (JT + 1);
+    umma_col_pair(c, pl, a, b);
+    const double* xa = xs + (b == -1 ? (K + a) : a) * (JT + 1);
     const double* xb = b < 0 ? nullptr : xs + b * (JT + 1);
     unsigned long long m = 0ull;
     for (int jj = 0; jj < JT; ++jj) {
@@ -139,8 +144,8 @@ __global__ void __launch_bounds__(128) k_ug_quantize(const double* __restrict__ 
     for (int s = 0; s < UG_SLICES; ++s) w[s] = 0u;
     if (c < pl.nc) {
       int a, b;
-      umma_col_pair(c, K, pl.ng, a, b);
-      const double* xa = xs + (b < 0 ? (K + a) : a) * XS + jg;
+      umma_col_pair(c, pl, a, b);
+      const double* xa = xs + (b == -1 ? (K + a) : a) * XS + jg;
       const double* xb = b < 0 ? nullptr : xs + b * XS + jg;
       const int sh = 55 - cexp[c];
 #pragma unroll
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   const int stages = a.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);   // full[stages], empty[stages], accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
-  uint16_t* pair_tab = reinterpret_cast<uint16_t*>(tmem_slot + 2);              // [cpc] (a<<8 | b), b = 0xff: variance
+  uint16_t* pair_tab = reinterpret_cast<uint16_t*>(tmem_slot + 2);   // [cpc] (a<<8 | b), b = 0xff: variance, 0xfd: sum
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
@@ -275,8 +280,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   }
   for (int cl = tid; cl < pl.cpc; cl += UG_THREADS) {
     const int c = ch * pl.cpc + cl;
-    int pa = 0xff, pb = 0xfe;                          // 0xff/0xfe: column beyond nc (nothing to store)
-    if (c < pl.nc) { int x, y; umma_col_pair(c, pl.K, pl.ng, x, y); pa = x; pb = y < 0 ? 0xff : y; }
+    int pa = 0xff, pb = 0xfe;                          // 0xfe: column beyond nc (nothing to store)
+    if (c < pl.nc) { int x, y; umma_col_pair(c, pl, x, y); pa = x; pb = y == -1 ? 0xff : (y == -2 ? 0xfd : y); }
     pair_tab[cl] = (uint16_t)((pa << 8) | pb);
   }
   tc_fence_before();
@@ -355,12 +360,20 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       const double v = fma((double)hi, 4294967296.0, (double)lo) * a.cscale[ch * pl.cpc + cl];
       if (pb == 0xff) {
         if (srow) srow[pa] = v;
+      } else if (pb == 0xfd) {
+        // masked column sum of X_k: the slot (k, K) of the packed tiles, where the DMMA kernel's ones-column puts it
+        const int ta = pa >> 3, tb = pl.K >> 3;
+        grow[(ta * NT - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (pa & 7) * 8 + (pl.K & 7)] = v;
       } else {
         const int ta = pa >> 3, tb = pb >> 3;
         const int p = ta * NT - ta * (ta - 1) / 2 + (tb - ta);
         grow[p * 64 + (pa & 7) * 8 + (pb & 7)] = v;
         if (ta == tb) grow[p * 64 + (pb & 7) * 8 + (pa & 7)] = v;
       }
+    }
+    if (live && ch == 0) {                               // |S(i)| in the (K, K) slot
+      const int tk = pl.K >> 3;
+      grow[(tk * NT - tk * (tk - 1) / 2) * 64 + (pl.K & 7) * 9] = (double)cnt;
     }
     tc_fence_before();
   } else if (warp == 4) {
@@ -439,20 +452,24 @@ static size_t ws_digits_offset(const UmmaPlan& pl) {
   return (o + 1023) / 1024 * 1024;
 }
 
-long long umma_workspace_bytes(int K, int vb, long long ld) {
-  const UmmaPlan pl = make_umma_plan(K, vb);
+static long long plan_workspace_bytes(const UmmaPlan& pl, long long ld) {
   return (long long)ws_digits_offset(pl) + (long long)pl.nch * pl.nb * ld;
 }
 
+long long umma_workspace_bytes(int K, int vb, long long ld) {
+  const long long a = plan_workspace_bytes(make_umma_plan(K, vb, 0), ld), b = plan_workspace_bytes(make_umma_plan(K, vb, 1), ld);
+  return a > b ? a : b;
+}
+
 int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, const double* Xp, const double* Vp, int K,
-                           int polarity, int nseg, int kt, double* Gout, double* SVout, void* workspace,
-                           long long workspace_bytes, cudaStream_t st) {
+                           int polarity, int nseg, int kt, int sums, int max_stages, double* Gout, double* SVout,
+                           void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (rows <= 0 || ld <= 0 || ld % 64 || nseg <= 0 || cols <= 0 || cols > ld) { set_error("stats_gram_umma: bad shape"); return -2; }
   if (kt != 64 && kt != 128) { set_error("stats_gram_umma: tile width must be 64 or 128"); return -2; }
   if ((long long)ld * 255 >= 2147483647ll) { set_error("stats_gram_umma: more than 8.4M columns would overflow the int32 accumulators"); return -2; }
   const int vb = Vp != nullptr;
-  const UmmaPlan pl = make_umma_plan(K, vb);
-  if (workspace_bytes < umma_workspace_bytes(K, vb, ld)) { set_error("stats_gram_umma: workspace too small"); return -2; }
+  const UmmaPlan pl = make_umma_plan(K, vb, sums);
+  if (workspace_bytes < plan_workspace_bytes(pl, ld)) { set_error("stats_gram_umma: workspace too small"); return -2; }
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("stats_gram_umma: cuTensorMapEncodeTiled not available"); return -3; }
 
@@ -498,11 +515,12 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   const int tail = (2 * 16 + 1) * 8 + 16 + 2 * pl.cpc + 64;
   int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
   if (stages > 16) stages = 16;
+  if (max_stages > 0 && stages > max_stages) stages = max_stages;
   if (stages < 2) { set_error("stats_gram_umma: stage does not fit"); return -2; }
   a.stages = stages;
-  // >= half of the SM's shared memory: one CTA per SM, so the 512-column tensor-memory allocation never waits
+  // > half of the SM's shared memory: one CTA per SM, so the 512-column tensor-memory allocation never waits
   size_t smem = (size_t)stages * stage_bytes + tail + 1024;
-  if (smem < 120 * 1024) smem = 120 * 1024;
+  if (smem < 116 * 1024) smem = 116 * 1024;
   dim3 grid((rows + UG_ROWS - 1) / UG_ROWS, pl.nch, nseg);
   if (kt == 128) {
     cudaFuncSetAttribute(k_gram_umma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -123,6 +123,40 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
       if (a.sterm) a.sterm[idx] = s;
     }
   }
+  if (a.mstat) {
+    // masked prediction sums of this row from its statistics (p_ij = u_i . x_j over the observed j):
+    //   sum r p = u . RX,   sum p^2 = u^T G_obs u,   sum p = u . (masked column sums = slot (k, K) of G_obs)
+    __syncwarp();
+    double* uu = G + K * GS;                             // row K of the staged matrix is free below column K
+    double colsum[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      colsum[q] = (c < K) ? G[c * GS + K] : 0.0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      if (c < K) uu[c] = u[q];
+    }
+    __syncwarp();
+    double rp = 0.0, pp = 0.0, sp = 0.0;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      if (c < K) {
+        double t = 0.0;
+        for (int k2 = 0; k2 < K; ++k2) t = fma(G[c * GS + k2], uu[k2], t);
+        pp = fma(u[q], t, pp);
+        rp = fma(u[q], rx[q], rp);
+        sp = fma(u[q], colsum[q], sp);
+      }
+    }
+    rp = warp_sum(rp); pp = warp_sum(pp); sp = warp_sum(sp);
+    if (lane == 0) *reinterpret_cast<double4*>(a.mstat + (size_t)row * 4) = make_double4(rp, pp, sp, 0.0);
+    __syncwarp();
+  }
   if (a.extra) {
     double e = 0.0;
 #pragma unroll
@@ -147,7 +181,8 @@ template <int KS, bool FULL>  // KS = ceil(K/4) k-steps
 __global__ void __launch_bounds__(256) k_masked_metrics(const double* __restrict__ R, const uint32_t* __restrict__ bits,
                                                        int rows, int ld, const double* __restrict__ Ap,
                                                        const double* __restrict__ Bp, int K, int KP, int seg_cols,
-                                                       double* __restrict__ partials) {
+                                                       double* __restrict__ partials, const int* __restrict__ run_flag) {
+  if (run_flag && *run_flag == 0) return;      // gated fallback of the statistics-based metrics (uniform exit)
   constexpr int CHM = KS <= 8 ? 128 : 64;
   constexpr int CS = CHM + 4;
   __shared__ double bs[4 * KS * CS];
@@ -255,7 +290,9 @@ __global__ void __launch_bounds__(256) k_masked_metrics(const double* __restrict
 }
 
 // lean mode: complete the 7-vector from the static sums of the training mask {sum r, sum r^2, |Omega|}
-__global__ void k_fill_static_sums(double* __restrict__ out8, const double* __restrict__ statics3) {
+__global__ void k_fill_static_sums(double* __restrict__ out8, const double* __restrict__ statics3,
+                                   const int* __restrict__ run_flag) {
+  if (run_flag && *run_flag == 0) return;
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const double e2 = out8[0], p2 = out8[2], r = statics3[0], r2 = statics3[1], n = statics3[2];
     out8[3] = 0.5 * (r2 + p2 - e2);
@@ -263,8 +300,56 @@ __global__ void k_fill_static_sums(double* __restrict__ out8, const double* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// training metrics without a pass over R: per-row sums from the solver (rows x 4) -> 64 block partials -> out4
+// = {sum r p, sum p^2, sum p, 0} (fixed summation order).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mstat_partial(const double* __restrict__ mstat, int rows, double* __restrict__ partial) {
+  double s[3] = {0, 0, 0};
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < rows; i += gridDim.x * 256) {
+    const double4 v = *reinterpret_cast<const double4*>(mstat + (size_t)i * 4);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z;
+  }
+  __shared__ double red[8][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double v = warp_sum(s[i]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    if (threadIdx.x < 3) for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+}
+__global__ void k_mstat_final(const double* __restrict__ partial, int nparts, double* __restrict__ out4) {
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int p = 0; p < nparts; ++p) v += partial[(size_t)p * 4 + threadIdx.x];
+    out4[threadIdx.x] = v;
+  }
+}
+// sums4 = global {sum r p, sum p^2, sum p}; statics3 = global {sum r, sum r^2, |Omega|}  ->  the 7 metric sums, with
+// sum e^2 = sum r^2 - 2 sum r p + sum p^2.  The subtraction loses log10(sum r^2 / sum e^2) digits, so when the fit
+// is closer than `guard` (relative), *direct_flag is raised and the caller's direct pass over R replaces the result.
+__global__ void k_metrics_from_sums(const double* __restrict__ sums4, const double* __restrict__ statics3, double guard,
+                                    double* __restrict__ out8, int* __restrict__ direct_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double rp = sums4[0], pp = sums4[1], sp = sums4[2], r = statics3[0], r2 = statics3[1], n = statics3[2];
+  const double e2 = (r2 - rp) + (pp - rp);
+  out8[0] = e2; out8[1] = sp; out8[2] = pp; out8[3] = rp; out8[4] = r; out8[5] = r2; out8[6] = n; out8[7] = 0.0;
+  *direct_flag = !(e2 > guard * r2) ? 1 : 0;            // also raised for NaN
+}
+// if *flag: out8 = direct8 (global sums of the direct pass)
+__global__ void k_select_metrics(const int* __restrict__ flag, const double* __restrict__ direct8, double* __restrict__ out8) {
+  if (*flag && threadIdx.x < 8) out8[threadIdx.x] = direct8[threadIdx.x];
+}
+
 // deterministic sum of `n` partial vectors of width 8 -> out[8]
-__global__ void k_reduce8(const double* __restrict__ partials, int n, double* __restrict__ out) {
+__global__ void k_reduce8(const double* __restrict__ partials, int n, double* __restrict__ out,
+                          const int* __restrict__ run_flag = nullptr) {
+  if (run_flag && *run_flag == 0) return;
   __shared__ double red[256][8];
   double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = threadIdx.x; i < n; i += 256)
@@ -490,23 +575,43 @@ int launch_row_solve(const RowSolveArgs& a, cudaStream_t st) {
 // partials must hold (ceil(rows/128) * nseg) * 8 doubles; out8 receives the reduced sums.  statics3 != NULL selects
 // the lean kernel (training mask: {sum r, sum r^2, |Omega|} known).
 int launch_masked_metrics(const double* R, const uint32_t* bits, int rows, int ld, const double* Ap, const double* Bp,
-                          int K, int nseg, const double* statics3, double* partials, double* out8, cudaStream_t st) {
+                          int K, int nseg, const double* statics3, double* partials, double* out8, const int* run_flag,
+                          cudaStream_t st) {
   const int KP = 8 * tiles_for(K);
   const int ks = (K + 3) / 4;
   const int chm = ks <= 8 ? 128 : 64;
   const int seg_cols = round_up((ld + nseg - 1) / nseg, chm);
   dim3 grid((rows + 127) / 128, nseg);
   switch (ks) {
-#define BNMTF_MM(N) case N: if (statics3) k_masked_metrics<N, false><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials); \
-                            else k_masked_metrics<N, true><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials); break;
+#define BNMTF_MM(N) case N: if (statics3) k_masked_metrics<N, false><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials, run_flag); \
+                            else k_masked_metrics<N, true><<<grid, 256, 0, st>>>(R, bits, rows, ld, Ap, Bp, K, KP, seg_cols, partials, run_flag); break;
     BNMTF_MM(1) BNMTF_MM(2) BNMTF_MM(3) BNMTF_MM(4) BNMTF_MM(5) BNMTF_MM(6) BNMTF_MM(7) BNMTF_MM(8)
     BNMTF_MM(9) BNMTF_MM(10) BNMTF_MM(11) BNMTF_MM(12) BNMTF_MM(13) BNMTF_MM(14) BNMTF_MM(15) BNMTF_MM(16)
 #undef BNMTF_MM
     default: set_error("masked_metrics: K=%d out of range", K); return -2;
   }
-  k_reduce8<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out8);
-  if (statics3) k_fill_static_sums<<<1, 32, 0, st>>>(out8, statics3);
+  k_reduce8<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out8, run_flag);
+  if (statics3) k_fill_static_sums<<<1, 32, 0, st>>>(out8, statics3, run_flag);
   return check_launch("masked_metrics");
+}
+
+// mstat: rows x 4 from the row solver -> out4 (this rank's sums); partial: >= 64*4 doubles
+int launch_mstat_reduce(const double* mstat, int rows, double* partial, double* out4, cudaStream_t st) {
+  int nparts = (rows + 255) / 256;
+  if (nparts > 64) nparts = 64;
+  if (nparts < 1) nparts = 1;
+  k_mstat_partial<<<nparts, 256, 0, st>>>(mstat, rows, partial);
+  k_mstat_final<<<1, 32, 0, st>>>(partial, nparts, out4);
+  return check_launch("mstat_reduce");
+}
+int launch_metrics_from_sums(const double* sums4, const double* statics3, double guard, double* out8, int* direct_flag,
+                             cudaStream_t st) {
+  k_metrics_from_sums<<<1, 32, 0, st>>>(sums4, statics3, guard, out8, direct_flag);
+  return check_launch("metrics_from_sums");
+}
+int launch_select_metrics(const int* flag, const double* direct8, double* out8, cudaStream_t st) {
+  k_select_metrics<<<1, 32, 0, st>>>(flag, direct8, out8);
+  return check_launch("select_metrics");
 }
 
 int launch_vb_factor_terms(const double* ex, const double* var, const double* mu, const double* tauf,

@@ -9,6 +9,8 @@ Multi-GPU layout ("dual R / R^T"): rank p owns rows [lo_I, lo_I+cnt_I) of R for 
 phase, so each rank runs the same kernels on its shard and the only exchanges per sweep are an all-gather of the new
 factor rows after each phase and one all-reduce of the metric / ELBO partial sums.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -177,8 +179,21 @@ class Factor:
 class BNMFEngine:
     """All device work of bnmf_gibbs_optimised / bnmf_vb_optimised / nmf_icm for one (R, M, K)."""
 
-    def __init__(self, dataset, K, mode, alpha, beta, seed=0, comm=None):
+    def __init__(self, dataset, K, mode, alpha, beta, seed=0, comm=None, gram=None):
         self.ds, self.K, self.mode = dataset, int(K), mode
+        # per-row Gram statistics: "umma" = tcgen05 fixed-point kernel (csrc/gram_umma.cu), "dmma" = fp64 mma.sync kernel
+        self.gram = gram or os.environ.get("BNMTF_GRAM", "umma")
+        assert self.gram in ("umma", "dmma")
+        # training metrics of a sweep: "stats" = from the column-phase statistics (no third pass over R; the direct
+        # pass runs only when the device-side cancellation guard trips), "direct" = always the pass over R
+        self.metrics_mode = os.environ.get("BNMTF_METRICS", "stats" if self.gram == "umma" else "direct")
+        self.guard = 1e-5
+        # 0: the two statistics kernels of a phase run back to back; 1/2 (experimental): the tcgen05 Gram kernel runs on a
+        # high-priority second stream beside the R-streaming kernel.  Measured on B200: no gain (the two kernels do not
+        # become co-resident: different shared-memory carveouts; forcing the same carveout slows the streaming kernel)
+        self.overlap = int(os.environ.get("BNMTF_OVERLAP", "0")) if self.gram == "umma" else 0
+        self.umma_stages = int(os.environ.get("BNMTF_UMMA_STAGES", "3" if self.overlap else "0"))
+        self._side = None
         self.m = MODE[mode]
         self.vb = mode == "vb"
         self.alpha, self.beta, self.seed = float(alpha), float(beta), int(seed) & (2 ** 64 - 1)
@@ -204,8 +219,18 @@ class BNMFEngine:
             rows = max(1, self.loc[side][1])
             rb = (rows + 127) // 128
             nrx = max(1, min(ld // 128, -(-2664 // rb)))
-            gb = (rows + 7) // 8
-            ng = max(1, min(-(-(ld // 32) // 32), -(-592 // gb)))
+            if self.gram == "umma":
+                # CTAs = row blocks x column chunks x segments; aim for ~10 waves of one CTA per SM
+                tile = 128 if ld >= 4096 else 64
+                nch = -(-(K * (K + 1) // 2 + (K if self.vb else 0)) // 73)
+                ktiles = -(-ld // tile)
+                ng = max(1, min(ktiles, round(1480 / (rb * nch))))
+                ng = -(-ktiles // -(-ktiles // ng))      # no empty segments
+                self.umma_tile = getattr(self, "umma_tile", {})
+                self.umma_tile[side] = tile
+            else:
+                gb = (rows + 7) // 8
+                ng = max(1, min(-(-(ld // 32) // 32), -(-592 // gb)))
             nm = max(1, min(ld // 128, -(-1776 // rb)))
             self.nseg[side] = (nrx, ng, nm)
         rI, rJ = max(1, self.loc[0][1]), max(1, self.loc[1][1])
@@ -216,10 +241,15 @@ class BNMFEngine:
         self.Gpart = f64(mg, GL)
         self.SVpart = f64(mg, KP) if self.vb else None
         self.Gfull = f64(GL + KP)
+        if self.gram == "umma":
+            self.ws_bytes = max(_lib.call("bnmtf_gram_umma_workspace_bytes", self.K, int(self.vb), ld)
+                                for ld in (dataset.ldJ, dataset.ldI))
+            self.ws = torch.zeros(self.ws_bytes + 1024, dtype=torch.uint8, device=dev)
+            self.ws_ptr = (self.ws.data_ptr() + 1023) // 1024 * 1024
         self.gscratch = f64(64 * (GL + KP))
         self.extra = f64(max(rI, rJ)) if self.vb else None
         self.red = f64(24)          # [0:8] metric sums, [8:16] factor ELBO terms, [16] VB extra term
-        self.m8, self.el8, self.ex1 = self.red[0:8], self.red[8:16], self.red[16:17]
+        self.m8, self.el8, self.ex1, self.sums4 = self.red[0:8], self.red[8:16], self.red[16:17], self.red[17:21]
         self.mpart = f64(((rI + 127) // 128) * self.nseg[0][2] * 8)
         self.nb_terms = 64
         self.elpart = f64(2 * self.nb_terms * 8) if self.vb else None
@@ -230,8 +260,14 @@ class BNMFEngine:
         if self.loc[0][1] > 0:
             _lib.call("bnmtf_masked_metrics_f64", _ptr(dataset.R), _ptr(dataset.bits), self.loc[0][1], dataset.ldJ,
                       _ptr(self.U.Xp), _ptr(self.V.Xp), self.K, self.nseg[0][2], 0, _ptr(self.mpart), _ptr(self.m8),
-                      _stream())
+                      0, _stream())
             self.statics.copy_(self.m8[4:7])
+        self.statics_global = self.statics.clone()
+        self.comm.allreduce(self.statics_global)
+        self.mstat = f64(max(rI, rJ), 4)
+        self.mstat_part = f64(256)
+        self.m8d = f64(8)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         if dataset.n_obs is None:
             tot = self.statics[2:3].clone()
             self.comm.allreduce(tot)
@@ -256,9 +292,9 @@ class BNMFEngine:
             return self.U, self.V, ds.R, ds.bits, cnt, ds.ldJ, lo
         return self.V, self.U, ds.RT, ds.bitsT, cnt, ds.ldI, lo
 
-    def stats(self, side, need_rx=True):
+    def stats(self, side, need_rx=True, sums=False):
         """Layer-1 passes for one phase: statistics of this rank's rows of R (side 0) / R^T (side 1) w.r.t. the
-        other factor."""
+        other factor.  sums: also the masked column sums of the other factor (for the statistics-based metrics)."""
         me, other, R, bits, rows, ld, lo = self._sides(side)
         nrx, ng, _ = self.nseg[side]
         other.pad()
@@ -267,14 +303,43 @@ class BNMFEngine:
         if self.polarity == 0:
             _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
                       _ptr(self.Gfull), _ptr(self.gscratch), _stream())
-        if need_rx:
-            _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), self.K, nrx,
-                      _ptr(self.RXpart), _stream())
-        _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp), _ptr(other.Vp), self.K,
-                  self.polarity, ng, _ptr(self.Gpart), _ptr(self.SVpart), _stream())
+        rx = lambda: _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), self.K, nrx,
+                               _ptr(self.RXpart), _stream())
+        if need_rx and self.overlap:
+            # the Gram kernel goes to a high-priority stream: its one-per-SM, long-lived CTAs are placed as soon as
+            # a CTA of the streaming kernel retires, and the two then share every SM (tensor pipe | fp64 pipe + HBM)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.ds.device, priority=-1)
+                self._ev = [torch.cuda.Event(), torch.cuda.Event()]
+            main = torch.cuda.current_stream()
+            self._ev[0].record(main)
+            self._side.wait_event(self._ev[0])
+            if self.overlap == 2:
+                rx()
+            with torch.cuda.stream(self._side):
+                self._gram(side, sums)
+                self._ev[1].record(self._side)
+            if self.overlap != 2:
+                rx()
+            main.wait_event(self._ev[1])
+        else:
+            if need_rx:
+                rx()
+            self._gram(side, sums)
+
+    def _gram(self, side, sums=False):
+        me, other, R, bits, rows, ld, lo = self._sides(side)
+        ng = self.nseg[side][1]
+        if self.gram == "umma":
+            _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, other.n, _ptr(other.Xp), _ptr(other.Vp), self.K,
+                      self.polarity, ng, self.umma_tile[side], 1 if sums else 0, self.umma_stages, _ptr(self.Gpart),
+                      _ptr(self.SVpart), self.ws_ptr, self.ws_bytes, _stream())
+        else:
+            _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp), _ptr(other.Vp), self.K,
+                      self.polarity, ng, _ptr(self.Gpart), _ptr(self.SVpart), _stream())
 
     def solve(self, side, order=None, n_order=None, apply=True, minimum_TN=0.0, want_sterm=False, want_extra=False,
-              use_iter=True, gather=True):
+              use_iter=True, gather=True, want_mstat=False):
         me, other, R, bits, rows, ld, lo = self._sides(side)
         nrx, ng, _ = self.nseg[side]
         order_ptr = 0
@@ -292,7 +357,8 @@ class BNMFEngine:
                       _ptr(me.fac, lo), _ptr(me.var, lo), _ptr(me.mu, lo), _ptr(me.tauf, lo), _ptr(me.lam, lo),
                       _ptr(self.scalars), order_ptr, n_order, 1 if apply else 0, float(minimum_TN),
                       self.seed, _ptr(self.iter if use_iter else self.iter_scratch), side, lo,
-                      _ptr(self.sterm, lo) if want_sterm else 0, _ptr(self.extra) if want_extra else 0, _stream())
+                      _ptr(self.sterm, lo) if want_sterm else 0, _ptr(self.extra) if want_extra else 0,
+                      _ptr(self.mstat) if want_mstat else 0, _stream())
         if gather and self.comm.world > 1:
             if apply:
                 self.comm.gather_rows(me.fac, me.part)
@@ -316,16 +382,18 @@ class BNMFEngine:
         self._metrics_padded(self.ds.bits if bits is None else bits)
         self.comm.allreduce(self.m8)
 
-    def _metrics_padded(self, bits):
-        """Local partial sums over this rank's rows of R -> self.m8 (not yet all-reduced)."""
+    def _metrics_padded(self, bits, gated=False):
+        """Local partial sums over this rank's rows of R -> self.m8 (not yet all-reduced).  gated: -> self.m8d, and
+        only if the device flag of the statistics-based metrics is raised."""
         ds = self.ds
         lo, rows = self.loc[0]
         if rows == 0:
-            self.m8.zero_()
+            (self.m8d if gated else self.m8).zero_()
             return
         statics = _ptr(self.statics) if bits is ds.bits else 0
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(bits), rows, ds.ldJ, _ptr(self.U.Xp, lo), _ptr(self.V.Xp),
-                  self.K, self.nseg[0][2], statics, _ptr(self.mpart), _ptr(self.m8), _stream())
+                  self.K, self.nseg[0][2], statics, _ptr(self.mpart), _ptr(self.m8d if gated else self.m8),
+                  _ptr(self.flag) if gated else 0, _stream())
 
     def _vb_terms(self):
         """Local partial sums of the factor-side ELBO terms over this rank's rows of U and V -> self.el8."""
@@ -373,16 +441,30 @@ class BNMFEngine:
     # ---- the sweep ------------------------------------------------------------------------------------
     def sweep(self, minimum_TN=0.0):
         """One iteration of run(): all U columns, all V columns, tau, metrics (reference run() bodies)."""
+        stat = self.metrics_mode == "stats"
         self.stats(0)
         self.solve(0, minimum_TN=minimum_TN)
-        self.stats(1)
-        self.solve(1, minimum_TN=minimum_TN, want_extra=self.vb)
+        self.stats(1, sums=stat)
+        self.solve(1, minimum_TN=minimum_TN, want_extra=self.vb, want_mstat=stat)
         self.V.pad()                      # U's padded image is current (made for the column phase)
-        self._metrics_padded(self.ds.bits)
+        if stat:
+            rows = self.loc[1][1]
+            if rows > 0:
+                _lib.call("bnmtf_mstat_reduce_f64", _ptr(self.mstat), rows, _ptr(self.mstat_part), _ptr(self.sums4), _stream())
+            else:
+                self.sums4.zero_()
+        else:
+            self._metrics_padded(self.ds.bits)
         if self.vb:
             self._vb_extra()
             self._vb_terms()
         self.comm.allreduce(self.red)     # one exchange for metric sums, ELBO terms and the VB extra term
+        if stat:
+            _lib.call("bnmtf_metrics_from_sums_f64", _ptr(self.sums4), _ptr(self.statics_global), self.guard,
+                      _ptr(self.m8), _ptr(self.flag), _stream())
+            self._metrics_padded(self.ds.bits, gated=True)     # returns at once unless the guard tripped
+            self.comm.allreduce(self.m8d)
+            _lib.call("bnmtf_select_metrics_f64", _ptr(self.flag), _ptr(self.m8d), _ptr(self.m8), _stream())
         self.finish(update_tau=True, record=True)
 
     def profile_sweep(self, reps=3):
@@ -410,9 +492,7 @@ class BNMFEngine:
                               _ptr(self.Gfull), _ptr(self.gscratch), _stream())
                 timed("stats_rx", lambda: _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp),
                                                     self.K, nrx, _ptr(self.RXpart), _stream()))
-                timed("stats_gram", lambda: _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp),
-                                                      _ptr(other.Vp), self.K, self.polarity, ng, _ptr(self.Gpart),
-                                                      _ptr(self.SVpart), _stream()))
+                timed("stats_gram", lambda: self._gram(side))
                 timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1, gather=False))
                 self.solve(side, n_order=0, apply=True, gather=True)   # exchange only (no column is updated)
             self.V.pad()

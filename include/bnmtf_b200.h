@@ -82,12 +82,16 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
  * the products X_ja X_jb (and Var_jk) are cut into seven exact 8-bit digits of a 56-bit fixed-point value per
  * column and multiplied with the 0/1 selection matrix of the rows, so the result is the exactly summed,
  * once-rounded value.  cols = number of valid columns (<= ld); tile = 64 or 128 (bytes of the column range staged
- * per pipeline stage); workspace: >= bnmtf_gram_umma_workspace_bytes(K, Vp != NULL, ld) bytes, 1024-byte aligned.
- * Only the entries (a, b < K) of the packed tiles and the first K entries of SVpart are written. */
+ * per pipeline stage); sums != 0 also accumulates the masked column sums of X (slot (k, K) of the packed tiles,
+ * as the ones-column of Xp does in bnmtf_stats_gram_f64; the selected-entry count always goes to slot (K, K));
+ * max_stages > 0 caps the pipeline depth (shared memory left for kernels running concurrently on other streams);
+ * workspace: >= bnmtf_gram_umma_workspace_bytes(K, Vp != NULL, ld) bytes, 1024-byte aligned.
+ * Only the entries (a, b < K), the slots above, and the first K entries of SVpart are written. */
 int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld);
 int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp,
-                              const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, double* Gpart,
-                              double* SVpart /*or NULL*/, void* workspace, int64_t workspace_bytes, void* stream);
+                              const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, int sums,
+                              int max_stages, double* Gpart, double* SVpart /*or NULL*/, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 /* scratch: >= 64 * (bnmtf_gram_len(K) + KP) doubles */
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t n, int K, int64_t dummy_row,
                         double* Gfull, double* scratch, void* stream);
@@ -101,20 +105,35 @@ int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t 
  *   mu,tauf,sterm : optional n x K outputs (conditional mean, precision, masked-sum term)
  *   extra         : optional rows doubles (VB): this row's share of exp_square_diff's variance term
  *   iter,salt,seed: Philox stream = (*iter)*16 + salt; index = (row_offset+row)*K + k
- *   row_offset    : global index of row 0 of the arrays passed (0 unless the rows are sharded across GPUs) */
+ *   row_offset    : global index of row 0 of the arrays passed (0 unless the rows are sharded across GPUs)
+ *   mstat         : optional rows x 4 doubles: {sum r p, sum p^2, sum p, 0} over the observed entries of the row with
+ *                   its factor values after the update, p = fac_i . X_j -- computed from the row's statistics
+ *                   (needs the masked column sums in slot (k, K) of the Gram tiles), no pass over R */
 int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, int polarity,
                        const double* RXpart, const double* Gpart, const double* SVpart, const double* Gfull,
                        double* fac, double* var, double* mu, double* tauf, const double* lambda,
                        const double* scalars, const int* order, int n_order, int apply, double min_tn,
                        uint64_t seed, const uint64_t* iter, uint64_t salt, int64_t row_offset, double* sterm,
-                       double* extra, void* stream);
+                       double* extra, double* mstat, void* stream);
 /* Sums over the set bits of `bits` of {e^2, p, p^2, r p, r, r^2, 1}, p = A_i.B_j  ->  out8 (predict(),
  * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8.
  * statics3 = {sum r, sum r^2, count} of this mask if already known (training mask; selects the lean kernel that
- * only accumulates e^2, p, p^2), else NULL. */
+ * only accumulates e^2, p, p^2), else NULL.  run_flag (device int, or NULL): when given and zero at execution
+ * time the kernels return at once and out8 is left untouched (gated fallback of bnmtf_metrics_from_sums_f64). */
 int bnmtf_masked_metrics_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Ap,
                              const double* Bp, int K, int nseg, const double* statics3, double* partials, double* out8,
-                             void* stream);
+                             const int* run_flag, void* stream);
+/* Training metrics of a sweep from the statistics of its last phase instead of a third pass over R
+ * (predict_while_running, bnmf_gibbs_optimised.py:199-223): mstat (rows x 4, bnmf_row_solve_f64) -> out4 = this
+ * shard's {sum r p, sum p^2, sum p, 0}; partial: >= 256 doubles of scratch. */
+int bnmtf_mstat_reduce_f64(const double* mstat, int64_t rows, double* partial, double* out4, void* stream);
+/* global sums4 + statics3 {sum r, sum r^2, count} -> the seven sums of bnmtf_masked_metrics_f64 with
+ * sum e^2 = sum r^2 - 2 sum r p + sum p^2; *direct_flag = 1 when sum e^2 <= guard * sum r^2 (cancellation too
+ * deep for 1e-9: run the direct pass), else 0. */
+int bnmtf_metrics_from_sums_f64(const double* sums4, const double* statics3, double guard, double* out8, int* direct_flag,
+                                void* stream);
+/* if *flag: out8 = direct8 */
+int bnmtf_select_metrics_f64(const int* flag, const double* direct8, double* out8, void* stream);
 /* Same seven sums for dense contiguous R, P (prediction) and 0/1 (or weight) mask M of n entries each: the
  * compute_MSE / compute_R2 / compute_Rp helpers.  partials: >= nblocks*8 doubles. */
 int bnmtf_dense_metrics_f64(const double* R, const double* P, const double* M, int64_t n, double* partials, int nblocks,

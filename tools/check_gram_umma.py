@@ -14,22 +14,23 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-# rows, cols, K, vb, polarity, nseg, tile, signed, timing reps
+# rows, cols, K, vb, polarity, nseg, tile, signed, timing reps, sums, max_stages
 CASES = [
-    (100, 80, 10, 0, 0, 1, 128, 0, 0),
-    (100, 80, 10, 0, 0, 1, 64, 0, 0),
-    (129, 65, 5, 1, 0, 1, 64, 0, 0),
-    (129, 65, 5, 1, 1, 1, 128, 0, 0),
-    (300, 1000, 20, 1, 0, 2, 64, 0, 0),
-    (300, 1000, 20, 0, 0, 3, 128, 1, 0),
-    (1000, 5000, 20, 1, 0, 1, 64, 1, 0),
-    (700, 3000, 33, 1, 0, 2, 128, 0, 0),
-    (65536, 32768, 20, 0, 0, 1, 64, 0, 3),
-    (65536, 32768, 20, 0, 0, 1, 128, 0, 3),
-    (65536, 32768, 20, 1, 0, 1, 64, 0, 3),
-    (32768, 65536, 20, 0, 0, 2, 64, 0, 3),
-    (32768, 65536, 20, 1, 0, 2, 64, 0, 3),
-    (32768, 65536, 20, 0, 0, 2, 128, 0, 3),
+    (100, 80, 10, 0, 0, 1, 128, 0, 0, 0, 0),
+    (100, 80, 10, 0, 0, 1, 64, 0, 0, 1, 0),
+    (129, 65, 5, 1, 0, 1, 64, 0, 0, 1, 2),
+    (129, 65, 5, 1, 1, 1, 128, 0, 0, 0, 0),
+    (300, 1000, 20, 1, 0, 2, 64, 0, 0, 1, 3),
+    (300, 1000, 20, 0, 0, 3, 128, 1, 0, 1, 0),
+    (1000, 5000, 20, 1, 0, 1, 64, 1, 0, 0, 0),
+    (700, 3000, 33, 1, 0, 2, 128, 0, 0, 1, 0),
+    (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 0),
+    (65536, 32768, 20, 0, 0, 1, 64, 0, 3, 0, 4),
+    (65536, 32768, 20, 0, 0, 1, 64, 0, 3, 0, 3),
+    (65536, 32768, 20, 0, 0, 1, 64, 0, 3, 0, 2),
+    (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 1),
+    (32768, 65536, 20, 0, 0, 2, 128, 0, 3, 1, 0),
+    (32768, 65536, 20, 1, 0, 2, 128, 0, 3, 1, 0),
 ]
 
 
@@ -38,7 +39,7 @@ def run_case(idx):
     import torch
     from bnmtf_b200 import _lib
     from bnmtf_b200.engine import _ptr, _stream, ld_for, kp_for, gram_len
-    rows, cols, K, vb, pol, nseg, tile, signed, reps = CASES[idx]
+    rows, cols, K, vb, pol, nseg, tile, signed, reps, sums, stages = CASES[idx]
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + idx)
@@ -72,10 +73,11 @@ def run_case(idx):
 
     def umma():
         _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, cols, _ptr(Xp), _ptr(Vp) if vb else 0, K, pol, nseg,
-                  tile, _ptr(G1), _ptr(S1), wsp, wsb, _stream())
+                  tile, sums, stages, _ptr(G1), _ptr(S1), wsp, wsb, _stream())
     umma()
     torch.cuda.synchronize()
-    out = {"case": idx, "shape": [rows, cols, K], "vb": vb, "pol": pol, "nseg": nseg, "tile": tile, "signed": signed}
+    out = {"case": idx, "shape": [rows, cols, K], "vb": vb, "pol": pol, "nseg": nseg, "tile": tile, "signed": signed,
+           "sums": sums, "stages": stages}
     # reference on the first chunk of rows: W @ P in fp64
     nr = min(rows, chunk)
     W = M0[:nr] if pol == 1 else 1.0 - M0[:nr]
@@ -97,6 +99,11 @@ def run_case(idx):
     idx_ba = torch.tensor([tile_index(int(b), int(a)) if a // 8 == b // 8 else tile_index(int(a), int(b))
                            for a, b in zip(ia, ib)], device=dev)
     out["mirror"] = float((Gu[:, idx_ba] - got).abs().max())
+    if sums:
+        Cref = W @ X
+        idx_k = torch.tensor([tile_index(k, K) for k in range(K)], device=dev)
+        out["sums_vs_ref"] = float(((Gu[:, idx_k] - Cref).abs() / Cref.abs().max(0).values.clamp_min(1e-300)).max())
+    out["count_err"] = float((Gu[:, tile_index(K, K)] - W.sum(1)).abs().max())
     if vb:
         Sref = W @ Var
         Su = S1.view(nseg, rows, KP).sum(0)[:nr, :K]
