@@ -25,7 +25,12 @@ int check_launch(const char* what) {
 }
 
 // ---- forward declarations of the launchers in the other translation units -----------------------------
-int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int, int, double*, cudaStream_t);
+int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int, int, double*, const int*, cudaStream_t);
+long long rxu_planes_bytes(long long, long long);
+long long rxu_workspace_bytes(int, long long);
+int launch_rxu_pack(const double*, const uint32_t*, int, int, uint8_t*, double*, int*, cudaStream_t);
+int launch_stats_rx_umma(const uint8_t*, const double*, const double*, const uint32_t*, int, int, int, const double*, int, int,
+                         double*, void*, long long, cudaStream_t);
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 long long umma_workspace_bytes(int, int, long long);
@@ -155,7 +160,30 @@ int bnmtf_pad_factor_f64(const double* X, const double* Var, int64_t n, int K, i
 int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, int K,
                        int nseg, double* RXpart, void* stream) {
   if (check_k(K)) return -2;
-  return launch_stats_rx(R, bits, (int)rows, (int)ld, Xp, K, nseg, RXpart, ST(stream));
+  return launch_stats_rx(R, bits, (int)rows, (int)ld, Xp, K, nseg, RXpart, nullptr, ST(stream));
+}
+
+int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld) {
+  if (rows <= 0 || ld <= 0 || ld % 64) return -1;
+  return rxu_planes_bytes(rows, ld);
+}
+
+int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
+                             double* rscale, int32_t* rexp_scratch, void* stream) {
+  return launch_rxu_pack(R, bits, (int)rows, (int)ld, planes, rscale, rexp_scratch, ST(stream));
+}
+
+int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld) {
+  if (K < 1 || K > 32 || ld <= 0) return -1;
+  return rxu_workspace_bytes(K, ld);
+}
+
+int bnmtf_stats_rx_umma_f64(const uint8_t* planes, const double* rscale, const double* R, const uint32_t* bits,
+                            int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, double* RXpart,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+  if (check_k(K)) return -2;
+  return launch_stats_rx_umma(planes, rscale, R, bits, (int)rows, (int)ld, (int)cols, Xp, K, nseg, RXpart, workspace,
+                              workspace_bytes, ST(stream));
 }
 
 int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp, int K,

@@ -29,7 +29,8 @@ namespace bnmtf {
 template <int NT>
 __global__ void __launch_bounds__(256, 3) k_stats_rx(const double* __restrict__ R, const uint32_t* __restrict__ bits,
                                                  int rows, int ld, const double* __restrict__ Xp, int seg_cols,
-                                                 double* __restrict__ out) {
+                                                 double* __restrict__ out, const int* __restrict__ run_flag) {
+  if (run_flag && *run_flag == 0) return;      // gated fallback of the tcgen05 kernel (rx_umma.cu)
   constexpr int KP = 8 * NT;
   constexpr int CH = NT <= 4 ? 128 : 64;   // columns of X staged per barrier pair (<= 34 KB of shared memory)
   constexpr int XS = KP + 1;  // odd stride: the 4 t-groups of a half warp land on disjoint 8-bank groups
@@ -304,12 +305,12 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int nparts, i
   }
 
 int launch_stats_rx(const double* R, const uint32_t* bits, int rows, int ld, const double* Xp, int K, int nseg,
-                    double* out, cudaStream_t st) {
+                    double* out, const int* run_flag, cudaStream_t st) {
   if (rows <= 0 || ld <= 0 || ld % 64 || nseg <= 0) { set_error("stats_rx: bad shape rows=%d ld=%d nseg=%d", rows, ld, nseg); return -2; }
   const int nt = tiles_for(K);
   const int seg_cols = round_up((ld + nseg - 1) / nseg, 64);
   dim3 grid((rows + 127) / 128, nseg);
-  BNMTF_DISPATCH_NT(nt, (k_stats_rx<NT><<<grid, 256, 0, st>>>(R, bits, rows, ld, Xp, seg_cols, out)));
+  BNMTF_DISPATCH_NT(nt, (k_stats_rx<NT><<<grid, 256, 0, st>>>(R, bits, rows, ld, Xp, seg_cols, out, run_flag)));
   return check_launch("stats_rx");
 }
 

@@ -100,6 +100,7 @@ class Dataset:
         self.world, self.rank = world, rank
         self.R = self.bits = self.RT = self.bitsT = None
         self.n_obs = None          # global |Omega|
+        self.planes = {}           # side -> (digit planes (uint8), row scales) for the tcgen05 R.X kernel, built on demand
 
     def _pack(self, R, M, rows, cols, ld):
         out = torch.zeros((max(rows, 1), ld), dtype=torch.float64, device=self.device)
@@ -149,6 +150,27 @@ class Dataset:
         _lib.call("bnmtf_transpose_dataset_f64", _ptr(self.R), _ptr(self.bits), I, J, self.ldJ,
                   _ptr(self.RT), _ptr(self.bitsT), self.ldI, _stream())
 
+    def ensure_planes(self, side):
+        """Seven 8-bit digit planes of this rank's rows of R (side 0) / R^T (side 1): the A operand of
+        bnmtf_stats_rx_umma_f64.  Built once per dataset (14 GiB per orientation at 65536 x 32768)."""
+        if side not in self.planes:
+            R, bits = (self.R, self.bits) if side == 0 else (self.RT, self.bitsT)
+            rows = (self.partI if side == 0 else self.partJ).cnt()
+            ld = self.ldJ if side == 0 else self.ldI
+            if rows == 0:
+                self.planes[side] = (None, None)
+                return self.planes[side]
+            nbytes = _lib.call("bnmtf_rx_planes_bytes", rows, ld)
+            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-buf.data_ptr()) % 1024
+            planes = buf[off:off + nbytes]
+            rscale = torch.empty(rows, dtype=torch.float64, device=self.device)
+            rexp = torch.empty(rows, dtype=torch.int32, device=self.device)
+            _lib.call("bnmtf_rx_planes_pack_f64", _ptr(R), _ptr(bits), rows, ld, planes.data_ptr(), _ptr(rscale),
+                      _ptr(rexp), _stream())
+            self.planes[side] = (planes, rscale, buf)
+        return self.planes[side]
+
     def pack_mask(self, M):
         """Bit-pack this rank's rows of another I x J 0/1 mask (predict(M_pred))."""
         lo, cnt = self.partI.lo(), self.partI.cnt()
@@ -186,6 +208,9 @@ class BNMFEngine:
         assert self.gram in ("umma", "dmma")
         # training metrics of a sweep: "stats" = from the column-phase statistics (no third pass over R; the direct
         # pass runs only when the device-side cancellation guard trips), "direct" = always the pass over R
+        # masked R.X statistics: "umma" = tcgen05 digit-plane kernel (csrc/rx_umma.cu, K <= 32), "dmma" = fp64 mma.sync
+        self.rx = os.environ.get("BNMTF_RX", "umma" if (self.gram == "umma" and self.K <= 32) else "dmma")
+        assert self.rx in ("umma", "dmma") and (self.rx == "dmma" or self.K <= 32)
         self.metrics_mode = os.environ.get("BNMTF_METRICS", "stats" if self.gram == "umma" else "direct")
         self.guard = 1e-5
         # 0: the two statistics kernels of a phase run back to back; 1/2 (experimental): the tcgen05 Gram kernel runs on a
@@ -218,7 +243,12 @@ class BNMFEngine:
         for side, ld in ((0, dataset.ldJ), (1, dataset.ldI)):
             rows = max(1, self.loc[side][1])
             rb = (rows + 127) // 128
-            nrx = max(1, min(ld // 128, -(-2664 // rb)))
+            if self.rx == "umma":
+                kt64 = ld // 64
+                nrx = max(1, min(kt64, round(1480 / rb)))
+                nrx = -(-kt64 // -(-kt64 // nrx))        # no empty segments
+            else:
+                nrx = max(1, min(ld // 128, -(-2664 // rb)))
             if self.gram == "umma":
                 # CTAs = row blocks x column chunks x segments; aim for ~10 waves of one CTA per SM
                 tile = 128 if ld >= 4096 else 64
@@ -241,6 +271,12 @@ class BNMFEngine:
         self.Gpart = f64(mg, GL)
         self.SVpart = f64(mg, KP) if self.vb else None
         self.Gfull = f64(GL + KP)
+        if self.rx == "umma":
+            self.wsrx_bytes = max(_lib.call("bnmtf_rx_umma_workspace_bytes", self.K, ld) for ld in (dataset.ldJ, dataset.ldI))
+            self.wsrx = torch.zeros(self.wsrx_bytes + 1024, dtype=torch.uint8, device=dev)
+            self.wsrx_ptr = (self.wsrx.data_ptr() + 1023) // 1024 * 1024
+            for side in (0, 1):
+                dataset.ensure_planes(side)
         if self.gram == "umma":
             self.ws_bytes = max(_lib.call("bnmtf_gram_umma_workspace_bytes", self.K, int(self.vb), ld)
                                 for ld in (dataset.ldJ, dataset.ldI))
@@ -303,8 +339,7 @@ class BNMFEngine:
         if self.polarity == 0:
             _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
                       _ptr(self.Gfull), _ptr(self.gscratch), _stream())
-        rx = lambda: _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), self.K, nrx,
-                               _ptr(self.RXpart), _stream())
+        rx = lambda: self._rx(side)
         if need_rx and self.overlap:
             # the Gram kernel goes to a high-priority stream: its one-per-SM, long-lived CTAs are placed as soon as
             # a CTA of the streaming kernel retires, and the two then share every SM (tensor pipe | fp64 pipe + HBM)
@@ -326,6 +361,17 @@ class BNMFEngine:
             if need_rx:
                 rx()
             self._gram(side, sums)
+
+    def _rx(self, side):
+        me, other, R, bits, rows, ld, lo = self._sides(side)
+        nrx = self.nseg[side][0]
+        if self.rx == "umma":
+            planes, rscale = self.ds.ensure_planes(side)[:2]
+            _lib.call("bnmtf_stats_rx_umma_f64", planes.data_ptr(), _ptr(rscale), _ptr(R), _ptr(bits), rows, ld, other.n,
+                      _ptr(other.Xp), self.K, nrx, _ptr(self.RXpart), self.wsrx_ptr, self.wsrx_bytes, _stream())
+        else:
+            _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), self.K, nrx,
+                      _ptr(self.RXpart), _stream())
 
     def _gram(self, side, sums=False):
         me, other, R, bits, rows, ld, lo = self._sides(side)
@@ -490,8 +536,7 @@ class BNMFEngine:
                 if self.polarity == 0:
                     _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
                               _ptr(self.Gfull), _ptr(self.gscratch), _stream())
-                timed("stats_rx", lambda: _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp),
-                                                    self.K, nrx, _ptr(self.RXpart), _stream()))
+                timed("stats_rx", lambda: self._rx(side))
                 timed("stats_gram", lambda: self._gram(side))
                 timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1, gather=False))
                 self.solve(side, n_order=0, apply=True, gather=True)   # exchange only (no column is updated)

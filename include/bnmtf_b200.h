@@ -74,6 +74,21 @@ int bnmtf_pad_factor_f64(const double* X, const double* Var /*or NULL*/, int64_t
 /* ---- layer 1: masked row statistics (the streaming passes over R) ------------------------------------- */
 int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, int K,
                        int nseg, double* RXpart, void* stream);
+/* The same product on the 5th-generation tensor cores (tcgen05.mma kind::i8, csrc/rx_umma.cu).  The dataset is
+ * packed ONCE into seven 8-bit digit planes of a per-row 56-bit fixed-point image of the observed entries
+ * (bnmtf_rx_planes_pack_f64: planes = bnmtf_rx_planes_bytes(rows, ld) bytes, 1024-byte aligned; rscale = rows doubles;
+ * rexp_scratch = rows int32), 7 instead of 8.125 bytes per entry streamed per phase.  Per call the factor is cut into
+ * digits too (K <= 32, entries >= 0) and the digit products are accumulated exactly in int32 tensor memory.  If the
+ * factor has a negative or non-finite entry, a device-side flag routes the call to the fp64 kernel above (R, bits are
+ * only read in that case); RXpart always receives nseg valid partial results.
+ * workspace: >= bnmtf_rx_umma_workspace_bytes(K, ld) bytes, 1024-byte aligned. */
+int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld);
+int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
+                             double* rscale, int32_t* rexp_scratch, void* stream);
+int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld);
+int bnmtf_stats_rx_umma_f64(const uint8_t* planes, const double* rscale, const double* R, const uint32_t* bits,
+                            int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, double* RXpart,
+                            void* workspace, int64_t workspace_bytes, void* stream);
 /* polarity 0: accumulate over the MISSING entries of each row (cheap when most entries are observed; the solver
  * subtracts from Gfull), 1: over the OBSERVED entries. */
 int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp /*or NULL*/,
