@@ -93,6 +93,61 @@ def make_synthetic(I, J, K, device, seed=0, row_lo=0, row_hi=None, tile=4096):
     return R, bits, n_obs
 
 
+def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
+    """Roofline block of the JSON line.  The dominant kernel of a sweep is the per-row Gram
+    (tcgen05 int8 tensor pipe); the R-streaming kernel is reported beside it against the HBM roof.  world > 1: the
+    per-launch figures are per rank (1/world of the entries), the whole-sweep HBM figure is against world x peak."""
+    hbm_peak, hbm_kind = measured_peaks()
+    N = float(I) * J / world
+    n_obs = n_obs / world
+    e0 = next(iter(engs.values()))
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            bf16 = float(json.load(fh)["bf16_tflops"])
+        bf16_kind = "measured"
+    except Exception:
+        bf16, bf16_kind = 1590.0, "fallback"
+    b_alg_sweep = 2.0 * N * world * 8.125
+    out = {"kernel_ms": prof,
+           "sweep_hbm": {"algorithmic_bytes_per_sweep": b_alg_sweep, "achieved_gbs": b_alg_sweep / sweep_s / 1e9,
+                         "peak_gbs": hbm_peak * world, "peak_kind": hbm_kind,
+                         "frac": b_alg_sweep / sweep_s / 1e9 / (hbm_peak * world)}}
+    if e0.gram == "umma":
+        # exact fixed-point Gram: 0/1 selection matrix (rows x cols) times seven int8 digit slices of K(K+1)/2 (+K
+        # variance, VB) (+K column-sum, metrics phase) product columns; algorithmic ops = 2 * rows * cols * digit columns
+        ops, ach = {}, {}
+        for k, e in engs.items():
+            nc = K * (K + 1) // 2 + (K if e.vb else 0)
+            ops[k] = 2.0 * N * (nc + 0.5 * (K if e.metrics_mode == "stats" else 0)) * 7
+            ach[k] = ops[k] / (prof[k]["stats_gram"] * 1e-3) / 1e12
+        mean_ach = sum(ach.values()) / len(ach)
+        peak = 2.0 * bf16
+        out.update({"bound": "tensor", "kernel": "k_gram_umma (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed)",
+                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": 1.5e9,
+                    "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is twice "
+                                   "the bf16 rate; ops are int8 multiply-adds x 2" % bf16_kind,
+                    "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary_umma.txt",
+                    "per_mode_achieved_tops": ach})
+    else:
+        miss = N - n_obs
+        pairs = K * (K + 1) / 2.0
+        fl = {"gibbs": miss * (pairs + K) * 2.0, "vb": miss * (pairs + 2 * K) * 2.0}
+        ach = {k: fl[k] / (prof[k]["stats_gram"] * 1e-3) / 1e12 for k in engs}
+        mean_ach = sum(ach.values()) / len(ach)
+        out.update({"bound": "tensor", "kernel": "k_stats_gram (fp64 DMMA, mma.sync.m8n8k4.f64)", "achieved": mean_ach,
+                    "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": mean_ach / FP64_PEAK_TFLOPS, "traffic": None,
+                    "peak_source": "fp64 DMMA peak measured by tools/microbench/fp64_pipes.cu"})
+    # the HBM-bound kernel: streams R once per phase (7 digit-plane bytes per entry for the tcgen05 kernel,
+    # 8 + 1/8 bytes for the fp64 kernel)
+    bpe = 7.0 if e0.rx == "umma" else 8.125
+    rx_ms = sum(prof[k]["stats_rx"] for k in engs) / len(engs)
+    rx_gbs = N * bpe / (rx_ms * 1e-3) / 1e9
+    out["hbm_kernel"] = {"bound": "hbm", "kernel": "k_rx_umma (tcgen05 digit planes)" if e0.rx == "umma" else "k_stats_rx (fp64 DMMA)",
+                         "achieved": rx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rx_gbs / hbm_peak,
+                         "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)"}
+    return out
+
+
 def cpu_baseline(K, seed=0, budget_s=20.0, sizes=((1024, 512), (2048, 1024))):
     """Time the CPU oracle (numpy restatement of the reference's sweep, same per-column full-GEMM cost structure) on
     bounded samples of the same synthetic workload and extrapolate linearly in I*J to the full shape."""
@@ -179,7 +234,7 @@ def main():
 
     if world > 1:
         from bnmtf_b200 import parallel
-        return parallel.bench_sharded(args, rank, world, device, ClockSampler, measured_peaks)
+        return parallel.bench_sharded(args, rank, world, device, ClockSampler, measured_peaks, build_roofline)
 
     R, bits, n_obs = make_synthetic(I, J, K, device)
     ds = engine.Dataset.from_device(R, bits, I, J, n_obs=n_obs)
@@ -245,27 +300,8 @@ def main():
                        "R itself (16 GiB) is resident like a dataset"}
 
     # ---- roofline ------------------------------------------------------------------------------------------------
-    hbm_peak, hbm_kind = measured_peaks()
+    roofline = build_roofline(engs, prof, I, J, K, n_obs, total_ms / 1e3 / (2.0 * args.steps))
     N = float(I) * J
-    miss = N - n_obs
-    pairs = K * (K + 1) / 2.0
-    # dominant kernel: the masked Gram pass (fp64 tensor pipe).  Algorithmic flops per launch (one phase):
-    # per missing entry K(K+1)/2 pair FMAs + K column-sum adds (+K variance adds for VB), 2 flop each.
-    gram_flops = {"gibbs": miss * (pairs + K) * 2.0, "vb": miss * (pairs + 2 * K) * 2.0}
-    dom = "stats_gram"
-    ach = {k: gram_flops[k] / (prof[k][dom] * 1e-3) / 1e12 for k in engs}
-    mean_ach = sum(ach.values()) / len(ach)
-    b_alg_sweep = 2.0 * N * 8.125
-    sweep_s = total_ms / 1e3 / (2.0 * args.steps)
-    roofline = {"bound": "tensor", "kernel": "k_stats_gram (fp64 DMMA, mma.sync.m8n8k4.f64)", "achieved": mean_ach,
-                "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": mean_ach / FP64_PEAK_TFLOPS, "traffic": None,
-                "peak_source": "fp64 DMMA peak measured on this pool's B200 by tools/microbench/fp64_pipes.cu "
-                               "(MEASURED_PEAKS.json has no fp64 entry)",
-                "per_mode_achieved_tflops": ach,
-                "kernel_ms": prof,
-                "sweep_hbm": {"algorithmic_bytes_per_sweep": b_alg_sweep, "achieved_gbs": b_alg_sweep / sweep_s / 1e9,
-                              "peak_gbs": hbm_peak, "peak_kind": hbm_kind,
-                              "frac": b_alg_sweep / sweep_s / 1e9 / hbm_peak}}
     line = {"metric": "BNMF Gibbs+VB sweeps/sec at %dx%d K=%d" % (I, J, K), "value": value, "unit": "sweeps/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / (2.0 * args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

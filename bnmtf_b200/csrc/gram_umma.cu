@@ -24,13 +24,15 @@
 //
 // Replaces the fp64 DMMA kernel k_stats_gram for the statistics of bnmf_gibbs_optimised.py:167-177,
 // bnmf_vb_optimised.py:189-195 (see stats.cu for the role of the statistics).
+#include <cstdlib>
 #include "umma.cuh"
 
 namespace bnmtf {
 
 constexpr int UG_SLICES = 7;
 constexpr int UG_ROWS = 128;     // rows per CTA = UMMA M
-constexpr int UG_THREADS = 192;
+constexpr int UG_EXP_WARPS = 8;   // mask-expander / epilogue warps (two threads per row)
+constexpr int UG_THREADS = (UG_EXP_WARPS + 2) * 32;
 
 struct UmmaPlan {
   int K, vb, sums;
@@ -173,6 +175,7 @@ struct UmmaGramArgs {
   double* Gout; double* SVout;
   int KP, gl;       // padded factor width, doubles per Gram record (NTP*64)
   int stages;
+  int dbg;   // timing experiments only: 1 = skip TMA loads after the first fill, 2 = skip the A-tile stores
 };
 
 template <int KT>
@@ -185,7 +188,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   const int stages = a.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);   // full[stages], empty[stages], accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
-  uint16_t* pair_tab = reinterpret_cast<uint16_t*>(tmem_slot + 2);   // [cpc] (a<<8 | b), b = 0xff: variance, 0xfd: sum
+  int* cnt_smem = reinterpret_cast<int*>(tmem_slot + 2);           // [256]
+  uint16_t* pair_tab = reinterpret_cast<uint16_t*>(cnt_smem + UG_EXP_WARPS * 32);   // [cpc] (a<<8 | b), b = 0xff: variance, 0xfd: sum
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
@@ -197,13 +201,13 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   const int kt_end = min(a.ktiles, kt_begin + a.tiles_per_seg);
   const int ntile = kt_end - kt_begin;                 // >= 1 by construction of the grid
 
-  if (warp == 4 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), 128 + 1); mbar_init(EMPTY_BAR(s), 1); }
+  if (warp == UG_EXP_WARPS && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), UG_EXP_WARPS * 32 + 1); mbar_init(EMPTY_BAR(s), 1); }
     mbar_init(ACCUM_BAR, 1);
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
-  if (warp == 5) {
+  if (warp == UG_EXP_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -218,65 +222,70 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ================= mask expander, then epilogue: thread <-> row =================
-    const int row = rb * UG_ROWS + tid;
+  if (warp < UG_EXP_WARPS) {
+    // ================= mask expanders, then epilogue: two threads per row (each owns half of every tile) =========
+    const int r = tid & (UG_ROWS - 1), half = tid >> 7;
+    const int row = rb * UG_ROWS + r;
     const bool live = row < a.rows;
     const uint32_t* mrow = a.bits + (size_t)(live ? row : 0) * a.wpr;
-    constexpr int WPT = KT / 32;                       // mask words per tile
+    constexpr int WPT = KT / 64;                       // mask words per thread and tile
+    constexpr int CPT = KT / 32;                       // 16-byte chunks per thread and tile
     const uint32_t flip = a.polarity ? 0u : 0xffffffffu;
     // byte offset of this row inside an A tile, and its swizzle key (16-byte chunk index XOR)
-    const uint32_t row_off = (uint32_t)(tid >> 3) * (8 * KT) + (uint32_t)(tid & 7) * KT;
-    const uint32_t key = KT == 128 ? (uint32_t)(tid & 7) : (uint32_t)((tid >> 1) & 3);
+    const uint32_t row_off = (uint32_t)(r >> 3) * (8 * KT) + (uint32_t)(r & 7) * KT;
+    const uint32_t key = KT == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
     int cnt = 0;
     uint32_t nxt[WPT];
     {
-      const int w0 = kt_begin * WPT;
+      const int w0 = kt_begin * (KT / 32) + half * WPT;
 #pragma unroll
       for (int i = 0; i < WPT; ++i) nxt[i] = (live && w0 + i < a.wpr) ? mrow[w0 + i] : 0u;
     }
     for (int it = 0; it < ntile; ++it) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
-      uint32_t w[WPT];
-      const int wbase = (kt_begin + it) * WPT;
+      const int wbase = (kt_begin + it) * (KT / 32) + half * WPT;
+      uint32_t y[CPT][4];
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
         uint32_t v = nxt[i] ^ flip;
         const int jb = (wbase + i) * 32;               // first column of this word
         if (jb + 32 > a.cols) v = jb >= a.cols ? 0u : (v & ((1u << (a.cols - jb)) - 1u));
-        w[i] = live ? v : 0u;
-        cnt += __popc(w[i]);
+        v = live ? v : 0u;
+        cnt += __popc(v);
+        // 4 mask bits -> 4 bytes: bit k of the nibble lands on bit 8k of (nibble * 0x00204081)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[2 * i + (q >> 2)][q & 3] = (((v >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
       }
       if (it + 1 < ntile) {
-        const int wn = wbase + WPT;
+        const int wn = wbase + (KT / 32);
 #pragma unroll
         for (int i = 0; i < WPT; ++i) nxt[i] = (live && wn + i < a.wpr) ? mrow[wn + i] : 0u;
       }
-      mbar_wait(EMPTY_BAR(s), ph ^ 1u);
+      mbar_wait(EMPTY_BAR(s), ph ^ 1u);                // the expansion above is done while the stage is still busy
       const uint32_t abase = smem_base + (uint32_t)s * STAGE + row_off;
+      if (!((a.dbg & 2) && it >= stages))
 #pragma unroll
-      for (int c16 = 0; c16 < KT / 16; ++c16) {
-        const uint32_t h = (w[c16 >> 1] >> (16 * (c16 & 1))) & 0xffffu;
-        const uint32_t y0 = ((h & 0xfu) * 0x00204081u) & 0x01010101u;
-        const uint32_t y1 = (((h >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-        const uint32_t y2 = (((h >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
-        const uint32_t y3 = ((h >> 12) * 0x00204081u) & 0x01010101u;
-        const uint32_t addr = abase + ((((uint32_t)c16) ^ key) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y0), "r"(y1), "r"(y2), "r"(y3) : "memory");
+      for (int c = 0; c < CPT; ++c) {
+        const uint32_t addr = abase + ((((uint32_t)(half * CPT + c)) ^ key) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y[c][0]), "r"(y[c][1]), "r"(y[c][2]), "r"(y[c][3]) : "memory");
       }
       fence_proxy_async();
       mbar_arrive(FULL_BAR(s));
     }
+    // |S(i)| = the two halves of the row
+    cnt_smem[tid] = cnt;
+    asm volatile("bar.sync 1, %0;" ::"n"(UG_EXP_WARPS * 32) : "memory");
+    cnt = cnt_smem[r] + cnt_smem[r + UG_ROWS];
 
-    // ---- epilogue ----
+    // ---- epilogue: the two threads of a row take alternate P-columns ----
     mbar_wait(ACCUM_BAR, 0u);
     tc_fence_after();
-    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     double* grow = a.Gout + ((size_t)seg * a.rows + (live ? row : 0)) * a.gl;
     double* srow = a.SVout ? a.SVout + ((size_t)seg * a.rows + (live ? row : 0)) * a.KP : nullptr;
     const int NT = a.KP >> 3;
-    for (int cl = 0; cl < pl.cpc; ++cl) {
+    for (int cl = half; cl < pl.cpc; cl += 2) {
       uint32_t d[UG_SLICES];
 #pragma unroll
       for (int s = 0; s < UG_SLICES; ++s) d[s] = tmem_ld1(tlane + (uint32_t)(cl * UG_SLICES + s));
@@ -300,18 +309,19 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
         if (ta == tb) grow[p * 64 + (pb & 7) * 8 + (pa & 7)] = v;
       }
     }
-    if (live && ch == 0) {                               // |S(i)| in the (K, K) slot
+    if (live && ch == 0 && half == 0) {                  // |S(i)| in the (K, K) slot
       const int tk = pl.K >> 3;
       grow[(tk * NT - tk * (tk - 1) / 2) * 64 + (pl.K & 7) * 9] = (double)cnt;
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == UG_EXP_WARPS) {
     // ================= TMA producer of the digit tiles =================
     if (lane == 0) {
       for (int it = 0; it < ntile; ++it) {
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(EMPTY_BAR(s), ph ^ 1u);
+        if ((a.dbg & 1) && it >= stages) { mbar_arrive(FULL_BAR(s)); continue; }
         mbar_expect_tx(FULL_BAR(s), (uint32_t)B_BYTES);
         const uint32_t bdst = smem_base + (uint32_t)s * STAGE + A_BYTES;
         const int x = (kt_begin + it) * KT;
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == UG_EXP_WARPS + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
@@ -424,12 +434,13 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   if (nseg_eff != nseg) { set_error("stats_gram_umma: nseg=%d leaves empty segments (use <= %d)", nseg, nseg_eff); return -2; }
   a.pl = pl; a.cscale = cscale; a.Gout = Gout; a.SVout = SVout; a.KP = KP; a.gl = nt * (nt + 1) / 2 * 64;
   const int stage_bytes = (UG_ROWS + pl.nb) * kt;
-  const int tail = (2 * 16 + 1) * 8 + 16 + 2 * pl.cpc + 64;
+  const int tail = (2 * 16 + 1) * 8 + 16 + UG_EXP_WARPS * 32 * 4 + 2 * pl.cpc + 64;
   int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
   if (stages > 16) stages = 16;
   if (max_stages > 0 && stages > max_stages) stages = max_stages;
   if (stages < 2) { set_error("stats_gram_umma: stage does not fit"); return -2; }
   a.stages = stages;
+  { const char* e = getenv("BNMTF_UMMA_DBG"); a.dbg = e ? atoi(e) : 0; }
   // > half of the SM's shared memory: one CTA per SM, so the 512-column tensor-memory allocation never waits
   size_t smem = (size_t)stages * stage_bytes + tail + 1024;
   if (smem < 116 * 1024) smem = 116 * 1024;

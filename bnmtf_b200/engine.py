@@ -514,8 +514,10 @@ class BNMFEngine:
         self.finish(update_tau=True, record=True)
 
     def profile_sweep(self, reps=3):
-        """Per-kernel CUDA-event timings (ms, mean over reps) of the two streaming passes and the solver, for the
-        roofline block of bench.py.  Runs real sweeps (the state advances)."""
+        """Per-kernel CUDA-event timings (ms per launch, mean over reps and over the two phases) of the statistics
+        passes and the solver, for the roofline block of bench.py.  Runs real sweeps (the state advances; the trace is
+        not written)."""
+        stat = self.metrics_mode == "stats"
         names = ("stats_rx", "stats_gram", "row_solve", "masked_metrics")
         acc = {n: 0.0 for n in names}
         count = {n: 0 for n in names}
@@ -531,21 +533,31 @@ class BNMFEngine:
         for _ in range(reps):
             for side in (0, 1):
                 me, other, R, bits, rows, ld, lo = self._sides(side)
-                nrx, ng, _ = self.nseg[side]
                 other.pad()
                 if self.polarity == 0:
                     _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
                               _ptr(self.Gfull), _ptr(self.gscratch), _stream())
                 timed("stats_rx", lambda: self._rx(side))
-                timed("stats_gram", lambda: self._gram(side))
-                timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1, gather=False))
+                timed("stats_gram", lambda: self._gram(side, sums=stat and side == 1))
+                timed("row_solve", lambda: self.solve(side, want_extra=self.vb and side == 1, gather=False,
+                                                      want_mstat=stat and side == 1))
                 self.solve(side, n_order=0, apply=True, gather=True)   # exchange only (no column is updated)
             self.V.pad()
-            timed("masked_metrics", lambda: self._metrics_padded(self.ds.bits))
+            if stat:
+                rows = self.loc[1][1]
+                if rows > 0:
+                    _lib.call("bnmtf_mstat_reduce_f64", _ptr(self.mstat), rows, _ptr(self.mstat_part), _ptr(self.sums4), _stream())
+                else:
+                    self.sums4.zero_()
+            else:
+                timed("masked_metrics", lambda: self._metrics_padded(self.ds.bits))
             if self.vb:
                 self._vb_extra()
                 self._vb_terms()
             self.comm.allreduce(self.red)
+            if stat:
+                _lib.call("bnmtf_metrics_from_sums_f64", _ptr(self.sums4), _ptr(self.statics_global), self.guard,
+                          _ptr(self.m8), _ptr(self.flag), _stream())
             self.finish(update_tau=True, record=False)
         return {n: acc[n] / max(1, count[n]) for n in names}
 

@@ -79,7 +79,7 @@ def make_synthetic_shards(I, J, K, device, rank, world, seed=0, tile=4096):
     return R, bits, RT, bitsT, n_obs
 
 
-def bench_sharded(args, rank, world, device, clock_sampler_cls, measured_peaks):
+def bench_sharded(args, rank, world, device, clock_sampler_cls, measured_peaks, build_roofline):
     """bench.py leg for N > 1: the same 65536 x 32768 problem, rows of R / R^T split over N ranks (strong scaling).
     Timed with CUDA events on every rank, max over ranks, barrier + synchronize on both sides."""
     import torch
@@ -127,17 +127,33 @@ def bench_sharded(args, rank, world, device, clock_sampler_cls, measured_peaks):
     prof = {k: e.profile_sweep(reps=1) for k, e in engs.items()}
     mse = {k: float(e.scalars.cpu()[engine.S_MSE]) for k, e in engs.items()}
     sampler.join(timeout=2)
+    # end to end through the class API on every rank: replicated factor state uploaded from host numpy, one sharded
+    # sweep, state and trace read back; wall clock between barriers, max over ranks
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        import time
+        for m in models.values():
+            m.run(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        w0 = time.time()
+        for m in models.values():
+            for _ in range(args.steps):
+                m.run(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([time.time() - w0], dtype=torch.float64, device=device)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        fU, fV = I * K * 8, J * K * 8
+        e2e = {"value": 2.0 * args.steps / float(dt.item()), "unit": "sweeps/s",
+               "h2d_bytes_per_step": int(world * (2 * (fU + fV) + 5 * (fU + fV)) / 2.0),
+               "d2h_bytes_per_step": int(world * (2 * (fU + fV) + 4 * (fU + fV)) / 2.0),
+               "note": "model.run(1) per step on every rank (factor state is replicated: each rank uploads and reads back "
+                       "all of it); the R / R^T shards stay resident"}
     if rank == 0:
-        hbm_peak, hbm_kind = measured_peaks()
         N = float(I) * J
         value = 2.0 * args.steps / (total_ms / 1e3)
         sweep_s = total_ms / 1e3 / (2.0 * args.steps)
-        b_alg = 2.0 * N * 8.125
-        miss = N - n_obs
-        pairs = K * (K + 1) / 2.0
-        gram_flops = {"gibbs": miss * (pairs + K) * 2.0 / world, "vb": miss * (pairs + 2 * K) * 2.0 / world}
-        ach = {k: gram_flops[k] / (prof[k]["stats_gram"] * 1e-3) / 1e12 for k in engs}
-        mean_ach = sum(ach.values()) / len(ach)
         line = {"metric": "BNMF Gibbs+VB sweeps/sec at %dx%d K=%d" % (I, J, K), "value": value, "unit": "sweeps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / (2.0 * args.steps),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -146,12 +162,8 @@ def bench_sharded(args, rank, world, device, clock_sampler_cls, measured_peaks):
                                           "one 24-double all-reduce per sweep (NCCL)" % world,
                            "l2": "inputs far larger than L2", "gibbs_sweeps_per_s": args.steps / (g_ms / 1e3),
                            "vb_sweeps_per_s": args.steps / (v_ms / 1e3), "train_mse_after": mse},
-                "roofline": {"bound": "tensor", "kernel": "k_stats_gram (fp64 DMMA), per rank", "achieved": mean_ach,
-                             "peak": 37.1, "unit": "TFLOP/s", "frac": mean_ach / 37.1, "traffic": None, "kernel_ms": prof,
-                             "sweep_hbm": {"algorithmic_bytes_per_sweep": b_alg, "achieved_gbs": b_alg / sweep_s / 1e9,
-                                           "peak_gbs": hbm_peak * world, "peak_kind": hbm_kind,
-                                           "frac": b_alg / sweep_s / 1e9 / (hbm_peak * world)}},
-                "e2e": None, "gpu_launches": launches, "clocks": sampler.summary()}
+                "roofline": build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=world),
+                "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
