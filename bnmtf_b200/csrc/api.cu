@@ -34,7 +34,7 @@ int launch_stats_rx_umma(const uint8_t*, const double*, const double*, const uin
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 long long umma_workspace_bytes(int, int, long long);
-int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, int, int,
+int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, int, int, int,
                            double*, double*, void*, long long, cudaStream_t);
 int launch_pad_factor(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_masked_metrics(const double*, const uint32_t*, int, int, const double*, const double*, int, int, const double*, double*, double*, const int*, cudaStream_t);
@@ -199,12 +199,13 @@ int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld) {
 }
 
 int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp,
-                              const double* Vp, int K, int polarity, int nseg, int tile, int sums, int max_stages,
-                              double* Gpart, double* SVpart, void* workspace, int64_t workspace_bytes, void* stream) {
+                              const double* Vp, int K, int polarity, int nseg, int tile, int pair, int sums,
+                              int max_stages, double* Gpart, double* SVpart, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram_umma: Vp and SVpart must be given together"); return -2; }
-  return launch_stats_gram_umma(bits, (int)rows, (int)ld, (int)cols, Xp, Vp, K, polarity, nseg, tile, sums, max_stages,
-                                Gpart, SVpart, workspace, workspace_bytes, ST(stream));
+  return launch_stats_gram_umma(bits, (int)rows, (int)ld, (int)cols, Xp, Vp, K, polarity, nseg, tile, pair, sums,
+                                max_stages, Gpart, SVpart, workspace, workspace_bytes, ST(stream));
 }
 
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp, int64_t n, int K, int64_t dummy_row, double* Gfull,

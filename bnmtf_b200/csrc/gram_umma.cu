@@ -44,7 +44,7 @@ struct UmmaPlan {
   int nb;       // digit rows per chunk in the staged B matrix = 2*n_half
 };
 
-__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums) {
+__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums, int pair) {
   UmmaPlan p;
   p.K = K; p.vb = vb; p.sums = sums;
   p.ng = K * (K + 1) / 2;
@@ -53,7 +53,8 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums) {
   p.nch = (p.nc + cmax - 1) / cmax;
   p.cpc = (p.nc + p.nch - 1) / p.nch;
   const int nd = p.cpc * UG_SLICES;
-  p.n_half = ((nd + 1) / 2 + 15) / 16 * 16;
+  const int gran = pair ? 32 : 16;                    // UMMA N granularity (CTA pair: each CTA holds n_half/2 digit rows)
+  p.n_half = ((nd + 1) / 2 + gran - 1) / gran * gran;
   p.nb = 2 * p.n_half;
   return p;
 }
@@ -178,13 +179,18 @@ struct UmmaGramArgs {
   int dbg;   // timing experiments only: 1 = skip TMA loads after the first fill, 2 = skip the A-tile stores
 };
 
-template <int KT>
+// PAIR: two CTAs of a cluster (adjacent row blocks, same chunk and segment) run every MMA as one cta_group::2
+// instruction of M = 256: each CTA expands its own 128 mask rows and loads only HALF of the digit rows of each
+// accumulator (the hardware reads the other half from the partner's shared memory), which halves the shared-memory
+// and L2 traffic per MMA -- the limit of the single-CTA form.
+template <int KT, bool PAIR>
 __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_constant__ CUtensorMap tmap, UmmaGramArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const UmmaPlan& pl = a.pl;
-  const int A_BYTES = UG_ROWS * KT, B_BYTES = pl.nb * KT, STAGE = A_BYTES + B_BYTES;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int A_BYTES = UG_ROWS * KT, B_BYTES = (PAIR ? pl.n_half : pl.nb) * KT, STAGE = A_BYTES + B_BYTES;
   const int stages = a.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);   // full[stages], empty[stages], accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
@@ -202,14 +208,22 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   const int ntile = kt_end - kt_begin;                 // >= 1 by construction of the grid
 
   if (warp == UG_EXP_WARPS && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), UG_EXP_WARPS * 32 + 1); mbar_init(EMPTY_BAR(s), 1); }
+    // full: every local expander thread + the TMA thread (+, CTA pair, leader: the partner's relay thread; the
+    // partner's own full barrier only collects its expanders)
+    const uint32_t nfull = UG_EXP_WARPS / 2 + (PAIR ? (rank == 0 ? 2u : 0u) : 1u);
+    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), nfull); mbar_init(EMPTY_BAR(s), 1); }
     mbar_init(ACCUM_BAR, 1);
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
   if (warp == UG_EXP_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int cl = tid; cl < pl.cpc; cl += UG_THREADS) {
     const int c = ch * pl.cpc + cl;
@@ -218,18 +232,20 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     pair_tab[cl] = (uint16_t)((pa << 8) | pb);
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers of BOTH CTAs are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < UG_EXP_WARPS) {
-    // ================= mask expanders, then epilogue: two threads per row (each owns half of every tile) =========
+    // ================= mask expanders, then epilogue =================
+    // two groups of 128 threads (thread <-> row) take alternate pipeline stages: the per-stage chain of one group
+    // (barrier wake-up, stores, proxy fence, arrive) overlaps the bit expansion of the other
     const int r = tid & (UG_ROWS - 1), half = tid >> 7;
     const int row = rb * UG_ROWS + r;
     const bool live = row < a.rows;
     const uint32_t* mrow = a.bits + (size_t)(live ? row : 0) * a.wpr;
-    constexpr int WPT = KT / 64;                       // mask words per thread and tile
-    constexpr int CPT = KT / 32;                       // 16-byte chunks per thread and tile
+    constexpr int WPT = KT / 32;                       // mask words per tile
+    constexpr int CPT = KT / 16;                       // 16-byte chunks per tile row
     const uint32_t flip = a.polarity ? 0u : 0xffffffffu;
     // byte offset of this row inside an A tile, and its swizzle key (16-byte chunk index XOR)
     const uint32_t row_off = (uint32_t)(r >> 3) * (8 * KT) + (uint32_t)(r & 7) * KT;
@@ -237,14 +253,14 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     int cnt = 0;
     uint32_t nxt[WPT];
     {
-      const int w0 = kt_begin * (KT / 32) + half * WPT;
+      const int w0 = (kt_begin + half) * WPT;
 #pragma unroll
-      for (int i = 0; i < WPT; ++i) nxt[i] = (live && w0 + i < a.wpr) ? mrow[w0 + i] : 0u;
+      for (int i = 0; i < WPT; ++i) nxt[i] = (live && half < ntile && w0 + i < a.wpr) ? mrow[w0 + i] : 0u;
     }
-    for (int it = 0; it < ntile; ++it) {
+    for (int it = half; it < ntile; it += 2) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
-      const int wbase = (kt_begin + it) * (KT / 32) + half * WPT;
+      const int wbase = (kt_begin + it) * WPT;
       uint32_t y[CPT][4];
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
@@ -257,8 +273,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 8; ++q) y[2 * i + (q >> 2)][q & 3] = (((v >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
       }
-      if (it + 1 < ntile) {
-        const int wn = wbase + (KT / 32);
+      if (it + 2 < ntile) {
+        const int wn = wbase + 2 * WPT;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) nxt[i] = (live && wn + i < a.wpr) ? mrow[wn + i] : 0u;
       }
@@ -267,13 +283,14 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       if (!((a.dbg & 2) && it >= stages))
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
-        const uint32_t addr = abase + ((((uint32_t)(half * CPT + c)) ^ key) << 4);
+        const uint32_t addr = abase + ((((uint32_t)c) ^ key) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y[c][0]), "r"(y[c][1]), "r"(y[c][2]), "r"(y[c][3]) : "memory");
       }
       fence_proxy_async();
-      mbar_arrive(FULL_BAR(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(FULL_BAR(s));           // one arrival per warp
     }
-    // |S(i)| = the two halves of the row
+    // |S(i)| = the tiles of both groups
     cnt_smem[tid] = cnt;
     asm volatile("bar.sync 1, %0;" ::"n"(UG_EXP_WARPS * 32) : "memory");
     cnt = cnt_smem[r] + cnt_smem[r + UG_ROWS];
@@ -321,44 +338,87 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(EMPTY_BAR(s), ph ^ 1u);
-        if ((a.dbg & 1) && it >= stages) { mbar_arrive(FULL_BAR(s)); continue; }
-        mbar_expect_tx(FULL_BAR(s), (uint32_t)B_BYTES);
         const uint32_t bdst = smem_base + (uint32_t)s * STAGE + A_BYTES;
         const int x = (kt_begin + it) * KT;
+        if (PAIR) {
+          // this CTA's half of the digit rows of each accumulator; the bytes of both CTAs are expected by the leader
+          const uint32_t lead_full = mapa_u32(FULL_BAR(s), 0);
+          if (rank == 0) mbar_expect_tx(FULL_BAR(s), 2u * (uint32_t)B_BYTES);
+          const int hh = pl.n_half >> 1;
+          tma_load_2d_pair(bdst, &tmap, x, ch * pl.nb + (int)rank * hh, lead_full);
+          tma_load_2d_pair(bdst + (uint32_t)hh * KT, &tmap, x, ch * pl.nb + pl.n_half + (int)rank * hh, lead_full);
+          continue;
+        }
+        if ((a.dbg & 1) && it >= stages) { mbar_arrive(FULL_BAR(s)); continue; }
+        mbar_expect_tx(FULL_BAR(s), (uint32_t)B_BYTES);
         tma_load_2d(bdst, &tmap, x, ch * pl.nb, FULL_BAR(s));
         tma_load_2d(bdst + (uint32_t)pl.n_half * KT, &tmap, x, ch * pl.nb + pl.n_half, FULL_BAR(s));
       }
     }
+    __syncwarp();
   } else {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, N = n_half, M = 128
-      const uint32_t idesc = (2u << 4) | ((uint32_t)(pl.n_half >> 3) << 17) | ((uint32_t)(UG_ROWS >> 4) << 24);
+    if (PAIR && lane == 0 && rank != 0) {
+      // partner CTA: relay "my A tile is complete" to the leader's full barrier, one cluster-scope arrive per stage
+      // (a release at cluster scope flushes L1: kept off the expander threads)
       for (int it = 0; it < ntile; ++it) {
         const int s = it % stages;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u;
-        mbar_wait(FULL_BAR(s), ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * STAGE;
-        const uint64_t ad = umma_desc<KT>(sa);
-        const uint64_t bd0 = umma_desc<KT>(sa + A_BYTES);
-        const uint64_t bd1 = umma_desc<KT>(sa + A_BYTES + (uint32_t)pl.n_half * KT);
-#pragma unroll
-        for (int kk = 0; kk < KT / 32; ++kk) {
-          const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-          umma_i8(tmem_base, ad + 2 * kk, bd0 + 2 * kk, idesc, acc);
-          umma_i8(tmem_base + (uint32_t)pl.n_half, ad + 2 * kk, bd1 + 2 * kk, idesc, acc);
-        }
-        umma_commit(EMPTY_BAR(s));
+        mbar_wait(FULL_BAR(s), (uint32_t)(it / stages) & 1u);
+        mbar_arrive_remote(mapa_u32(FULL_BAR(s), 0));
       }
-      umma_commit(ACCUM_BAR);
+    }
+    if (rank == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, N = n_half,
+      // M = 128 (256 for the CTA pair)
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(pl.n_half >> 3) << 17) | ((uint32_t)((PAIR ? 2 * UG_ROWS : UG_ROWS) >> 4) << 24);
+      // The whole warp runs this loop (convergent code keeps descriptors in uniform registers: with a single-lane
+      // loop every tcgen05.mma needed five R2UR moves, ~150 dependent instructions per stage, and the issuing thread
+      // itself limited the tensor pipe); only the tcgen05 instructions are predicated on one elected lane.  No
+      // divisions, no clock reads, descriptors by addition.
+      const uint64_t ad0 = umma_desc<KT>(smem_base);
+      const uint64_t bd00 = umma_desc<KT>(smem_base + A_BYTES);
+      const uint64_t bd10 = umma_desc<KT>(smem_base + A_BYTES + (uint32_t)(PAIR ? pl.n_half >> 1 : pl.n_half) * KT);
+      const uint64_t dstep = (uint64_t)(STAGE >> 4);
+      const uint32_t tm1 = tmem_base + (uint32_t)pl.n_half;
+      int s = 0;
+      uint32_t ph = 0;
+      uint64_t soff = 0;
+      mbar_wait(FULL_BAR(0), 0u);
+      for (int it = 0; it < ntile; ++it) {
+        tc_fence_after();
+        const uint64_t ad = ad0 + soff, bd0 = bd00 + soff, bd1 = bd10 + soff;
+        // next stage's barrier is polled while the last MMAs of this stage are still executing
+        int sn = s + 1;
+        uint32_t phn = ph;
+        if (sn == stages) { sn = 0; phn ^= 1u; }
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < KT / 32; ++kk) {
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+            if (PAIR) {
+              umma_i8_pair(tmem_base, ad + 2 * kk, bd0 + 2 * kk, idesc, acc);
+              umma_i8_pair(tm1, ad + 2 * kk, bd1 + 2 * kk, idesc, acc);
+            } else {
+              umma_i8(tmem_base, ad + 2 * kk, bd0 + 2 * kk, idesc, acc);
+              umma_i8(tm1, ad + 2 * kk, bd1 + 2 * kk, idesc, acc);
+            }
+          }
+          if (PAIR) umma_commit_pair(EMPTY_BAR(s)); else umma_commit(EMPTY_BAR(s));
+        }
+        __syncwarp();
+        if (it + 1 < ntile) mbar_wait(FULL_BAR(sn), phn);
+        s = sn; ph = phn;
+        soff = s == 0 ? 0 : soff + dstep;
+      }
+      if (elect_one()) { if (PAIR) umma_commit_pair(ACCUM_BAR); else umma_commit(ACCUM_BAR); }
     }
     __syncwarp();
   }
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // nobody frees tensor memory the partner still reads
   if (warp == UG_EXP_WARPS + 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 #undef FULL_BAR
 #undef EMPTY_BAR
@@ -379,18 +439,23 @@ static long long plan_workspace_bytes(const UmmaPlan& pl, long long ld) {
 }
 
 long long umma_workspace_bytes(int K, int vb, long long ld) {
-  const long long a = plan_workspace_bytes(make_umma_plan(K, vb, 0), ld), b = plan_workspace_bytes(make_umma_plan(K, vb, 1), ld);
-  return a > b ? a : b;
+  long long m = 0;
+  for (int sums = 0; sums < 2; ++sums)
+    for (int pair = 0; pair < 2; ++pair) {
+      const long long b = plan_workspace_bytes(make_umma_plan(K, vb, sums, pair), ld);
+      m = b > m ? b : m;
+    }
+  return m;
 }
 
 int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, const double* Xp, const double* Vp, int K,
-                           int polarity, int nseg, int kt, int sums, int max_stages, double* Gout, double* SVout,
+                           int polarity, int nseg, int kt, int pair, int sums, int max_stages, double* Gout, double* SVout,
                            void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (rows <= 0 || ld <= 0 || ld % 64 || nseg <= 0 || cols <= 0 || cols > ld) { set_error("stats_gram_umma: bad shape"); return -2; }
   if (kt != 64 && kt != 128) { set_error("stats_gram_umma: tile width must be 64 or 128"); return -2; }
   if ((long long)ld * 255 >= 2147483647ll) { set_error("stats_gram_umma: more than 8.4M columns would overflow the int32 accumulators"); return -2; }
   const int vb = Vp != nullptr;
-  const UmmaPlan pl = make_umma_plan(K, vb, sums);
+  const UmmaPlan pl = make_umma_plan(K, vb, sums, pair);
   if (workspace_bytes < plan_workspace_bytes(pl, ld)) { set_error("stats_gram_umma: workspace too small"); return -2; }
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("stats_gram_umma: cuTensorMapEncodeTiled not available"); return -3; }
@@ -418,7 +483,7 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   {
     const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)pl.nch * pl.nb};
     const cuuint64_t gstr[1] = {(cuuint64_t)ld};
-    const cuuint32_t box[2] = {(cuuint32_t)kt, (cuuint32_t)pl.n_half};
+    const cuuint32_t box[2] = {(cuuint32_t)kt, (cuuint32_t)(pair ? pl.n_half / 2 : pl.n_half)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, Bd, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               kt == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -433,7 +498,7 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   const int nseg_eff = (a.ktiles + a.tiles_per_seg - 1) / a.tiles_per_seg;
   if (nseg_eff != nseg) { set_error("stats_gram_umma: nseg=%d leaves empty segments (use <= %d)", nseg, nseg_eff); return -2; }
   a.pl = pl; a.cscale = cscale; a.Gout = Gout; a.SVout = SVout; a.KP = KP; a.gl = nt * (nt + 1) / 2 * 64;
-  const int stage_bytes = (UG_ROWS + pl.nb) * kt;
+  const int stage_bytes = (UG_ROWS + (pair ? pl.n_half : pl.nb)) * kt;
   const int tail = (2 * 16 + 1) * 8 + 16 + UG_EXP_WARPS * 32 * 4 + 2 * pl.cpc + 64;
   int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
   if (stages > 16) stages = 16;
@@ -444,14 +509,20 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   // > half of the SM's shared memory: one CTA per SM, so the 512-column tensor-memory allocation never waits
   size_t smem = (size_t)stages * stage_bytes + tail + 1024;
   if (smem < 116 * 1024) smem = 116 * 1024;
-  dim3 grid((rows + UG_ROWS - 1) / UG_ROWS, pl.nch, nseg);
-  if (kt == 128) {
-    cudaFuncSetAttribute(k_gram_umma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_gram_umma<128><<<grid, UG_THREADS, smem, st>>>(tmap, a);
-  } else {
-    cudaFuncSetAttribute(k_gram_umma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_gram_umma<64><<<grid, UG_THREADS, smem, st>>>(tmap, a);
-  }
+  int rbs = (rows + UG_ROWS - 1) / UG_ROWS;
+  if (pair) rbs = (rbs + 1) / 2 * 2;                   // a padding CTA (no live rows) completes the last pair
+  dim3 grid(rbs, pl.nch, nseg);
+  void (*kern)(const CUtensorMap, UmmaGramArgs) =
+      kt == 128 ? (pair ? k_gram_umma<128, true> : k_gram_umma<128, false>) : (pair ? k_gram_umma<64, true> : k_gram_umma<64, false>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(UG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+  if (le != cudaSuccess) { set_error("stats_gram_umma: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return -1; }
   return check_launch("stats_gram_umma");
 }
 

@@ -307,37 +307,44 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
         tma_load_2d(dst + RXU_A_BYTES, &tmap, (kt_begin + it) * RXU_KT, 0, FULL_BAR(s));
       }
     }
+    __syncwarp();
   } else {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // the whole warp runs the loop (descriptors stay in uniform registers); one elected lane issues
+    {
+      int s = 0;
+      uint32_t ph = 0;
       for (int d = 0; d < nper; ++d) {
         const int b = d & 1;
         mbar_wait(ACC_EMPTY(b), (uint32_t)(d >> 1) & 1u);
         tc_fence_after();
         const int it_end = min(ntile, (d + 1) * RXU_DRAIN);
         for (int it = d * RXU_DRAIN; it < it_end; ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(FULL_BAR(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)s * STAGE;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < RXU_KT / 32; ++kk) {
+            for (int kk = 0; kk < RXU_KT / 32; ++kk) {
 #pragma unroll
-            for (int p = 0; p < RXU_PLANES; ++p) {
-              const int tmin = p < RXU_UMIN ? RXU_UMIN - p : 0;
-              const int nt = RXU_VDIG - tmin;
-              // D = s32, A = u8 (top plane: s8), B = u8, K-major both, N = nt*KPAD, M = 128
-              const uint32_t idesc = (2u << 4) | ((p == RXU_PLANES - 1 ? 1u : 0u) << 7) |
-                                     ((uint32_t)((nt * KPAD) >> 3) << 17) | (8u << 24);
-              const uint64_t ad = umma_desc<RXU_KT>(sa + (uint32_t)p * RXU_PLANE_TILE) + 2 * kk;
-              const uint64_t bd = umma_desc<RXU_KT>(sa + RXU_A_BYTES + (uint32_t)(tmin * KPAD * RXU_KT)) + 2 * kk;
-              umma_i8(tmem_base + (uint32_t)(b * SET + (p + tmin - RXU_UMIN) * KPAD), ad, bd, idesc, 1u);
+              for (int p = 0; p < RXU_PLANES; ++p) {
+                const int tmin = p < RXU_UMIN ? RXU_UMIN - p : 0;
+                const int nt = RXU_VDIG - tmin;
+                // D = s32, A = u8 (top plane: s8), B = u8, K-major both, N = nt*KPAD, M = 128
+                const uint32_t idesc = (2u << 4) | ((p == RXU_PLANES - 1 ? 1u : 0u) << 7) |
+                                       ((uint32_t)((nt * KPAD) >> 3) << 17) | (8u << 24);
+                const uint64_t ad = umma_desc<RXU_KT>(sa + (uint32_t)p * RXU_PLANE_TILE) + 2 * kk;
+                const uint64_t bd = umma_desc<RXU_KT>(sa + RXU_A_BYTES + (uint32_t)(tmin * KPAD * RXU_KT)) + 2 * kk;
+                umma_i8(tmem_base + (uint32_t)(b * SET + (p + tmin - RXU_UMIN) * KPAD), ad, bd, idesc, 1u);
+              }
             }
+            umma_commit(EMPTY_BAR(s));
           }
-          umma_commit(EMPTY_BAR(s));
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(ACC_FULL(b));
+        if (elect_one()) umma_commit(ACC_FULL(b));
+        __syncwarp();
       }
     }
     __syncwarp();

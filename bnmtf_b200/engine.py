@@ -218,6 +218,7 @@ class BNMFEngine:
         # become co-resident: different shared-memory carveouts; forcing the same carveout slows the streaming kernel)
         self.overlap = int(os.environ.get("BNMTF_OVERLAP", "0")) if self.gram == "umma" else 0
         self.umma_stages = int(os.environ.get("BNMTF_UMMA_STAGES", "3" if self.overlap else "0"))
+        self.umma_pair = int(os.environ.get("BNMTF_UMMA_PAIR", "1"))   # CTA pairs (cta_group::2) in the Gram kernel
         self._side = None
         self.m = MODE[mode]
         self.vb = mode == "vb"
@@ -251,7 +252,7 @@ class BNMFEngine:
                 nrx = max(1, min(ld // 128, -(-2664 // rb)))
             if self.gram == "umma":
                 # CTAs = row blocks x column chunks x segments; aim for ~10 waves of one CTA per SM
-                tile = 128 if ld >= 4096 else 64
+                tile = 128 if ld >= 256 else 64
                 nch = -(-(K * (K + 1) // 2 + (K if self.vb else 0)) // 73)
                 ktiles = -(-ld // tile)
                 ng = max(1, min(ktiles, round(1480 / (rb * nch))))
@@ -378,7 +379,8 @@ class BNMFEngine:
         ng = self.nseg[side][1]
         if self.gram == "umma":
             _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, other.n, _ptr(other.Xp), _ptr(other.Vp), self.K,
-                      self.polarity, ng, self.umma_tile[side], 1 if sums else 0, self.umma_stages, _ptr(self.Gpart),
+                      self.polarity, ng, self.umma_tile[side], self.umma_pair, 1 if sums else 0, self.umma_stages,
+                      _ptr(self.Gpart),
                       _ptr(self.SVpart), self.ws_ptr, self.ws_bytes, _stream())
         else:
             _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp), _ptr(other.Vp), self.K,

@@ -97,14 +97,15 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
  * the products X_ja X_jb (and Var_jk) are cut into seven exact 8-bit digits of a 56-bit fixed-point value per
  * column and multiplied with the 0/1 selection matrix of the rows, so the result is the exactly summed,
  * once-rounded value.  cols = number of valid columns (<= ld); tile = 64 or 128 (bytes of the column range staged
- * per pipeline stage); sums != 0 also accumulates the masked column sums of X (slot (k, K) of the packed tiles,
+ * per pipeline stage); pair != 0 runs CTA pairs (cta_group::2: adjacent 128-row blocks share every MMA and each
+ * CTA stages only half of the digit rows); sums != 0 also accumulates the masked column sums of X (slot (k, K) of the packed tiles,
  * as the ones-column of Xp does in bnmtf_stats_gram_f64; the selected-entry count always goes to slot (K, K));
  * max_stages > 0 caps the pipeline depth (shared memory left for kernels running concurrently on other streams);
  * workspace: >= bnmtf_gram_umma_workspace_bytes(K, Vp != NULL, ld) bytes, 1024-byte aligned.
  * Only the entries (a, b < K), the slots above, and the first K entries of SVpart are written. */
 int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld);
 int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp,
-                              const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, int sums,
+                              const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, int pair, int sums,
                               int max_stages, double* Gpart, double* SVpart /*or NULL*/, void* workspace,
                               int64_t workspace_bytes, void* stream);
 /* scratch: >= 64 * (bnmtf_gram_len(K) + KP) doubles */

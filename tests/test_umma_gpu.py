@@ -46,7 +46,7 @@ def _tile_index(a, b, KP):
     return (ta * nt - ta * (ta - 1) // 2 + (tb - ta)) * 64 + (a % 8) * 8 + (b % 8)
 
 
-def _gram_umma(d, rows, cols, K, vb, polarity, nseg, tile, sums, stages=0):
+def _gram_umma(d, rows, cols, K, vb, polarity, nseg, tile, sums, stages=0, pair=0):
     import torch
     from bnmtf_b200 import _lib
     from bnmtf_b200.engine import _ptr, _stream, gram_len
@@ -57,24 +57,25 @@ def _gram_umma(d, rows, cols, K, vb, polarity, nseg, tile, sums, stages=0):
     G = torch.zeros((nseg * rows, GL), dtype=torch.float64, device=d["dev"])
     S = torch.zeros((nseg * rows, d["KP"]), dtype=torch.float64, device=d["dev"]) if vb else None
     _lib.call("bnmtf_stats_gram_umma_f64", _ptr(d["bits"]), rows, d["ld"], cols, _ptr(d["Xp"]), _ptr(d["Vp"]) if vb else 0,
-              K, polarity, nseg, tile, sums, stages, _ptr(G), _ptr(S), wsp, wsb, _stream())
+              K, polarity, nseg, tile, pair, sums, stages, _ptr(G), _ptr(S), wsp, wsb, _stream())
     torch.cuda.synchronize()
     G = G.view(nseg, rows, GL).sum(0).cpu().numpy()
     S = S.view(nseg, rows, d["KP"]).sum(0).cpu().numpy() if vb else None
     return G, S
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("rows,cols,K,vb,polarity,nseg,tile,sums", [
     (100, 80, 10, 0, 0, 1, 128, 0),      # config-1 shape
     (100, 80, 5, 1, 0, 1, 64, 1),        # config-2 shape, VB, with the column sums
     (129, 65, 5, 1, 1, 1, 64, 1),        # ragged rows/cols, observed-set polarity
-    (622, 138, 10, 1, 0, 1, 64, 1),      # GDSC shape
+    (622, 138, 10, 1, 0, 1, 64, 1),      # GDSC shape (odd number of row blocks: a padding CTA completes the last pair)
     (300, 1000, 20, 1, 0, 2, 64, 1),     # two column segments, four chunks
     (260, 700, 33, 0, 0, 3, 128, 0),     # K > 32: eight chunks
 ])
-def test_gram_umma_matches_numpy(rows, cols, K, vb, polarity, nseg, tile, sums):
+def test_gram_umma_matches_numpy(rows, cols, K, vb, polarity, nseg, tile, sums, pair):
     d = _setup(rows, cols, K, seed=rows + cols + K)
-    G, S = _gram_umma(d, rows, cols, K, vb, polarity, nseg, tile, sums)
+    G, S = _gram_umma(d, rows, cols, K, vb, polarity, nseg, tile, sums, pair=pair)
     W = d["M"] if polarity else 1.0 - d["M"]
     X, KP = d["X"], d["KP"]
     for a in range(K):
@@ -99,8 +100,8 @@ def test_gram_umma_is_exact_on_integers():
     rows, cols, K = 200, 900, 12
     d = _setup(rows, cols, K, seed=5, integer=True)
     W = 1.0 - d["M"]
-    for nseg, tile in ((1, 64), (3, 128)):
-        G, S = _gram_umma(d, rows, cols, K, 1, 0, nseg, tile, 1)
+    for nseg, tile, pair in ((1, 64, 0), (3, 128, 0), (2, 128, 1)):
+        G, S = _gram_umma(d, rows, cols, K, 1, 0, nseg, tile, 1, pair=pair)
         for a in range(K):
             for b in range(a, K):
                 assert np.array_equal(G[:, _tile_index(a, b, d["KP"])], W @ (d["X"][:, a] * d["X"][:, b]))

@@ -12,6 +12,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PAIR = int(os.environ.get("PAIR", "0"))
 sys.path.insert(0, ROOT)
 
 # rows, cols, K, vb, polarity, nseg, tile, signed, timing reps, sums, max_stages
@@ -31,6 +32,11 @@ CASES = [
     (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 1),
     (32768, 65536, 20, 0, 0, 2, 128, 0, 3, 1, 0),
     (32768, 65536, 20, 1, 0, 2, 128, 0, 3, 1, 0),
+    (65536, 32768, 20, 0, 0, 1, 64, 0, 3, 0, 0),     # 15: tile 64, as many stages as fit
+    (65536, 32768, 20, 0, 0, 1, 64, 0, 3, 0, 6),
+    (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 3),
+    (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 2),
+    (65536, 32768, 20, 1, 0, 1, 128, 0, 3, 0, 0),    # 19: VB row phase
 ]
 
 
@@ -73,7 +79,7 @@ def run_case(idx):
 
     def umma():
         _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, cols, _ptr(Xp), _ptr(Vp) if vb else 0, K, pol, nseg,
-                  tile, sums, stages, _ptr(G1), _ptr(S1), wsp, wsb, _stream())
+                  tile, PAIR, sums, stages, _ptr(G1), _ptr(S1), wsp, wsb, _stream())
     umma()
     torch.cuda.synchronize()
     out = {"case": idx, "shape": [rows, cols, K], "vb": vb, "pol": pol, "nseg": nseg, "tile": tile, "signed": signed,
