@@ -123,10 +123,10 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
         mean_ach = sum(ach.values()) / len(ach)
         peak = 2.0 * bf16
         out.update({"bound": "tensor", "kernel": "k_gram_umma (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed)",
-                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": 1.5e9,
+                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": 1.6e9,
                     "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is twice "
                                    "the bf16 rate; ops are int8 multiply-adds x 2" % bf16_kind,
-                    "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary_umma.txt",
+                    "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary_final.txt",
                     "per_mode_achieved_tops": ach})
     else:
         miss = N - n_obs
@@ -144,7 +144,8 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
     rx_gbs = N * bpe / (rx_ms * 1e-3) / 1e9
     out["hbm_kernel"] = {"bound": "hbm", "kernel": "k_rx_umma (tcgen05 digit planes)" if e0.rx == "umma" else "k_stats_rx (fp64 DMMA)",
                          "achieved": rx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rx_gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)"}
+                         "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)",
+                         "traffic": 15.15e9 * (N / 2.0 ** 31) if e0.rx == "umma" else None}
     return out
 
 

@@ -218,6 +218,10 @@ class BNMFEngine:
         # become co-resident: different shared-memory carveouts; forcing the same carveout slows the streaming kernel)
         self.overlap = int(os.environ.get("BNMTF_OVERLAP", "0")) if self.gram == "umma" else 0
         self.umma_stages = int(os.environ.get("BNMTF_UMMA_STAGES", "3" if self.overlap else "0"))
+        # 1: replay the sweep as a CUDA graph (single-GPU runs); 2: also when sharded (NCCL collectives captured)
+        g = int(os.environ.get("BNMTF_GRAPH", "1"))
+        self.use_graph = g >= 2 or (g == 1 and dataset.world == 1)
+        self._graph = self._graph_key = self._graph_seen = None
         self.umma_pair = int(os.environ.get("BNMTF_UMMA_PAIR", "1"))   # CTA pairs (cta_group::2) in the Gram kernel
         self._side = None
         self.m = MODE[mode]
@@ -488,7 +492,30 @@ class BNMFEngine:
 
     # ---- the sweep ------------------------------------------------------------------------------------
     def sweep(self, minimum_TN=0.0):
-        """One iteration of run(): all U columns, all V columns, tau, metrics (reference run() bodies)."""
+        """One iteration of run().  The launch sequence of a sweep is static (about 45 launches, every pointer fixed
+        while the trace buffer stays the same, the sweep counter lives on the device), so from the second sweep of a
+        run on it is replayed as one CUDA graph: the small kernels between the big ones no longer wait for the host."""
+        if self.use_graph:
+            key = (self.trace.data_ptr() if self.trace is not None else 0, self.trace_base, self.trace_cap, float(minimum_TN))
+            if self._graph is not None and self._graph_key == key:
+                self._graph.replay()
+                self.sweeps_done += 1
+                return
+            if self._graph_seen == key:
+                g = torch.cuda.CUDAGraph()
+                done = self.sweeps_done
+                with torch.cuda.graph(g):
+                    self._sweep_eager(minimum_TN)          # captured, not executed
+                self.sweeps_done = done
+                self._graph, self._graph_key = g, key
+                g.replay()
+                self.sweeps_done += 1
+                return
+            self._graph_seen = key
+        self._sweep_eager(minimum_TN)
+
+    def _sweep_eager(self, minimum_TN=0.0):
+        """All U columns, all V columns, tau, metrics (reference run() bodies), launch by launch."""
         stat = self.metrics_mode == "stats"
         self.stats(0)
         self.solve(0, minimum_TN=minimum_TN)
