@@ -297,8 +297,9 @@ def main():
         d2h = ((2 * (fU + fV)) + (4 * (fU + fV))) / 2.0        # gibbs: state + the kept sample; vb: exp,var,mu,tau
         e2e = {"value": 2.0 * args.steps / dt, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h),
-               "note": "model.run(1) per step: factor state uploaded from host numpy, one sweep, state+trace read back; "
-                       "R itself (16 GiB) is resident like a dataset"}
+               "note": "model.run(1) per step: factor state DMA'd from the model's page-locked host arrays, one sweep, state + "
+                       "trace read back into them; the priors come from pageable numpy; R itself (16 GiB) is resident like "
+                       "a dataset"}
 
     # ---- roofline ------------------------------------------------------------------------------------------------
     roofline = build_roofline(engs, prof, I, J, K, n_obs, total_ms / 1e3 / (2.0 * args.steps))

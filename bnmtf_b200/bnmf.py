@@ -117,6 +117,27 @@ class _TwoFactorBase(object):
     def _down(src, n=None):
         return (src if n is None else src[:n]).detach().cpu().numpy().copy()
 
+    # Factor state crosses PCIe through persistent page-locked buffers.  After run() the state attributes (U, expU, ...)
+    # ARE numpy views of those buffers, rewritten in place by the next run() -- the same aliasing the reference has,
+    # whose updates write into self.U in place -- and _push() DMAs straight from them (no staging copy) as long as
+    # the attribute still is that view; anything the caller assigned instead takes the pageable path.
+    def _down_s(self, key, src, n):
+        pins = self.__dict__.setdefault('_pins', {})
+        t = src[:n]
+        ent = pins.get(key)
+        if ent is None or tuple(ent[0].shape) != tuple(t.shape):
+            buf = torch.empty(tuple(t.shape), dtype=torch.float64, pin_memory=True)
+            ent = pins[key] = (buf, buf.numpy())
+        ent[0].copy_(t, non_blocking=True)       # caller synchronises before handing the view out
+        return ent[1]
+
+    def _up_s(self, key, dst, src):
+        ent = self.__dict__.get('_pins', {}).get(key)
+        if ent is not None and src is ent[1]:
+            dst[:src.shape[0]].copy_(ent[0], non_blocking=True)
+        else:
+            self._up(dst, src)
+
     def _set_scalars(self, eng, kv):
         s = eng.scalars.cpu().numpy()
         for k, v in kv.items():
@@ -210,7 +231,7 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
 
     def _push(self):
         eng = self._engine()
-        self._up(eng.U.fac, self.U), self._up(eng.V.fac, self.V)
+        self._up_s('U', eng.U.fac, self.U), self._up_s('V', eng.V.fac, self.V)
         self._up(eng.U.lam, self.lambdaU), self._up(eng.V.lam, self.lambdaV)
         self._set_scalars(eng, {S_TAU: float(getattr(self, 'tau', 1.0))})
         return eng
@@ -225,9 +246,9 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
         def keep(it):
             all_U[it].copy_(eng.U.fac[:self.I]), all_V[it].copy_(eng.V.fac[:self.J])
         tr = self._run_loop(eng, iterations, per_iteration=keep)
-        self.all_U, self.all_V = self._down(all_U), self._down(all_V)
+        self.U, self.V = self._down_s('U', eng.U.fac, self.I), self._down_s('V', eng.V.fac, self.J)
+        self.all_U, self.all_V = self._down(all_U), self._down(all_V)      # (synchronises)
         self.all_tau = tr[:, 0].copy()
-        self.U, self.V = self._down(eng.U.fac, self.I), self._down(eng.V.fac, self.J)
         if iterations > 0:
             self.tau = float(tr[-1, 0])
         if self.verbose:
@@ -327,7 +348,8 @@ class nmf_icm(_TwoFactorBase):
         self._init_trace_lists()
         tr = self._run_loop(eng, iterations, minimum_TN=minimum_TN)
         self.all_tau = tr[:, 0].copy()
-        self.U, self.V = self._down(eng.U.fac, self.I), self._down(eng.V.fac, self.J)
+        self.U, self.V = self._down_s('U', eng.U.fac, self.I), self._down_s('V', eng.V.fac, self.J)
+        torch.cuda.current_stream().synchronize()
         if iterations > 0:
             self.tau = float(tr[-1, 0])
         return
@@ -378,8 +400,8 @@ class bnmf_vb_optimised(_TwoFactorBase):
     def _push(self):
         eng = self._engine()
         for f, s in ((eng.U, 'U'), (eng.V, 'V')):
-            self._up(f.fac, getattr(self, 'exp' + s)), self._up(f.var, getattr(self, 'var' + s))
-            self._up(f.mu, getattr(self, 'mu' + s)), self._up(f.tauf, getattr(self, 'tau' + s))
+            self._up_s('exp' + s, f.fac, getattr(self, 'exp' + s)), self._up_s('var' + s, f.var, getattr(self, 'var' + s))
+            self._up_s('mu' + s, f.mu, getattr(self, 'mu' + s)), self._up_s('tau' + s, f.tauf, getattr(self, 'tau' + s))
             self._up(f.lam, getattr(self, 'lambda' + s))
         self._set_scalars(eng, {S_TAU: float(getattr(self, 'exptau', 1.0)), S_LOGTAU: float(getattr(self, 'explogtau', 0.0)),
                                   S_BETA_S: float(getattr(self, 'beta_s', 1.0))})
@@ -389,7 +411,8 @@ class bnmf_vb_optimised(_TwoFactorBase):
         for f, s in ((eng.U, 'U'), (eng.V, 'V')):
             for attr, t in (('exp', f.fac), ('var', f.var), ('mu', f.mu), ('tau', f.tauf)):
                 if names is None or attr + s in names:
-                    setattr(self, attr + s, self._down(t, f.n))
+                    setattr(self, attr + s, self._down_s(attr + s, t, f.n))
+        torch.cuda.current_stream().synchronize()
 
     def run(self, iterations):
         eng = self._push()
