@@ -52,6 +52,20 @@ def gram_len(K):
     return nt * (nt + 1) // 2 * 64
 
 
+def _pick_nseg(units, ktiles, t_tile, t_fix, sms=148, nmax=32):
+    """Number of column segments for a tensor-bound kernel whose grid is `units` x nseg CTAs of one per SM: minimise
+    waves x (stages per CTA x t_tile + t_fix) [us] over the segment counts that leave no segment empty."""
+    best = None
+    for n in range(1, min(ktiles, nmax) + 1):
+        tps = -(-ktiles // n)
+        if -(-ktiles // tps) != n:
+            continue
+        cost = -(-(units * n) // sms) * (tps * t_tile + t_fix)
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, n)
+    return best[1]
+
+
 class Partition:
     """Contiguous equal-size row shards: rank p owns [lo(p), lo(p)+cnt(p)); the last shards may be short or empty."""
 
@@ -249,18 +263,23 @@ class BNMFEngine:
             rows = max(1, self.loc[side][1])
             rb = (rows + 127) // 128
             if self.rx == "umma":
+                # HBM-bound: enough CTAs to keep ~120 SMs streaming, as few segments as possible beyond that (every
+                # CTA pays ~10 us of tensor-memory set-up and pipeline fill)
                 kt64 = ld // 64
-                nrx = max(1, min(kt64, round(1480 / rb)))
+                nrx = max(1, min(kt64, -(-120 // rb)))
+                if rb * (kt64 // 160) >= 444:            # plenty of long CTAs: several waves even out the tail
+                    nrx = kt64 // 160
                 nrx = -(-kt64 // -(-kt64 // nrx))        # no empty segments
             else:
                 nrx = max(1, min(ld // 128, -(-2664 // rb)))
             if self.gram == "umma":
                 # CTAs = row blocks x column chunks x segments; aim for ~10 waves of one CTA per SM
                 tile = 128 if ld >= 256 else 64
-                nch = -(-(K * (K + 1) // 2 + (K if self.vb else 0)) // 73)
+                sums = K if (side == 1 and self.metrics_mode == "stats") else 0
+                nch = -(-(K * (K + 1) // 2 + (K if self.vb else 0) + sums) // 73)
                 ktiles = -(-ld // tile)
-                ng = max(1, min(ktiles, round(1480 / (rb * nch))))
-                ng = -(-ktiles // -(-ktiles // ng))      # no empty segments
+                ng = _pick_nseg(((rb + 1) // 2 * 2 if self.umma_pair else rb) * nch, ktiles,
+                                t_tile=0.55 * tile / 128, t_fix=10.0)
                 self.umma_tile = getattr(self, "umma_tile", {})
                 self.umma_tile[side] = tile
             else:
