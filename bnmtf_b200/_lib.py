@@ -23,7 +23,7 @@ SIGNATURES = {
     "bnmtf_rx_planes_bytes": [c_i64, c_i64],
     "bnmtf_rx_planes_pack_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     "bnmtf_rx_umma_workspace_bytes": [c_i, c_i64],
-    "bnmtf_stats_rx_umma_f64": [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i, c_i, c_p, c_p, c_i64, c_p],
+    "bnmtf_stats_rx_umma_f64": [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_i64, c_p],
     "bnmtf_stats_gram_f64": [c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "bnmtf_gram_full_f64": [c_p, c_p, c_i64, c_i, c_i64, c_p, c_p, c_p],
     "bnmtf_gram_umma_workspace_bytes": [c_i, c_i, c_i64],

@@ -30,7 +30,7 @@ long long rxu_planes_bytes(long long, long long);
 long long rxu_workspace_bytes(int, long long);
 int launch_rxu_pack(const double*, const uint32_t*, int, int, uint8_t*, double*, int*, cudaStream_t);
 int launch_stats_rx_umma(const uint8_t*, const double*, const double*, const uint32_t*, int, int, int, const double*, int, int,
-                         double*, void*, long long, cudaStream_t);
+                         int, double*, void*, long long, cudaStream_t);
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 long long umma_workspace_bytes(int, int, long long);
@@ -179,11 +179,11 @@ int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld) {
 }
 
 int bnmtf_stats_rx_umma_f64(const uint8_t* planes, const double* rscale, const double* R, const uint32_t* bits,
-                            int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, double* RXpart,
-                            void* workspace, int64_t workspace_bytes, void* stream) {
+                            int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, int max_ctas,
+                            double* RXpart, void* workspace, int64_t workspace_bytes, void* stream) {
   if (check_k(K)) return -2;
-  return launch_stats_rx_umma(planes, rscale, R, bits, (int)rows, (int)ld, (int)cols, Xp, K, nseg, RXpart, workspace,
-                              workspace_bytes, ST(stream));
+  return launch_stats_rx_umma(planes, rscale, R, bits, (int)rows, (int)ld, (int)cols, Xp, K, nseg, max_ctas, RXpart,
+                              workspace, workspace_bytes, ST(stream));
 }
 
 int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp, int K,

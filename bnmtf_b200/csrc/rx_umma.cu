@@ -202,7 +202,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 struct RxUmmaArgs {
   const uint8_t* planes; const double* rscale; const double* cscale; const int* flag;
-  int rows, K, KP, ktiles, tiles_per_seg, stages;
+  int rows, K, KP, ktiles, tiles_per_seg, stages, nseg;
   double* out;
 };
 
@@ -225,11 +225,12 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
 #define ACC_FULL(b) (bar_base + 8u * (uint32_t)(2 * stages + (b)))
 #define ACC_EMPTY(b) (bar_base + 8u * (uint32_t)(2 * stages + 2 + (b)))
 
-  const int rb = blockIdx.x, seg = blockIdx.y;
-  const int kt_begin = seg * a.tiles_per_seg;
-  const int kt_end = min(a.ktiles, kt_begin + a.tiles_per_seg);
-  const int ntile = kt_end - kt_begin;
-  const int nper = (ntile + RXU_DRAIN - 1) / RXU_DRAIN;
+  // Persistent CTA: work items (segment-major: item = seg * row_blocks + row_block, so that concurrently running
+  // CTAs read the same factor-digit tiles from L2) are taken round-robin; the smem stage ring, the accumulator-set
+  // ring and all mbarrier phases simply continue from one item to the next.  A launch with fewer CTAs than SMs
+  // leaves the other SMs to a kernel running beside it (the HBM-bound R.X next to the tensor-bound Gram).
+  const int rbs = (a.rows + 127) >> 7;
+  const int nitems = rbs * a.nseg;
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), 1); mbar_init(EMPTY_BAR(s), 1); }
@@ -248,7 +249,6 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
 
   if (warp < 4) {
     // ================= accumulator drains: thread <-> row =================
-    const int row = rb * 128 + tid;
     const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
     for (int c0 = 0; c0 < 2 * SET; c0 += 16) tmem_st_zero16(tlane + c0);
@@ -256,55 +256,69 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
     tc_fence_before();
     mbar_arrive(ACC_EMPTY(0));
     mbar_arrive(ACC_EMPTY(1));
-    double c[KPAD];
+    uint32_t dg = 0;                                    // accumulator periods so far (all items)
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int seg = item / rbs, rb = item - seg * rbs;
+      const int kt_begin = seg * a.tiles_per_seg;
+      const int ntile = min(a.ktiles, kt_begin + a.tiles_per_seg) - kt_begin;
+      const int nper = (ntile + RXU_DRAIN - 1) / RXU_DRAIN;
+      const int row = rb * 128 + tid;
+      double c[KPAD];
 #pragma unroll
-    for (int k = 0; k < KPAD; ++k) c[k] = 0.0;
-    for (int d = 0; d < nper; ++d) {
-      const int b = d & 1;
-      mbar_wait(ACC_FULL(b), (uint32_t)(d >> 1) & 1u);
-      tc_fence_after();
+      for (int k = 0; k < KPAD; ++k) c[k] = 0.0;
+      for (int d = 0; d < nper; ++d, ++dg) {
+        const uint32_t b = dg & 1u;
+        mbar_wait(ACC_FULL(b), (dg >> 1) & 1u);
+        tc_fence_after();
 #pragma unroll
-      for (int h = 0; h < KPAD / 16; ++h) {              // 16 factor columns at a time keeps the register count down
-        double v[16];
+        for (int h = 0; h < KPAD / 16; ++h) {            // 16 factor columns at a time keeps the register count down
+          double v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = 0.0;
+          for (int k = 0; k < 16; ++k) v[k] = 0.0;
 #pragma unroll
-        for (int u = RXU_NU - 1; u >= 0; --u) {
-          uint32_t reg[16];
-          tmem_ld_n<16>(tlane + (uint32_t)(b * SET + u * KPAD + 16 * h), reg);
-          tmem_ld_wait();
+          for (int u = RXU_NU - 1; u >= 0; --u) {
+            uint32_t reg[16];
+            tmem_ld_n<16>(tlane + (uint32_t)(b * SET + u * KPAD + 16 * h), reg);
+            tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = fma(v[k], 256.0, (double)(int)reg[k]);
+            for (int k = 0; k < 16; ++k) v[k] = fma(v[k], 256.0, (double)(int)reg[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) c[16 * h + k] += v[k];
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) c[16 * h + k] += v[k];
+        for (int c0 = 0; c0 < SET; c0 += 16) tmem_st_zero16(tlane + (uint32_t)(b * SET + c0));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(ACC_EMPTY(b));
       }
+      if (row < a.rows) {
+        const double rs = a.rscale[row] * 1099511627776.0;        // 2^40 = 256^UMIN
+        double* o = a.out + ((size_t)seg * a.rows + row) * a.KP;
 #pragma unroll
-      for (int c0 = 0; c0 < SET; c0 += 16) tmem_st_zero16(tlane + (uint32_t)(b * SET + c0));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(ACC_EMPTY(b));
-    }
-    if (row < a.rows) {
-      const double rs = a.rscale[row] * 1099511627776.0;          // 2^40 = 256^UMIN
-      double* o = a.out + ((size_t)seg * a.rows + row) * a.KP;
-#pragma unroll
-      for (int k = 0; k < KPAD; ++k)
-        if (k < a.KP) o[k] = (k < a.K) ? c[k] * rs * a.cscale[k] : 0.0;
-      for (int k = KPAD; k < a.KP; ++k) o[k] = 0.0;
+        for (int k = 0; k < KPAD; ++k)
+          if (k < a.KP) o[k] = (k < a.K) ? c[k] * rs * a.cscale[k] : 0.0;
+        for (int k = KPAD; k < a.KP; ++k) o[k] = 0.0;
+      }
     }
     tc_fence_before();
   } else if (warp == 4) {
     // ================= producer: one bulk copy of the seven plane tiles + the digit rows of X =================
     if (lane == 0) {
-      for (int it = 0; it < ntile; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u;
-        mbar_wait(EMPTY_BAR(s), ph ^ 1u);
-        mbar_expect_tx(FULL_BAR(s), (uint32_t)STAGE);
-        const uint32_t dst = smem_base + (uint32_t)s * STAGE;
-        bulk_load(dst, a.planes + rxu_tile_offset(rb, kt_begin + it, a.ktiles), (uint32_t)RXU_A_BYTES, FULL_BAR(s));
-        tma_load_2d(dst + RXU_A_BYTES, &tmap, (kt_begin + it) * RXU_KT, 0, FULL_BAR(s));
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int seg = item / rbs, rb = item - seg * rbs;
+        const int kt_begin = seg * a.tiles_per_seg;
+        const int ntile = min(a.ktiles, kt_begin + a.tiles_per_seg) - kt_begin;
+        for (int it = 0; it < ntile; ++it) {
+          mbar_wait(EMPTY_BAR(s), ph ^ 1u);
+          mbar_expect_tx(FULL_BAR(s), (uint32_t)STAGE);
+          const uint32_t dst = smem_base + (uint32_t)s * STAGE;
+          bulk_load(dst, a.planes + rxu_tile_offset(rb, kt_begin + it, a.ktiles), (uint32_t)RXU_A_BYTES, FULL_BAR(s));
+          tma_load_2d(dst + RXU_A_BYTES, &tmap, (kt_begin + it) * RXU_KT, 0, FULL_BAR(s));
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
       }
     }
     __syncwarp();
@@ -313,38 +327,44 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
     // the whole warp runs the loop (descriptors stay in uniform registers); one elected lane issues
     {
       int s = 0;
-      uint32_t ph = 0;
-      for (int d = 0; d < nper; ++d) {
-        const int b = d & 1;
-        mbar_wait(ACC_EMPTY(b), (uint32_t)(d >> 1) & 1u);
-        tc_fence_after();
-        const int it_end = min(ntile, (d + 1) * RXU_DRAIN);
-        for (int it = d * RXU_DRAIN; it < it_end; ++it) {
-          mbar_wait(FULL_BAR(s), ph);
+      uint32_t ph = 0, dg = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int seg = item / rbs;
+        const int kt_begin = seg * a.tiles_per_seg;
+        const int ntile = min(a.ktiles, kt_begin + a.tiles_per_seg) - kt_begin;
+        const int nper = (ntile + RXU_DRAIN - 1) / RXU_DRAIN;
+        for (int d = 0; d < nper; ++d, ++dg) {
+          const uint32_t b = dg & 1u;
+          mbar_wait(ACC_EMPTY(b), (dg >> 1) & 1u);
           tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)s * STAGE;
-          if (elect_one()) {
+          const int it_end = min(ntile, (d + 1) * RXU_DRAIN);
+          for (int it = d * RXU_DRAIN; it < it_end; ++it) {
+            mbar_wait(FULL_BAR(s), ph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)s * STAGE;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < RXU_KT / 32; ++kk) {
+              for (int kk = 0; kk < RXU_KT / 32; ++kk) {
 #pragma unroll
-              for (int p = 0; p < RXU_PLANES; ++p) {
-                const int tmin = p < RXU_UMIN ? RXU_UMIN - p : 0;
-                const int nt = RXU_VDIG - tmin;
-                // D = s32, A = u8 (top plane: s8), B = u8, K-major both, N = nt*KPAD, M = 128
-                const uint32_t idesc = (2u << 4) | ((p == RXU_PLANES - 1 ? 1u : 0u) << 7) |
-                                       ((uint32_t)((nt * KPAD) >> 3) << 17) | (8u << 24);
-                const uint64_t ad = umma_desc<RXU_KT>(sa + (uint32_t)p * RXU_PLANE_TILE) + 2 * kk;
-                const uint64_t bd = umma_desc<RXU_KT>(sa + RXU_A_BYTES + (uint32_t)(tmin * KPAD * RXU_KT)) + 2 * kk;
-                umma_i8(tmem_base + (uint32_t)(b * SET + (p + tmin - RXU_UMIN) * KPAD), ad, bd, idesc, 1u);
+                for (int p = 0; p < RXU_PLANES; ++p) {
+                  const int tmin = p < RXU_UMIN ? RXU_UMIN - p : 0;
+                  const int nt = RXU_VDIG - tmin;
+                  // D = s32, A = u8 (top plane: s8), B = u8, K-major both, N = nt*KPAD, M = 128
+                  const uint32_t idesc = (2u << 4) | ((p == RXU_PLANES - 1 ? 1u : 0u) << 7) |
+                                         ((uint32_t)((nt * KPAD) >> 3) << 17) | (8u << 24);
+                  const uint64_t ad = umma_desc<RXU_KT>(sa + (uint32_t)p * RXU_PLANE_TILE) + 2 * kk;
+                  const uint64_t bd = umma_desc<RXU_KT>(sa + RXU_A_BYTES + (uint32_t)(tmin * KPAD * RXU_KT)) + 2 * kk;
+                  umma_i8(tmem_base + b * SET + (uint32_t)((p + tmin - RXU_UMIN) * KPAD), ad, bd, idesc, 1u);
+                }
               }
+              umma_commit(EMPTY_BAR(s));
             }
-            umma_commit(EMPTY_BAR(s));
+            __syncwarp();
+            if (++s == stages) { s = 0; ph ^= 1u; }
           }
+          if (elect_one()) umma_commit(ACC_FULL(b));
           __syncwarp();
-          if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        if (elect_one()) umma_commit(ACC_FULL(b));
-        __syncwarp();
       }
     }
     __syncwarp();
@@ -388,8 +408,8 @@ int launch_stats_rx(const double* R, const uint32_t* bits, int rows, int ld, con
                     const int* run_flag, cudaStream_t st);
 
 int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const double* R, const uint32_t* bits, int rows, int ld,
-                         int cols, const double* Xp, int K, int nseg, double* out, void* workspace, long long workspace_bytes,
-                         cudaStream_t st) {
+                         int cols, const double* Xp, int K, int nseg, int max_ctas, double* out, void* workspace,
+                         long long workspace_bytes, cudaStream_t st) {
   if (rows <= 0 || ld <= 0 || ld % 64 || nseg <= 0 || cols <= 0 || cols > ld) { set_error("stats_rx_umma: bad shape"); return -2; }
   if (K > 32) { set_error("stats_rx_umma: K=%d > 32 (use the DMMA kernel)", K); return -2; }
   if (workspace_bytes < rxu_workspace_bytes(K, ld)) { set_error("stats_rx_umma: workspace too small"); return -2; }
@@ -427,21 +447,31 @@ int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const doub
   a.rows = rows; a.K = K; a.KP = KP; a.ktiles = ld / RXU_KT;
   a.tiles_per_seg = (a.ktiles + nseg - 1) / nseg;
   if ((a.ktiles + a.tiles_per_seg - 1) / a.tiles_per_seg != nseg) { set_error("stats_rx_umma: nseg=%d leaves empty segments", nseg); return -2; }
-  a.out = out;
+  a.out = out; a.nseg = nseg;
   const int stage_bytes = RXU_A_BYTES + RXU_VDIG * KPAD * RXU_KT;
   const int tail = (2 * 8 + 4) * 8 + 64;
   int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
   if (stages > 8) stages = 8;
   a.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + tail + 1024;      // > half an SM: one CTA (and its 512 TMEM columns) per SM
-  dim3 grid((rows + 127) / 128, nseg);
-  if (KPAD == 32) {
-    cudaFuncSetAttribute(k_rx_umma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_rx_umma<32><<<grid, RXU_THREADS, smem, st>>>(tmap, a);
-  } else {
-    cudaFuncSetAttribute(k_rx_umma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_rx_umma<16><<<grid, RXU_THREADS, smem, st>>>(tmap, a);
-  }
+  // persistent CTAs, one per SM; max_ctas > 0 caps their number (rounded down to whole SM pairs and launched as
+  // clusters of two so that they occupy whole TPCs and leave whole TPCs to the CTA pairs of a concurrent kernel)
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  const int nitems = ((rows + 127) / 128) * nseg;
+  int nctas = nitems;                                  // default: one item per CTA (the block scheduler balances the tail)
+  int cluster = 1;
+  if (max_ctas > 0 && max_ctas < nctas && max_ctas <= sm_count) { nctas = max_ctas; if (nctas >= 2) { nctas &= ~1; cluster = 2; } }
+  void (*kern)(const CUtensorMap, RxUmmaArgs) = KPAD == 32 ? k_rx_umma<32> : k_rx_umma<16>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nctas); cfg.blockDim = dim3(RXU_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+  if (le != cudaSuccess) { set_error("stats_rx_umma: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return -1; }
   if (check_launch("stats_rx_umma")) return -1;
   // factor with negative / non-finite entries: the fp64 kernel produces the same nseg partial results instead
   return launch_stats_rx(R, bits, rows, ld, Xp, K, nseg, out, flag, st);

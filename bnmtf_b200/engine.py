@@ -236,6 +236,7 @@ class BNMFEngine:
         g = int(os.environ.get("BNMTF_GRAPH", "1"))
         self.use_graph = g >= 2 or (g == 1 and dataset.world == 1)
         self._graph = self._graph_key = self._graph_seen = None
+        self.split = int(os.environ.get("BNMTF_SPLIT", "72"))    # SMs given to the R.X kernel when both run concurrently (0: one after the other)
         self.umma_pair = int(os.environ.get("BNMTF_UMMA_PAIR", "1"))   # CTA pairs (cta_group::2) in the Gram kernel
         self._side = None
         self.m = MODE[mode]
@@ -364,7 +365,21 @@ class BNMFEngine:
             _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, self.K, ld,
                       _ptr(self.Gfull), _ptr(self.gscratch), _stream())
         rx = lambda: self._rx(side)
-        if need_rx and self.overlap:
+        if need_rx and self.split > 0 and self.rx == "umma" and self.gram == "umma":
+            # SM split: the persistent, HBM-bound R.X kernel takes `split` SMs (high-priority stream, launched first),
+            # the tensor-bound Gram kernel the rest; neither could share an SM's tensor memory with the other
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.ds.device, priority=-1)
+                self._ev = [torch.cuda.Event(), torch.cuda.Event()]
+            main = torch.cuda.current_stream()
+            self._ev[0].record(main)
+            self._side.wait_event(self._ev[0])
+            with torch.cuda.stream(self._side):
+                self._rx(side, max_ctas=self.split)
+                self._ev[1].record(self._side)
+            self._gram(side, sums)
+            main.wait_event(self._ev[1])
+        elif need_rx and self.overlap:
             # the Gram kernel goes to a high-priority stream: its one-per-SM, long-lived CTAs are placed as soon as
             # a CTA of the streaming kernel retires, and the two then share every SM (tensor pipe | fp64 pipe + HBM)
             if self._side is None:
@@ -386,13 +401,13 @@ class BNMFEngine:
                 rx()
             self._gram(side, sums)
 
-    def _rx(self, side):
+    def _rx(self, side, max_ctas=0):
         me, other, R, bits, rows, ld, lo = self._sides(side)
         nrx = self.nseg[side][0]
         if self.rx == "umma":
             planes, rscale = self.ds.ensure_planes(side)[:2]
             _lib.call("bnmtf_stats_rx_umma_f64", planes.data_ptr(), _ptr(rscale), _ptr(R), _ptr(bits), rows, ld, other.n,
-                      _ptr(other.Xp), self.K, nrx, _ptr(self.RXpart), self.wsrx_ptr, self.wsrx_bytes, _stream())
+                      _ptr(other.Xp), self.K, nrx, max_ctas, _ptr(self.RXpart), self.wsrx_ptr, self.wsrx_bytes, _stream())
         else:
             _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), self.K, nrx,
                       _ptr(self.RXpart), _stream())

@@ -80,15 +80,17 @@ int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int6
  * rexp_scratch = rows int32), 7 instead of 8.125 bytes per entry streamed per phase.  Per call the factor is cut into
  * digits too (K <= 32, entries >= 0) and the digit products are accumulated exactly in int32 tensor memory.  If the
  * factor has a negative or non-finite entry, a device-side flag routes the call to the fp64 kernel above (R, bits are
- * only read in that case); RXpart always receives nseg valid partial results.
+ * only read in that case); RXpart always receives nseg valid partial results.  The kernel is persistent (one CTA per
+ * SM looping over 128-row x segment work items); max_ctas > 0 caps the number of CTAs, leaving the other SMs to a
+ * kernel running concurrently on another stream (0: all SMs).
  * workspace: >= bnmtf_rx_umma_workspace_bytes(K, ld) bytes, 1024-byte aligned. */
 int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld);
 int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
                              double* rscale, int32_t* rexp_scratch, void* stream);
 int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld);
 int bnmtf_stats_rx_umma_f64(const uint8_t* planes, const double* rscale, const double* R, const uint32_t* bits,
-                            int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, double* RXpart,
-                            void* workspace, int64_t workspace_bytes, void* stream);
+                            int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, int max_ctas,
+                            double* RXpart, void* workspace, int64_t workspace_bytes, void* stream);
 /* polarity 0: accumulate over the MISSING entries of each row (cheap when most entries are observed; the solver
  * subtracts from Gfull), 1: over the OBSERVED entries. */
 int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp /*or NULL*/,

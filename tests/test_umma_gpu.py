@@ -143,7 +143,7 @@ def _rx_both(d, rows, cols, K, nseg):
     O1 = torch.full((nseg * rows, KP), float("nan"), dtype=torch.float64, device=dev)
     O0 = torch.full((nseg * rows, KP), float("nan"), dtype=torch.float64, device=dev)
     _lib.call("bnmtf_stats_rx_umma_f64", pptr, _ptr(rscale), _ptr(d["Rp"]), _ptr(d["bits"]), rows, ld, cols, _ptr(d["Xp"]), K,
-              nseg, _ptr(O1), wsp, wsb, _stream())
+              nseg, 0, _ptr(O1), wsp, wsb, _stream())
     _lib.call("bnmtf_stats_rx_f64", _ptr(d["Rp"]), _ptr(d["bits"]), rows, ld, _ptr(d["Xp"]), K, nseg, _ptr(O0), _stream())
     torch.cuda.synchronize()
     return (O1.view(nseg, rows, KP).sum(0)[:, :K].cpu().numpy(), O0.view(nseg, rows, KP).sum(0)[:, :K].cpu().numpy())

@@ -12,6 +12,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAXCTAS = int(os.environ.get("MAXCTAS", "0"))
 sys.path.insert(0, ROOT)
 
 # rows, cols, K, nseg, kind of data, timing reps
@@ -83,7 +84,7 @@ def run_case(idx):
 
     def umma():
         _lib.call("bnmtf_stats_rx_umma_f64", pptr, _ptr(rscale), _ptr(R), _ptr(bits), rows, ld, cols, _ptr(Xp), K, nseg,
-                  _ptr(O1), wsp, wsb, _stream())
+                  MAXCTAS, _ptr(O1), wsp, wsb, _stream())
 
     def dmma():
         _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(Xp), K, nseg, _ptr(O0), _stream())
