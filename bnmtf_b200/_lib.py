@@ -81,6 +81,22 @@ class BnmtfError(RuntimeError):
     pass
 
 
+_seed_calls = [0]
+
+
+def derive_seed():
+    """A Philox seed for the device-side draws that is a deterministic function of numpy's global random state and of
+    how many seeds were asked for so far, WITHOUT consuming from that stream: the host random numbers the reference
+    draws (initialisations, folds, K-means) keep their positions, so seeded runs with several models stay aligned
+    with the reference."""
+    import numpy as np
+    st = np.random.get_state()
+    keys, pos = st[1], int(st[2])
+    _seed_calls[0] += 1
+    h = (int(keys[pos % 624]) * 2654435761 + int(keys[(pos + 311) % 624]) * 40503 + pos * 97 + _seed_calls[0] * 1000003)
+    return int(h % (2 ** 31 - 1))
+
+
 def load():
     """Load the shared library (once) and declare every prototype of include/bnmtf_b200.h."""
     global _lib

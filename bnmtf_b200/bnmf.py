@@ -104,7 +104,7 @@ class _TwoFactorBase(object):
                 world, rank = dist.get_world_size(), dist.get_rank()
             ds = Dataset.from_host(self.R, self.M, dev, world, rank)
             # every rank must use the same Philox seed: draw it from numpy's (seeded) stream or pass seed=
-            seed = self._seed if self._seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+            seed = self._seed if self._seed is not None else _lib.derive_seed()
             self._eng = BNMFEngine(ds, self.K, self._mode, self.alpha, self.beta, seed=seed)
         return self._eng
 

@@ -262,7 +262,7 @@ class _ThreeFactorBase(object):
         if self._eng is None:
             dev = require_cuda(self._device_arg)
             ds = Dataset.from_host(self.R, self.M, dev)
-            seed = self._seed if self._seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+            seed = self._seed if self._seed is not None else _lib.derive_seed()
             self._eng = BNMTFEngine(ds, self.K, self.L, self._mode, self.alpha, self.beta, seed=seed)
         return self._eng
 

@@ -17,6 +17,8 @@ int check_launch(const char* what);
 constexpr int kMaxTiles = 8;            // KP = 8*NT <= 64  ->  K <= 63 latent factors
 constexpr double kInvSqrt2 = 0.70710678118654752440;
 constexpr double kInvSqrt2Pi = 0.39894228040143267794;
+constexpr double kSqrt2 = 1.4142135623730951;       // math.sqrt(2), the divisor the reference uses
+constexpr double kSqrt2Pi = 2.5066282746310002;     // numpy.sqrt(2*pi), scipy.stats.norm's _norm_pdf_C
 constexpr double kLog2Pi = 1.8378770664093454836;
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -142,6 +144,19 @@ struct Philox {
 // ---- truncated normal N(mu, 1/tau) on [0, inf) -------------------------------------------------------
 __device__ __forceinline__ double clean_nonneg(double v) { return (v >= 0.0 && isfinite(v)) ? v : 0.0; }
 
+// erfc as the reference's SciPy evaluates it.  scipy.special.erfc is Cephes' ndtr.c: for |a| >= 1 it returns
+// exp(-a*a) * P(a)/Q(a), and the ROUNDING of the product a*a (relative 2^-53, i.e. an absolute 1e-16 * a^2 in the
+// exponent) is by far its largest error -- up to 2e-13 relative in the tail, which the TN variance below amplifies by
+// x^4.  An exactly rounded erfc therefore does NOT reproduce the reference there; exp(-(a*a)) * erfcx(a) with the
+// same rounded a*a does (to ~1e-15; measured against SciPy on 2e6 points), and so does the variance (6e-10 at the
+// 30-sigma switch instead of 1.3e-7).
+__device__ __forceinline__ double erfc_ref(double a) {
+  const double t = fabs(a);
+  if (t < 1.0) return erfc(a);
+  const double y = exp(-__dmul_rn(t, t)) * erfcx(t);
+  return a < 0.0 ? 2.0 - y : y;
+}
+
 // Mean and variance exactly as the reference evaluates them (truncated_normal_vector.py:53-73): same
 // formula, same mu < -30 sigma switch to the exponential limit, same clamp of non-finite / negative to 0.
 __device__ __forceinline__ void tn_moments(double mu, double tau, double& e, double& v) {
@@ -151,7 +166,8 @@ __device__ __forceinline__ void tn_moments(double mu, double tau, double& e, dou
     v = e * e;
   } else {
     double x = -mu / sigma;
-    double lam = (exp(-0.5 * x * x) * kInvSqrt2Pi) / (0.5 * erfc(x * kInvSqrt2));
+    // norm.pdf(x) = exp(-x**2/2) / sqrt(2 pi);  0.5 * erfc(x / sqrt(2)) -- same operations, same roundings
+    double lam = (exp(-0.5 * __dmul_rn(x, x)) / kSqrt2Pi) / (0.5 * erfc_ref(x / kSqrt2));
     e = mu + sigma * lam;
     v = sigma * sigma * (1.0 - lam * (lam - x));
   }

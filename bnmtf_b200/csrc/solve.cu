@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(256) k_vb_factor_terms(const double* __restric
     const double l = lambda[i], e = ex[i], v = var[i], m = mu[i], t = tauf[i];
     s0 += log(l) - l * e;
     const double d = e - m;
-    s1 += -0.5 * log(t) + log(0.5 * erfc(-m * sqrt(t) * kInvSqrt2)) + t * 0.5 * (v + d * d);
+    s1 += -0.5 * log(t) + log(0.5 * erfc_ref(-m * sqrt(t) / kSqrt2)) + t * 0.5 * (v + d * d);
   }
   __shared__ double red[8][2];
   s0 = warp_sum(s0); s1 = warp_sum(s1);

@@ -10,6 +10,7 @@ phase, so each rank runs the same kernels on its shard and the only exchanges pe
 factor rows after each phase and one all-reduce of the metric / ELBO partial sums.
 """
 import os
+import threading
 
 import numpy as np
 import torch
@@ -17,6 +18,9 @@ import torch
 from . import _lib
 
 MODE = {"gibbs": 0, "vb": 1, "icm": 2}
+# per-thread switches: DevicePool workers set no_graph (stream capture is process-global: a capture on one thread is
+# invalidated by allocations and function-attribute calls made by the fits running on the other threads)
+thread_flags = threading.local()
 TRACE_COLS = ("tau", "MSE", "R^2", "Rp", "ELBO", "sum_e2", "exp_square_diff", "explogtau")
 S_TAU, S_LOGTAU, S_ALPHA_S, S_BETA_S, S_SUM_E2, S_ESD, S_MSE, S_R2, S_RP, S_ELBO = range(10)
 
@@ -529,7 +533,7 @@ class BNMFEngine:
         """One iteration of run().  The launch sequence of a sweep is static (about 45 launches, every pointer fixed
         while the trace buffer stays the same, the sweep counter lives on the device), so from the second sweep of a
         run on it is replayed as one CUDA graph: the small kernels between the big ones no longer wait for the host."""
-        if self.use_graph:
+        if self.use_graph and not getattr(thread_flags, "no_graph", False):
             key = (self.trace.data_ptr() if self.trace is not None else 0, self.trace_base, self.trace_cap, float(minimum_TN))
             if self._graph is not None and self._graph_key == key:
                 self._graph.replay()

@@ -7,6 +7,12 @@ over the coordinates observed in both the point and the centroid (None / infinit
 to the lowest cluster index); centroid = per-coordinate mean of the observed values of its points (coordinate masked
 out when none is observed); an empty cluster takes the point currently furthest from its centroid ('singleton');
 stop when no assignment changes or after 200 iterations; result = one-hot assignment matrix.
+
+One reference quirk is kept on purpose, because it changes the clustering in about a third of seeded runs on the toy
+data: the 'singleton' rule binds the empty cluster's centroid to the ROW OF X ITSELF (kmeans.py:149,
+`self.centroids[c] = self.X[index_furthest_away]`, a numpy view of the model's private copy of X), so every later
+centroid update of that cluster (kmeans.py:170) also overwrites that data point.  Here the centroids are a list of row
+arrays as well, and the singleton rule stores the view, so the same write-through happens.
 """
 import random
 
@@ -40,7 +46,7 @@ class KMeans(object):
         obs = self.M != 0
         self.mins = [self.X[obs[:, j], j].min() for j in range(self.no_coordinates)]
         self.maxs = [self.X[obs[:, j], j].max() for j in range(self.no_coordinates)]
-        self.centroids = np.array([self.random_cluster_centroid() for _ in range(self.K)], dtype=float)
+        self.centroids = [np.array(self.random_cluster_centroid(), dtype=float) for _ in range(self.K)]
         self.cluster_assignments = np.full(self.no_points, -1, dtype=int)
         self.mask_centroids = np.ones((self.K, self.no_coordinates))
 
@@ -62,7 +68,7 @@ class KMeans(object):
         """no_points x K matrix of masked mean squared differences (inf where nothing overlaps)."""
         both = self.M[:, None, :] * self.mask_centroids[None, :, :]
         overlap = both.sum(axis=2)
-        sq = (both * (self.X[:, None, :] - self.centroids[None, :, :]) ** 2).sum(axis=2)
+        sq = (both * (self.X[:, None, :] - np.stack(self.centroids)[None, :, :]) ** 2).sum(axis=2)
         with np.errstate(all='ignore'):
             return np.where(overlap > 0, sq / overlap, np.inf)
 
@@ -87,7 +93,7 @@ class KMeans(object):
                 if self.resolve_empty == 'singleton':
                     far = int(self.distances.argmax())
                     old = int(self.cluster_assignments[far])
-                    self.centroids[c] = self.X[far]
+                    self.centroids[c] = self.X[far]          # a VIEW: later updates of c write through into X (see top)
                     self.mask_centroids[c] = self.M[far]
                     self.distances[far] = 0.0
                     self.cluster_assignments[far] = c
@@ -95,14 +101,14 @@ class KMeans(object):
                     self.data_point_assignments[old].remove(far)
                     self.update_cluster(old)
                 else:
-                    self.centroids[c] = self.random_cluster_centroid()
+                    self.centroids[c] = np.array(self.random_cluster_centroid(), dtype=float)
                     self.mask_centroids[c] = np.ones(self.no_coordinates)
             return
         Xc, Mc = self.X[members], self.M[members]
         counts = Mc.sum(axis=0)
         with np.errstate(all='ignore'):
             means = np.where(counts > 0, (Mc * Xc).sum(axis=0) / counts, 0.0)
-        self.centroids[c] = means
+        self.centroids[c][:] = means                         # in place, like the reference's per-coordinate writes
         self.mask_centroids[c] = (counts > 0).astype(float)
 
     def create_matrix(self):
