@@ -1,5 +1,6 @@
 // Layer 2 for the two-factor model R ~ U V^T: per-row sequential column updates from the row statistics,
 // the masked prediction metrics, the noise-precision update and the small elementwise helpers.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bnmtf {
@@ -167,6 +168,122 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
     e = warp_sum(e);
     if (lane == 0) a.extra[row] = e;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_bnmf_row_solve_lane: the same per-row update with ONE THREAD per row, for the natural column order.
+//
+// The K updates of a row form a serial chain whose links are a truncated-normal draw / moment evaluation (a few
+// hundred dependent fp64 instructions).  With a warp per row all 32 lanes walk that chain redundantly and a
+// 65536-row phase needs ~10 waves of resident warps, each as long as the chain (0.41-0.47 ms, fp64 pipe 35 % busy
+// with redundant work).  With a thread per row the whole phase is one wave of 14 warps per SM, and the Gram row is
+// read exactly once from its packed tiles (row k of the upper triangle, contiguous 64-byte pieces):
+//     dot_k = acc[k] + sum_{c>k} G[k][c] u_c(old),   then   acc[c] += G[k][c] u_k(new)  for c > k,
+// i.e. acc[k] = sum_{c<k} G[c][k] u_c(new) has been pushed by the earlier columns (G is symmetric).  The per-row
+// outputs for the statistics-based metrics and the VB extra term accumulate along the way:
+//     sum p^2 = u^T G u = sum_k u_k (G_kk u_k + 2 acc[k]),   sum r p = sum_k u_k RX_k,   sum p = sum_k u_k G[k][K].
+// u and acc live in shared memory ([column][thread], conflict-free), so K is a runtime value.
+// ---------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) {
+  constexpr int KP = 8 * NT;
+  constexpr int NTP = NT * (NT + 1) / 2;
+  __shared__ double u_s[KP][32];
+  __shared__ double acc_s[KP][32];
+  const int lane = threadIdx.x;
+  const int row = blockIdx.x * 32 + lane;
+  if (row >= a.rows) return;
+  const int K = a.K;
+  const bool vb = a.mode == MODE_VB;
+  for (int c = 0; c < KP; ++c) {
+    u_s[c][lane] = c < K ? a.fac[(size_t)row * K + c] : 0.0;
+    acc_s[c][lane] = 0.0;
+  }
+  const double tau = a.scalars[S_TAU];
+  const unsigned long long it = a.iter ? *a.iter : 0ull;
+  const size_t gstride = (size_t)a.rows * (NTP * 64);
+  const double* grow = a.Gpart + (size_t)row * (NTP * 64);
+  double rp = 0.0, pp = 0.0, sp = 0.0, ex = 0.0;
+
+  for (int k = 0; k < K; ++k) {
+    const int ta = k >> 3, r = k & 7;
+    // row k of the upper triangle: tiles (ta, tb >= ta), 8 contiguous doubles each
+    double g[KP];
+#pragma unroll
+    for (int tb = 0; tb < NT; ++tb) {
+      if (tb >= ta) {
+        const int off = tile_pair(ta, tb, NT) * 64 + r * 8;
+        double4 lo = make_double4(0, 0, 0, 0), hi = make_double4(0, 0, 0, 0);
+        for (int sgm = 0; sgm < a.nseg_g; ++sgm) {
+          const double4 x = *reinterpret_cast<const double4*>(grow + sgm * gstride + off);
+          const double4 y = *reinterpret_cast<const double4*>(grow + sgm * gstride + off + 4);
+          lo.x += x.x; lo.y += x.y; lo.z += x.z; lo.w += x.w;
+          hi.x += y.x; hi.y += y.y; hi.z += y.z; hi.w += y.w;
+        }
+        if (!a.polarity) {
+          const double4 x = *reinterpret_cast<const double4*>(a.Gfull + off);
+          const double4 y = *reinterpret_cast<const double4*>(a.Gfull + off + 4);
+          lo.x = x.x - lo.x; lo.y = x.y - lo.y; lo.z = x.z - lo.z; lo.w = x.w - lo.w;
+          hi.x = y.x - hi.x; hi.y = y.y - hi.y; hi.z = y.z - hi.z; hi.w = y.w - hi.w;
+        }
+        g[8 * tb + 0] = lo.x; g[8 * tb + 1] = lo.y; g[8 * tb + 2] = lo.z; g[8 * tb + 3] = lo.w;
+        g[8 * tb + 4] = hi.x; g[8 * tb + 5] = hi.y; g[8 * tb + 6] = hi.z; g[8 * tb + 7] = hi.w;
+      }
+    }
+    double rxk = 0.0, svk = 0.0;
+    for (int sgm = 0; sgm < a.nseg_rx; ++sgm) rxk += a.RXpart[((size_t)sgm * a.rows + row) * KP + k];
+    if (vb) {
+      double t = 0.0;
+      for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += a.SVpart[((size_t)sgm * a.rows + row) * KP + k];
+      svk = a.polarity ? t : a.Gfull[NTP * 64 + k] - t;
+    }
+    const double acck = acc_s[k][lane];
+    double part = 0.0, gkk = 0.0, colsum = 0.0;
+#pragma unroll
+    for (int c = 0; c < KP; ++c) {
+      if (c >= 8 * ta) {                       // (tiles below ta were not loaded)
+        if (c == k) gkk = g[c];
+        else if (c > k && c < K) part = fma(g[c], u_s[c][lane], part);
+        if (c == K) colsum = g[c];
+      }
+    }
+    const double s = rxk - (acck + part);
+    const double b = vb ? gkk + svk : gkk;
+    const size_t idx = (size_t)row * K + k;
+    const double lam = a.lambda[idx];
+    const double tau_k = tau * b;
+    const double mu_k = (1.0 / tau_k) * (-lam + tau * s);
+    double unew = u_s[k][lane], vv = vb ? a.var[idx] : 0.0;
+    if (a.apply) {
+      double val = 0.0;
+      vv = 0.0;
+      if (a.mode == MODE_GIBBS) {
+        Philox rng(a.seed, it * 16ull + a.salt, (unsigned long long)(a.row_offset + row) * K + k);
+        val = tn_draw(mu_k, tau_k, rng);
+      } else if (vb) {
+        tn_moments(mu_k, tau_k, val, vv);
+      } else {
+        val = (mu_k != mu_k) ? mu_k : fmax(mu_k, 0.0);   // numpy.maximum propagates NaN (nmf_icm.py:129)
+        val = (val != val) ? val : fmax(val, a.min_tn);
+      }
+      unew = val;
+      u_s[k][lane] = val;
+      a.fac[idx] = val;
+      if (vb) a.var[idx] = vv;
+    }
+    if (a.mu) a.mu[idx] = mu_k;
+    if (a.tauf) a.tauf[idx] = tau_k;
+    if (a.sterm) a.sterm[idx] = s;
+#pragma unroll
+    for (int c = 0; c < KP; ++c)
+      if (c > k && c < K && c >= 8 * ta) acc_s[c][lane] = fma(g[c], unew, acc_s[c][lane]);
+    rp = fma(unew, rxk, rp);
+    sp = fma(unew, colsum, sp);
+    pp = fma(unew, fma(gkk, unew, 2.0 * acck), pp);
+    ex += vv * (gkk + svk) + unew * unew * svk;
+  }
+  if (a.mstat) *reinterpret_cast<double4*>(a.mstat + (size_t)row * 4) = make_double4(rp, pp, sp, 0.0);
+  if (a.extra) a.extra[row] = ex;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -554,8 +671,25 @@ int launch_pad_factor(const double* X, const double* Var, int n, int K, int n_al
   return check_launch("pad_factor");
 }
 
+// Default: thread-per-row whenever the columns are updated in their natural order -- at every size, so that a sharded
+// run uses the same kernel (and draws bit-identical Gibbs chains) as the unsharded one; both kernels are bound by the
+// same serial chain when the rows fit one wave.  White-box single-column calls and explicit orders use the
+// warp-per-row kernel.  BNMTF_SOLVE=warp forces it everywhere (tests compare the two).
 int launch_row_solve(const RowSolveArgs& a, cudaStream_t st) {
   const int nt = tiles_for(a.K);
+  const char* pref = getenv("BNMTF_SOLVE");
+  const bool natural = a.order == nullptr && a.n_order == a.K;
+  const bool lane = natural && !(pref && pref[0] == 'w');
+  if (lane) {
+    const int grid = (a.rows + 31) / 32;
+    switch (nt) {
+#define BNMTF_RL(N) case N: k_bnmf_row_solve_lane<N><<<grid, 32, 0, st>>>(a); break;
+      BNMTF_RL(1) BNMTF_RL(2) BNMTF_RL(3) BNMTF_RL(4) BNMTF_RL(5) BNMTF_RL(6) BNMTF_RL(7) BNMTF_RL(8)
+#undef BNMTF_RL
+      default: set_error("row_solve: K=%d out of range", a.K); return -2;
+    }
+    return check_launch("row_solve_lane");
+  }
   const int KP = 8 * nt;
   const size_t per_warp = (size_t)KP * (KP + 1) * sizeof(double);
   int warps = (int)(40 * 1024 / per_warp);

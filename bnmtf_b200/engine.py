@@ -537,16 +537,20 @@ class BNMFEngine:
             key = (self.trace.data_ptr() if self.trace is not None else 0, self.trace_base, self.trace_cap, float(minimum_TN))
             if self._graph is not None and self._graph_key == key:
                 self._graph.replay()
+                _lib.launch_count[0] += self._graph_kernels       # a replay launches every kernel node of the capture
                 self.sweeps_done += 1
                 return
             if self._graph_seen == key:
                 g = torch.cuda.CUDAGraph()
-                done = self.sweeps_done
+                done, count0 = self.sweeps_done, _lib.launch_count[0]
                 with torch.cuda.graph(g):
                     self._sweep_eager(minimum_TN)          # captured, not executed
+                self._graph_kernels = _lib.launch_count[0] - count0
+                _lib.launch_count[0] = count0
                 self.sweeps_done = done
                 self._graph, self._graph_key = g, key
                 g.replay()
+                _lib.launch_count[0] += self._graph_kernels
                 self.sweeps_done += 1
                 return
             self._graph_seen = key

@@ -175,3 +175,52 @@ def test_tn_moments_in_the_tail_follow_scipys_erfc():
     # beyond the switch: the exponential limit, exactly
     mu, tau = np.array([-31.0, -2000.0, -40.0]), np.array([1.0, 1.0, 4.0])
     np.testing.assert_allclose(D.TN_vector_variance(mu, tau), (1.0 / (np.abs(mu) * tau)) ** 2, rtol=1e-15)
+
+
+# ---- the thread-per-row solver (k_bnmf_row_solve_lane, the default for run()) vs the warp-per-row one ---------------
+@pytest.mark.parametrize("name", ["toy_bnmf_vb", "gdsc_bnmf_vb"])
+def test_warp_solver_vb_trajectory_matches_reference(models, golden, name, monkeypatch):
+    """The same golden VB trajectories with the warp-per-row solver forced (BNMTF_SOLVE=warp), 1e-9 as above."""
+    monkeypatch.setenv("BNMTF_SOLVE", "warp")
+    g = golden(name)
+    m = vb_from_golden(models, g)
+    m.run(int(g["its"]))
+    close(m.all_performances["MSE"], g["trace_MSE"], what="MSE trace")
+    close(m.all_exp_tau, g["trace_exptau"], what="exptau trace")
+    ok = np.isfinite(g["trace_elbo"])
+    close(np.asarray(m.all_elbo)[ok], g["trace_elbo"][ok], what="ELBO trace")
+    for k in ("expU", "varU", "muU", "tauU", "expV", "varV", "muV", "tauV"):
+        close(getattr(m, k), g["final_" + k], what=k)
+
+
+def test_warp_solver_icm_trajectory_matches_reference(models, golden, monkeypatch):
+    monkeypatch.setenv("BNMTF_SOLVE", "warp")
+    g = golden("toy_nmf_icm")
+    m = models.nmf_icm(g["R"], g["M"], int(g["K"]), priors2(g))
+    m.initialise("exp")
+    m.U, m.V = g["init_U"].copy(), g["init_V"].copy()
+    m.tau = (m.alpha_s() - 1.0) / m.beta_s()
+    m.run(int(g["its"]), minimum_TN=float(g["minimum_TN"]))
+    close(m.all_performances["MSE"], g["trace_MSE"]), close(m.all_tau, g["trace_tau"])
+    close(m.U, g["final_U"]), close(m.V, g["final_V"])
+
+
+@pytest.mark.parametrize("shape,K", [((300, 170), 7), ((2500, 96), 20), ((130, 2300), 33)])
+def test_lane_and_warp_solvers_draw_the_same_gibbs_chain(models, shape, K, monkeypatch):
+    """Same Philox counters, same statistics: the two solvers differ only in the summation order of the K-term dot
+    products, so a short Gibbs chain agrees to ~1e-10 (a draw that lands on a branch boundary of the sampler would
+    show up as an O(1) difference)."""
+    rng = np.random.RandomState(5)
+    I, J = shape
+    R = rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (J, K)).T + rng.normal(size=(I, J))
+    M = (rng.rand(I, J) >= 0.25).astype(float)
+    pri = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
+    out = {}
+    for solver in ("warp", "lane"):
+        monkeypatch.setenv("BNMTF_SOLVE", solver)
+        m = models.bnmf_gibbs_optimised(R, M, K, pri, seed=3)
+        m.initialise("exp")
+        m.run(4)
+        out[solver] = (m.U.copy(), m.V.copy(), m.tau, list(m.all_performances["MSE"]))
+    for a, b in zip(out["lane"], out["warp"]):
+        close(a, b, rtol=1e-8)
