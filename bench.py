@@ -22,6 +22,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HBM_FALLBACK_GBS = 6650.0
+# ncu dram bytes (read + write) per matrix entry of one k_rx_umma launch, by digit count (profiles/r01_ncu_summary_*.txt)
+RX_TRAFFIC_PER_ENTRY = {7: 15.15e9 / 2.0 ** 31}
+GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9}
 FP64_PEAK_TFLOPS = 37.1   # measured here: tools/microbench/fp64_pipes.cu -> profiles/r01_microbench_fp64_pipes.txt
 
 
@@ -112,18 +115,21 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
            "sweep_hbm": {"algorithmic_bytes_per_sweep": b_alg_sweep, "achieved_gbs": b_alg_sweep / sweep_s / 1e9,
                          "peak_gbs": hbm_peak * world, "peak_kind": hbm_kind,
                          "frac": b_alg_sweep / sweep_s / 1e9 / (hbm_peak * world)}}
+    from bnmtf_b200 import _lib
+    digits = _lib.call("bnmtf_fixed_point_digits")       # bytes per fixed-point image (6 by default)
+    out["fixed_point_digits"] = digits
     if e0.gram == "umma":
-        # exact fixed-point Gram: 0/1 selection matrix (rows x cols) times seven int8 digit slices of K(K+1)/2 (+K
+        # exact fixed-point Gram: 0/1 selection matrix (rows x cols) times the int8 digit slices of K(K+1)/2 (+K
         # variance, VB) (+K column-sum, metrics phase) product columns; algorithmic ops = 2 * rows * cols * digit columns
         ops, ach = {}, {}
         for k, e in engs.items():
             nc = K * (K + 1) // 2 + (K if e.vb else 0)
-            ops[k] = 2.0 * N * (nc + 0.5 * (K if e.metrics_mode == "stats" else 0)) * 7
+            ops[k] = 2.0 * N * (nc + 0.5 * (K if e.metrics_mode == "stats" else 0)) * digits
             ach[k] = ops[k] / (prof[k]["stats_gram"] * 1e-3) / 1e12
         mean_ach = sum(ach.values()) / len(ach)
         peak = 2.0 * bf16
         out.update({"bound": "tensor", "kernel": "k_gram_umma (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed)",
-                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": 1.6e9,
+                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": GRAM_TRAFFIC_PER_LAUNCH.get(digits),
                     "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is twice "
                                    "the bf16 rate; ops are int8 multiply-adds x 2" % bf16_kind,
                     "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary_final.txt",
@@ -137,15 +143,16 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
         out.update({"bound": "tensor", "kernel": "k_stats_gram (fp64 DMMA, mma.sync.m8n8k4.f64)", "achieved": mean_ach,
                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": mean_ach / FP64_PEAK_TFLOPS, "traffic": None,
                     "peak_source": "fp64 DMMA peak measured by tools/microbench/fp64_pipes.cu"})
-    # the HBM-bound kernel: streams R once per phase (7 digit-plane bytes per entry for the tcgen05 kernel,
+    # the HBM-bound kernel: streams R once per phase (`digits` digit-plane bytes per entry for the tcgen05 kernel,
     # 8 + 1/8 bytes for the fp64 kernel)
-    bpe = 7.0 if e0.rx == "umma" else 8.125
+    bpe = float(digits) if e0.rx == "umma" else 8.125
     rx_ms = sum(prof[k]["stats_rx"] for k in engs) / len(engs)
     rx_gbs = N * bpe / (rx_ms * 1e-3) / 1e9
     out["hbm_kernel"] = {"bound": "hbm", "kernel": "k_rx_umma (tcgen05 digit planes)" if e0.rx == "umma" else "k_stats_rx (fp64 DMMA)",
                          "achieved": rx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rx_gbs / hbm_peak,
                          "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)",
-                         "traffic": 15.15e9 * (N / 2.0 ** 31) if e0.rx == "umma" else None}
+                         "traffic": RX_TRAFFIC_PER_ENTRY.get(digits, 0) * N if (e0.rx == "umma" and digits in RX_TRAFFIC_PER_ENTRY) else None,
+                         "traffic_source": "ncu dram__bytes_read+write per launch / entries, profiles/ (see DESIGN.md section 5)"}
     return out
 
 

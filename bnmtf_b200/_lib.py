@@ -20,6 +20,7 @@ SIGNATURES = {
     "bnmtf_transpose_dataset_f64": [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_p],
     "bnmtf_pad_factor_f64": [c_p, c_p, c_i64, c_i, c_i64, c_p, c_p, c_p],
     "bnmtf_stats_rx_f64": [c_p, c_p, c_i64, c_i64, c_p, c_i, c_i, c_p, c_p],
+    "bnmtf_fixed_point_digits": [],
     "bnmtf_rx_planes_bytes": [c_i64, c_i64],
     "bnmtf_rx_planes_pack_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     "bnmtf_rx_umma_workspace_bytes": [c_i, c_i64],
@@ -57,7 +58,7 @@ SIGNATURES = {
 _RESTYPES = {"bnmtf_last_error": ctypes.c_char_p, "bnmtf_ld_for": c_i64, "bnmtf_gram_len": c_i64,
              "bnmtf_gram_umma_workspace_bytes": c_i64, "bnmtf_rx_planes_bytes": c_i64,
              "bnmtf_rx_umma_workspace_bytes": c_i64}
-_PLAIN = {"bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "bnmtf_gram_len",
+_PLAIN = {"bnmtf_fixed_point_digits", "bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "bnmtf_gram_len",
           "bnmtf_gram_umma_workspace_bytes", "bnmtf_rx_planes_bytes", "bnmtf_rx_umma_workspace_bytes"}
 
 _lib = None

@@ -163,6 +163,8 @@ int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int6
   return launch_stats_rx(R, bits, (int)rows, (int)ld, Xp, K, nseg, RXpart, nullptr, ST(stream));
 }
 
+int bnmtf_fixed_point_digits(void) { return kDigits; }
+
 int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld) {
   if (rows <= 0 || ld <= 0 || ld % 64) return -1;
   return rxu_planes_bytes(rows, ld);

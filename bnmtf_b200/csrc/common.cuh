@@ -14,6 +14,18 @@ namespace bnmtf {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Bytes ("digits") of the fixed-point images the tcgen05 statistics kernels sum exactly (gram_umma.cu, rx_umma.cu).
+// 6 digits = 48 bits below a per-row / per-column power-of-two scale: each term is rounded to 2^-49 of that scale
+// and the SUM is then exact, so the relative error of a sum of n terms is ~2^-49 (max/mean) / sqrt(3n) -- 4e-15 for
+// a single-term sum, 1e-15 at the toy shapes, 1e-16 at 65536 x 32768 -- below what an fp64 summation of the same
+// terms accumulates (the fp64 mma.sync kernel measures 1.4e-14 there).  7 digits (56 bits, build with
+// -DBNMTF_DIGITS=7) cost 1/6 more HBM traffic and tensor work for digits no fp64 consumer can see.
+#ifndef BNMTF_DIGITS
+#define BNMTF_DIGITS 6
+#endif
+constexpr int kDigits = BNMTF_DIGITS;
+static_assert(kDigits == 6 || kDigits == 7, "BNMTF_DIGITS must be 6 or 7");
+
 constexpr int kMaxTiles = 8;            // KP = 8*NT <= 64  ->  K <= 63 latent factors
 constexpr double kInvSqrt2 = 0.70710678118654752440;
 constexpr double kInvSqrt2Pi = 0.39894228040143267794;

@@ -3,17 +3,17 @@
 //   G_i[a][b] = sum_{j in S(i)} X_ja X_jb   (a <= b),      SV_i[k] = sum_{j in S(i)} Var_jk     (VB)
 //
 // is  W (rows x cols, 0/1: the selected set of each row)  times  P (cols x NC),  P_jc = X_ja X_jb | Var_jk.
-// W is exact in any format; P is turned into 56-bit fixed point per column (scale = power of two above the
-// column's largest magnitude) and cut into seven unsigned bytes, so that
+// W is exact in any format; P is turned into fixed point per column (T+1 = 8 * kDigits bits: 48 by default, 56 with
+// -DBNMTF_DIGITS=7; scale = power of two above the column's largest magnitude) and cut into unsigned bytes, so that
 //
-//   sum_j W_ij P_jc  =  2^(e_c-55) * ( sum_s 256^s * sum_j W_ij d_s(j,c)  -  2^55 * |S(i)| )
+//   sum_j W_ij P_jc  =  2^(e_c-T) * ( sum_s 256^s * sum_j W_ij d_s(j,c)  -  2^T * |S(i)| )
 //
 // where every inner sum is an int32 accumulated by tcgen05.mma.kind::i8 (u8 x u8 -> s32) in tensor memory: no
 // rounding anywhere until the final conversion to double (one rounding of the exact fixed-point total), i.e. the
 // result is the correctly rounded sum of the quantised products -- at least as accurate as an fp64 accumulation
-// and independent of the order of summation.  (The 2^55 offset makes signed P representable with unsigned digits.)
+// and independent of the order of summation.  (The 2^T offset makes signed P representable with unsigned digits.)
 //
-// Kernel k_gram_umma: one CTA = 128 rows x one chunk of <= 73 P-columns (<= 511 digit columns = the whole tensor
+// Kernel k_gram_umma: one CTA = 128 rows x one chunk of <= 512 / kDigits P-columns (<= 512 digit columns = the whole tensor
 // memory of an SM as two accumulators of n_half columns) x one segment of the column range.
 //   warps 0-3  expand the mask bits of their 128 rows into the K-major, 64/128-byte-swizzled A tile (generic
 //              proxy stores + fence.proxy.async), count |S(i)|, and run the epilogue (tcgen05.ld -> fixed point
@@ -29,7 +29,8 @@
 
 namespace bnmtf {
 
-constexpr int UG_SLICES = 7;
+constexpr int UG_SLICES = kDigits;          // bytes per product column (common.cuh)
+constexpr int UG_TOP = 8 * UG_SLICES - 1;    // products are stored as llrint(P 2^(TOP-e)) + 2^TOP, 2^e > max|P|
 constexpr int UG_ROWS = 128;     // rows per CTA = UMMA M
 constexpr int UG_EXP_WARPS = 8;   // mask-expander / epilogue warps (two threads per row)
 constexpr int UG_THREADS = (UG_EXP_WARPS + 2) * 32;
@@ -49,7 +50,7 @@ __host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums, int 
   p.K = K; p.vb = vb; p.sums = sums;
   p.ng = K * (K + 1) / 2;
   p.nc = p.ng + (vb ? K : 0) + (sums ? K : 0);
-  const int cmax = 512 / UG_SLICES;                   // 73
+  const int cmax = 512 / UG_SLICES;                   // 85 (73 with seven digits)
   p.nch = (p.nc + cmax - 1) / cmax;
   p.cpc = (p.nc + p.nch - 1) / p.nch;
   const int nd = p.cpc * UG_SLICES;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) k_ug_colmax(const double* __restrict__ Xp
   }
 }
 
-// scale of column c: P is stored as llrint(P * 2^(55-e)) with 2^e > max|P|;  cscale = 2^(e-55) (NaN if not finite)
+// scale of column c: P is stored as llrint(P * 2^(T-e)) with 2^e > max|P|;  cscale = 2^(e-T) (NaN if not finite)
 __global__ void k_ug_scales(const unsigned long long* __restrict__ colmax, int nc, double* __restrict__ cscale,
                             int* __restrict__ cexp) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,14 +115,14 @@ __global__ void k_ug_scales(const unsigned long long* __restrict__ colmax, int n
   if (!isfinite(m)) { s = __longlong_as_double(0x7ff8000000000000ll); }
   else {
     if (m > 0.0) { frexp(m, &e); }       // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
-    s = scalbn(1.0, e - 55);
+    s = scalbn(1.0, e - UG_TOP);
   }
   cscale[c] = s;
   cexp[c] = e;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// pre-pass 2: the digit matrix  Bd[ch*nb + cl*7 + s][j] = byte s of ( llrint(P_jc 2^(55-e_c)) + 2^55 ),  0 for j >= n
+// pre-pass 2: the digit matrix  Bd[ch*nb + cl*kDigits + s][j] = byte s of ( llrint(P_jc 2^(T-e_c)) + 2^T ),  0 for j >= n
 // CTA = 128 threads = 32 column groups of 4 consecutive j  x  4 interleaved P-column subsets.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_ug_quantize(const double* __restrict__ Xp, const double* __restrict__ Vp, int n,
@@ -149,12 +150,14 @@ __global__ void __launch_bounds__(128) k_ug_quantize(const double* __restrict__ 
       umma_col_pair(c, pl, a, b);
       const double* xa = xs + (b == -1 ? (K + a) : a) * XS + jg;
       const double* xb = b < 0 ? nullptr : xs + b * XS + jg;
-      const int sh = 55 - cexp[c];
+      const int sh = UG_TOP - cexp[c];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (j0 + jg + i < n) {
           const double p = xb ? xa[i] * xb[i] : xa[i];
-          const long long q = llrint(scalbn(p, sh)) + (1ll << 55);
+          long long q = llrint(scalbn(p, sh));
+          q = q > (1ll << UG_TOP) - 1 ? (1ll << UG_TOP) - 1 : (q < -(1ll << UG_TOP) ? -(1ll << UG_TOP) : q);   // rounding at the scale's edge
+          q += 1ll << UG_TOP;
 #pragma unroll
           for (int s = 0; s < UG_SLICES; ++s) w[s] |= (uint32_t)((q >> (8 * s)) & 0xff) << (8 * i);
         }
@@ -310,8 +313,12 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       const uint32_t pr = pair_tab[cl];
       const int pa = pr >> 8, pb = pr & 0xff;
       if (!live || pb == 0xfe) continue;
+      // the top digit carries the +2^TOP offset of every summed term: 128 * 256^(SLICES-1) * cnt
       const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
-      const long long hi = (long long)d[4] + ((long long)d[5] << 8) + (((long long)(int)d[6] - 128ll * cnt) << 16);
+      long long hi = 0;
+#pragma unroll
+      for (int s = 4; s < UG_SLICES; ++s)
+        hi += ((long long)(int)d[s] - (s == UG_SLICES - 1 ? 128ll * cnt : 0ll)) << (8 * (s - 4));
       const double v = fma((double)hi, 4294967296.0, (double)lo) * a.cscale[ch * pl.cpc + cl];
       if (pb == 0xff) {
         if (srow) srow[pa] = v;

@@ -2,7 +2,9 @@
 // integer GEMM on tcgen05 (the fp64 DMMA kernel k_stats_rx is bound by the fp64 pipe at ~3.7 ms per phase of the
 // 65536 x 32768 problem; this one is bound by streaming the data: 7 bytes per entry instead of 8).
 //
-// Both operands are 56-bit fixed point cut into bytes ("digits"):
+// Both operands are fixed point cut into bytes ("digits"); the text below describes the 7-digit (56-bit) build
+// (-DBNMTF_DIGITS=7), the default is 6 digits = 48 bits (common.cuh: kDigits): six planes, pairs with s+t < 4 dropped,
+// seven accumulators, 6 bytes per entry streamed.
 //   R (static): per row i, q_ij = llrint(R_ij 2^(55-e_i)) with 2^e_i > max_j |R_ij| over the observed entries, stored
 //       once per dataset as seven digit PLANES (two's complement: planes 0..5 unsigned, plane 6 signed), zero at
 //       missing entries -- the mask is folded into the data.  Layout: [row block of 128][column tile of 64][plane]
@@ -26,10 +28,13 @@
 
 namespace bnmtf {
 
-constexpr int RXU_PLANES = 7;
-constexpr int RXU_VDIG = 7;
-constexpr int RXU_UMIN = 5;                       // keep digit pairs with s + t >= UMIN
-constexpr int RXU_NU = RXU_PLANES + RXU_VDIG - 1 - RXU_UMIN;   // 8 accumulators (u = 5..12)
+constexpr int RXU_PLANES = kDigits;               // digit planes of R (7: the figures quoted above; 6: 48-bit images)
+constexpr int RXU_VDIG = kDigits;                 // digits of the factor
+constexpr int RXU_UMIN = kDigits - 2;             // keep digit pairs with s + t >= UMIN (the dropped ones: < 2^-51 of the scale)
+constexpr int RXU_NU = RXU_PLANES + RXU_VDIG - 1 - RXU_UMIN;   // 8 accumulators (u = 5..12) / 7 (u = 4..10)
+constexpr int RXU_RBITS = 8 * RXU_PLANES - 1;     // R: signed, |q| < 2^RBITS
+constexpr int RXU_XBITS = 8 * RXU_VDIG;           // X: unsigned, q < 2^XBITS
+static_assert(2 * RXU_NU * 32 <= 512, "two accumulator sets must fit tensor memory");
 constexpr int RXU_KT = 64;                        // bytes (= columns) per pipeline stage
 constexpr int RXU_DRAIN = 64;                     // stages per accumulator period: 4096 columns
 constexpr int RXU_PLANE_TILE = 128 * RXU_KT;      // 8 KB
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(256) k_rxu_rowscale(const double* __restrict__
     int e = 0;
     if (m > 0.0) frexp(m, &e);
     rexp[row] = e;
-    rscale[row] = bad ? __longlong_as_double(0x7ff8000000000000ll) : scalbn(1.0, e - 55);
+    rscale[row] = bad ? __longlong_as_double(0x7ff8000000000000ll) : scalbn(1.0, e - RXU_RBITS);
   }
 }
 
@@ -86,13 +91,15 @@ __global__ void __launch_bounds__(256) k_rxu_pack(const double* __restrict__ R, 
     const uint32_t word = bits[(size_t)row * (ld >> 5) + (j0 >> 5)];
     const uint32_t m16 = (word >> (j0 & 31)) & 0xffffu;
     if (m16) {
-      const int sh = 55 - rexp[row];
+      const int sh = RXU_RBITS - rexp[row];
       const double* rr = R + (size_t)row * ld + j0;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if ((m16 >> i) & 1u) {
           const double v = rr[i];
-          const long long q = isfinite(v) ? llrint(scalbn(v, sh)) : 0ll;
+          // |v| < 2^e, but with fewer than 53 bits below the scale the rounding can reach +-2^RBITS: clamp (1 unit)
+          long long q = isfinite(v) ? llrint(scalbn(v, sh)) : 0ll;
+          q = q > (1ll << RXU_RBITS) - 1 ? (1ll << RXU_RBITS) - 1 : (q < -(1ll << RXU_RBITS) + 1 ? -(1ll << RXU_RBITS) + 1 : q);
 #pragma unroll
           for (int s = 0; s < RXU_PLANES; ++s) dig[s][i >> 2] |= (uint32_t)((q >> (8 * s)) & 0xff) << (8 * (i & 3));
         }
@@ -135,7 +142,7 @@ __global__ void k_rxu_colscale(const unsigned long long* __restrict__ colmax, in
   int e = 0;
   if (isfinite(m) && m > 0.0) frexp(m, &e);
   cexp[k] = e;
-  cscale[k] = scalbn(1.0, e - 56);
+  cscale[k] = scalbn(1.0, e - RXU_XBITS);
 }
 
 // Bd[t*KPAD + k][j] = byte t of llrint(X_jk 2^(56-e_k)); zero for j >= n and for k >= K.  thread <-> (k, 4 columns)
@@ -152,11 +159,12 @@ __global__ void __launch_bounds__(256) k_rxu_quantize(const double* __restrict__
 #pragma unroll
   for (int t = 0; t < RXU_VDIG; ++t) w[t] = 0u;
   if (k < K) {
-    const int sh = 56 - cexp[k];
+    const int sh = RXU_XBITS - cexp[k];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (jg + i < n) {
-        const long long q = llrint(scalbn(Xp[(size_t)(jg + i) * KP + k], sh));
+        long long q = llrint(scalbn(Xp[(size_t)(jg + i) * KP + k], sh));
+        q = q > (1ll << RXU_XBITS) - 1 ? (1ll << RXU_XBITS) - 1 : q;     // rounding up to 2^XBITS would lose the top digit
 #pragma unroll
         for (int t = 0; t < RXU_VDIG; ++t) w[t] |= (uint32_t)((q >> (8 * t)) & 0xff) << (8 * i);
       }
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
         mbar_arrive(ACC_EMPTY(b));
       }
       if (row < a.rows) {
-        const double rs = a.rscale[row] * 1099511627776.0;        // 2^40 = 256^UMIN
+        const double rs = scalbn(a.rscale[row], 8 * RXU_UMIN);        // the lowest kept weight is 256^UMIN
         double* o = a.out + ((size_t)seg * a.rows + row) * a.KP;
 #pragma unroll
         for (int k = 0; k < KPAD; ++k)

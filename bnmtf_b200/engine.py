@@ -281,7 +281,7 @@ class BNMFEngine:
                 # CTAs = row blocks x column chunks x segments; aim for ~10 waves of one CTA per SM
                 tile = 128 if ld >= 256 else 64
                 sums = K if (side == 1 and self.metrics_mode == "stats") else 0
-                nch = -(-(K * (K + 1) // 2 + (K if self.vb else 0) + sums) // 73)
+                nch = -(-(K * (K + 1) // 2 + (K if self.vb else 0) + sums) // (512 // _lib.call("bnmtf_fixed_point_digits")))
                 ktiles = -(-ld // tile)
                 ng = _pick_nseg(((rb + 1) // 2 * 2 if self.umma_pair else rb) * nch, ktiles,
                                 t_tile=0.55 * tile / 128, t_fix=10.0)

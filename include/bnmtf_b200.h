@@ -84,6 +84,9 @@ int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int6
  * SM looping over 128-row x segment work items); max_ctas > 0 caps the number of CTAs, leaving the other SMs to a
  * kernel running concurrently on another stream (0: all SMs).
  * workspace: >= bnmtf_rx_umma_workspace_bytes(K, ld) bytes, 1024-byte aligned. */
+/* Bytes per fixed-point image in the tcgen05 statistics kernels (6 = 48 bits by default; 7 when the library was built
+ * with -DBNMTF_DIGITS=7): digit planes per entry of R, digits per factor entry and per Gram product. */
+int bnmtf_fixed_point_digits(void);
 int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld);
 int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
                              double* rscale, int32_t* rexp_scratch, void* stream);
