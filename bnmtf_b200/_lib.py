@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbnmtf_b200.so")
+# BNMTF_LIB: another build of the same library (A/B runs of build options such as -DBNMTF_DIGITS=7, tools/gpu_margins.py)
+LIB_PATH = os.environ.get("BNMTF_LIB") or os.path.join(_HERE, "libbnmtf_b200.so")
 
 c_i, c_i64, c_u64, c_d, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
 

@@ -15,11 +15,13 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
 // Bytes ("digits") of the fixed-point images the tcgen05 statistics kernels sum exactly (gram_umma.cu, rx_umma.cu).
-// 6 digits = 48 bits below a per-row / per-column power-of-two scale: each term is rounded to 2^-49 of that scale
-// and the SUM is then exact, so the relative error of a sum of n terms is ~2^-49 (max/mean) / sqrt(3n) -- 4e-15 for
-// a single-term sum, 1e-15 at the toy shapes, 1e-16 at 65536 x 32768 -- below what an fp64 summation of the same
-// terms accumulates (the fp64 mma.sync kernel measures 1.4e-14 there).  7 digits (56 bits, build with
-// -DBNMTF_DIGITS=7) cost 1/6 more HBM traffic and tensor work for digits no fp64 consumer can see.
+// 6 digits = 48 bits below a per-row / per-column power-of-two scale 2^e: each term is rounded to a multiple of
+// 2^(e-47) (error uniform within half of that) and the SUM is then exact, so a sum of n terms of mean magnitude m
+// has a relative error of about 2^-47 (2^e / m) / sqrt(12 n): measured 2e-14 (max) on Gram entries with ~1600 terms
+// and 2^e / m ~ 100, ~1e-14 at 65536 x 32768 -- the level of this library's fp64 mma.sync kernel (1.4e-14 there),
+// 30-100 x the error of a BLAS fp64 matmul, five orders of magnitude inside the 1e-9 parity tolerance; the golden
+// trajectories cannot tell the two builds apart (tools/gpu_margins.py: 9.9e-11 vs 1.3e-10 on the toy VB factors).
+// 7 digits (56 bits, build with -DBNMTF_DIGITS=7: errors 256 x smaller) cost 1/6 more HBM traffic and tensor work.
 #ifndef BNMTF_DIGITS
 #define BNMTF_DIGITS 6
 #endif

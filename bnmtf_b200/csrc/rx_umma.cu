@@ -3,8 +3,8 @@
 // 65536 x 32768 problem; this one is bound by streaming the data: 7 bytes per entry instead of 8).
 //
 // Both operands are fixed point cut into bytes ("digits"); the text below describes the 7-digit (56-bit) build
-// (-DBNMTF_DIGITS=7), the default is 6 digits = 48 bits (common.cuh: kDigits): six planes, pairs with s+t < 4 dropped,
-// seven accumulators, 6 bytes per entry streamed.
+// (-DBNMTF_DIGITS=7), the default is 6 digits = 48 bits (common.cuh: kDigits): six planes, pairs with s+t < 3 dropped,
+// eight accumulators, 6 bytes per entry streamed.
 //   R (static): per row i, q_ij = llrint(R_ij 2^(55-e_i)) with 2^e_i > max_j |R_ij| over the observed entries, stored
 //       once per dataset as seven digit PLANES (two's complement: planes 0..5 unsigned, plane 6 signed), zero at
 //       missing entries -- the mask is folded into the data.  Layout: [row block of 128][column tile of 64][plane]
@@ -30,8 +30,11 @@ namespace bnmtf {
 
 constexpr int RXU_PLANES = kDigits;               // digit planes of R (7: the figures quoted above; 6: 48-bit images)
 constexpr int RXU_VDIG = kDigits;                 // digits of the factor
-constexpr int RXU_UMIN = kDigits - 2;             // keep digit pairs with s + t >= UMIN (the dropped ones: < 2^-51 of the scale)
-constexpr int RXU_NU = RXU_PLANES + RXU_VDIG - 1 - RXU_UMIN;   // 8 accumulators (u = 5..12) / 7 (u = 4..10)
+// keep digit pairs with s + t >= UMIN.  The dropped partial products are all non-negative (only the top plane is
+// signed), i.e. a one-sided error that grows with n, not sqrt(n): it has to stay far below the quantisation noise of
+// the operands (2^-48 of the scale per term with six digits), hence < 2^-60 of the product scale per term in both builds
+constexpr int RXU_UMIN = 2 * kDigits - 9;         // 7 digits: 5 (u = 5..12);  6 digits: 3 (u = 3..10)
+constexpr int RXU_NU = RXU_PLANES + RXU_VDIG - 1 - RXU_UMIN;   // 8 accumulators
 constexpr int RXU_RBITS = 8 * RXU_PLANES - 1;     // R: signed, |q| < 2^RBITS
 constexpr int RXU_XBITS = 8 * RXU_VDIG;           // X: unsigned, q < 2^XBITS
 static_assert(2 * RXU_NU * 32 <= 512, "two accumulator sets must fit tensor memory");

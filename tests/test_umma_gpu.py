@@ -175,6 +175,49 @@ def test_rx_umma_is_exact_on_integers():
     assert np.array_equal(got, (d["R"] * d["M"]) @ d["X"])
 
 
+def test_fixed_point_statistics_error_model():
+    """The accuracy statement of csrc/common.cuh (kDigits): every term is rounded to a multiple of 2^(e-T) (T = 47 with
+    six digits, 55 with seven; 2^e = the power of two above the column's / row's largest magnitude) and the sum is
+    then exact, so the error of a sum of n terms is a random walk of n roundings, sigma = 2^(e-T) sqrt(n / 12).
+    Checked against an extended-precision (numpy longdouble) evaluation at a shape with ~1600 terms per Gram sum and
+    ~6500 per R.X sum: every entry within 6 sigma of the exact value, and some entry beyond sigma / 20 when T = 47
+    (i.e. the model is not vacuous: the digits really are the only error)."""
+    from bnmtf_b200 import _lib
+    T = 8 * _lib.call("bnmtf_fixed_point_digits") - 1
+    rows, cols, K = 64, 8192, 20
+    d = _setup(rows, cols, K, seed=77)
+    ld_ = np.longdouble
+    W = 1.0 - d["M"]
+    X = d["X"]
+    G, _ = _gram_umma(d, rows, cols, K, 0, 0, 1, 128, 0, pair=1)
+    worst = 0.0
+    for a, b in ((0, 0), (0, 1), (3, 17), (19, 19), (7, 12)):
+        p = X[:, a] * X[:, b]
+        exact = W.astype(ld_) @ p.astype(ld_)
+        got = G[:, _tile_index(a, b, d["KP"])].astype(ld_)
+        quantum = 2.0 ** (np.frexp(p.max())[1] - T)
+        sigma = quantum * np.sqrt(W.sum(1) / 12.0) + 1.2e-16 * np.abs(exact).astype(float)     # + the final rounding to double
+        z = np.abs(got - exact).astype(float) / sigma
+        assert z.max() < 6.0, (a, b, z.max())
+        worst = max(worst, float(z.max()))
+        assert float(np.max(np.abs(got - exact) / exact)) < (1e-13 if T == 47 else 1e-15)
+    if T == 47:
+        assert worst > 0.05
+    got, _ = _rx_both(d, rows, cols, K, 1)
+    RM = d["R"] * d["M"]
+    exact = RM.astype(ld_) @ X.astype(ld_)
+    # two quantised operands: q_R q_X, errors 2^(eR-T) |X| / sqrt(12) and 2^(eX-T-1) |R| / sqrt(12) per term, plus the
+    # dropped low digit pairs (< 2^(eR+eX-60) per term, one-sided: negligible by design, rx_umma.cu RXU_UMIN)
+    eR = np.frexp(np.abs(RM).max(1))[1][:, None].astype(float)
+    eX = np.frexp(X.max(0))[1][None, :].astype(float)
+    var = (4.0 ** (eR - T)) * (d["M"] @ X ** 2) / 12.0 + (4.0 ** (eX - T - 1)) * (RM ** 2 @ np.ones_like(X)) / 12.0
+    bias = 2.0 ** (eR + eX - 60) * d["M"].sum(1)[:, None]
+    err = np.abs(got.astype(ld_) - exact).astype(float)
+    assert np.all(err < 6.0 * np.sqrt(var) + bias + 2.5e-16 * np.abs(exact).astype(float))
+    scale = np.abs(RM) @ np.abs(X)
+    assert float(np.max(err / scale)) < (1e-14 if T == 47 else 1e-15)
+
+
 @pytest.mark.parametrize("mode", ["vb", "icm"])
 def test_engine_paths_agree_over_a_trajectory(mode, monkeypatch):
     """tcgen05 statistics + statistics-based metrics vs fp64 mma.sync statistics + direct metrics: same trajectory."""
