@@ -104,12 +104,15 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
     N = float(I) * J / world
     n_obs = n_obs / world
     e0 = next(iter(engs.values()))
+    # the Gram kernel is timed inside a long, power-capped run: the sustained cuBLAS figure is its denominator
+    # (B200_PROFILING.md); the burst figure is reported beside it
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            bf16 = float(json.load(fh)["bf16_tflops"])
-        bf16_kind = "measured"
+            pk = json.load(fh)
+        bf16, bf16_burst = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])), float(pk["bf16_tflops"])
+        bf16_kind = "measured, sustained"
     except Exception:
-        bf16, bf16_kind = 1590.0, "fallback"
+        bf16, bf16_burst, bf16_kind = 1400.0, 1590.0, "fallback, sustained"
     b_alg_sweep = 2.0 * N * world * 8.125
     out = {"kernel_ms": prof,
            "sweep_hbm": {"algorithmic_bytes_per_sweep": b_alg_sweep, "achieved_gbs": b_alg_sweep / sweep_s / 1e9,
@@ -130,8 +133,10 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
         peak = 2.0 * bf16
         out.update({"bound": "tensor", "kernel": "k_gram_umma (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed)",
                     "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": GRAM_TRAFFIC_PER_LAUNCH.get(digits),
-                    "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is twice "
-                                   "the bf16 rate; ops are int8 multiply-adds x 2" % bf16_kind,
+                    "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is "
+                                   "twice the bf16 rate; ops are int8 multiply-adds x 2; the kernel is timed inside the "
+                                   "power-capped sweep loop" % bf16_kind,
+                    "frac_of_burst_peak": mean_ach / (2.0 * bf16_burst),
                     "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary_final.txt",
                     "per_mode_achieved_tops": ach})
     else:
@@ -156,9 +161,11 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
     return out
 
 
-def cpu_baseline(K, seed=0, budget_s=20.0, sizes=((1024, 512), (2048, 1024))):
+def cpu_baseline(K, seed=0, budget_s=8.0, sizes=((1024, 512), (2048, 1024), (4096, 2048))):
     """Time the CPU oracle (numpy restatement of the reference's sweep, same per-column full-GEMM cost structure) on
-    bounded samples of the same synthetic workload and extrapolate linearly in I*J to the full shape."""
+    bounded samples of the same synthetic workload and extrapolate linearly in I*J to the full shape.  A size is
+    started while less than budget_s seconds have been used: the last one (4096 x 2048, ~10-20 s for the two sweeps
+    on 8-16 cores) brings the sample to the 10-30 s the bench contract asks for."""
     from oracle import bnmtf_oracle as orc
     try:
         import threadpoolctl
@@ -194,7 +201,7 @@ def cpu_baseline(K, seed=0, budget_s=20.0, sizes=((1024, 512), (2048, 1024))):
 def run_reference(args):
     I, J, K = args.rows, args.cols, args.K
     t0 = time.time()
-    per_elem, cores, desc, used = cpu_baseline(K, budget_s=25.0 * max(1, args.steps))
+    per_elem, cores, desc, used = cpu_baseline(K)
     biggest = max(n for (_, n) in per_elem)
     s_gibbs, s_vb = per_elem[("gibbs", biggest)] * I * J, per_elem[("vb", biggest)] * I * J
     value = 2.0 / (s_gibbs + s_vb)

@@ -205,8 +205,22 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) 
   const double* grow = a.Gpart + (size_t)row * (NTP * 64);
   double rp = 0.0, pp = 0.0, sp = 0.0, ex = 0.0;
 
+  // the per-row vectors this thread will read one element per column (RX, SV, lambda, var): pull their lines towards L2
+  // now; none of the loads below depends on the update chain, only their consumers do
+  {
+    const char* l0 = reinterpret_cast<const char*>(a.lambda + (size_t)row * K);
+    const char* r0 = reinterpret_cast<const char*>(a.RXpart + (size_t)row * KP);
+    for (int off = 0; off < K * 8; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l0 + off));
+    for (int off = 0; off < KP * 8; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + off));
+  }
   for (int k = 0; k < K; ++k) {
     const int ta = k >> 3, r = k & 7;
+    if (k + 1 < K) {                           // row k+1 of the Gram tiles: in L2 by the time the chain gets there
+      const int tn = (k + 1) >> 3, rn = (k + 1) & 7;
+      for (int sgm = 0; sgm < a.nseg_g; ++sgm)
+        for (int tb = tn; tb < NT; ++tb)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + sgm * gstride + tile_pair(tn, tb, NT) * 64 + rn * 8));
+    }
     // row k of the upper triangle: tiles (ta, tb >= ta), 8 contiguous doubles each
     double g[KP];
 #pragma unroll
