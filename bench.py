@@ -22,9 +22,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HBM_FALLBACK_GBS = 6650.0
-# ncu dram bytes (read + write) per matrix entry of one k_rx_umma launch, by digit count (profiles/r01_ncu_summary_*.txt)
-RX_TRAFFIC_PER_ENTRY = {7: 15.15e9 / 2.0 ** 31}
-GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9}
+# ncu dram bytes (read + write) per matrix entry of one k_rx_umma launch, by digit count (profiles/r01_ncu_summary_final.txt: 7, profiles/r01d_ncu_summary.txt: 6)
+RX_TRAFFIC_PER_ENTRY = {7: 15.15e9 / 2.0 ** 31, 6: 12.98e9 / 2.0 ** 31}
+GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9, 6: 1.29e9}       # mean of the two phases, at the full 65536 x 32768 shape on one GPU
 FP64_PEAK_TFLOPS = 37.1   # measured here: tools/microbench/fp64_pipes.cu -> profiles/r01_microbench_fp64_pipes.txt
 
 
@@ -132,12 +132,12 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
         mean_ach = sum(ach.values()) / len(ach)
         peak = 2.0 * bf16
         out.update({"bound": "tensor", "kernel": "k_gram_umma (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed)",
-                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": GRAM_TRAFFIC_PER_LAUNCH.get(digits),
+                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": (GRAM_TRAFFIC_PER_LAUNCH.get(digits) / world if GRAM_TRAFFIC_PER_LAUNCH.get(digits) else None),
                     "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is "
                                    "twice the bf16 rate; ops are int8 multiply-adds x 2; the kernel is timed inside the "
                                    "power-capped sweep loop" % bf16_kind,
                     "frac_of_burst_peak": mean_ach / (2.0 * bf16_burst),
-                    "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary_final.txt",
+                    "traffic_source": "ncu dram__bytes_read+write per launch at the full shape on one GPU, profiles/r01d_ncu_summary.txt",
                     "per_mode_achieved_tops": ach})
     else:
         miss = N - n_obs
@@ -157,7 +157,7 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
                          "achieved": rx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rx_gbs / hbm_peak,
                          "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)",
                          "traffic": RX_TRAFFIC_PER_ENTRY.get(digits, 0) * N if (e0.rx == "umma" and digits in RX_TRAFFIC_PER_ENTRY) else None,
-                         "traffic_source": "ncu dram__bytes_read+write per launch / entries, profiles/ (see DESIGN.md section 5)"}
+                         "traffic_source": "ncu dram__bytes_read+write per launch / entries, profiles/r01d_ncu_summary.txt"}
     return out
 
 
