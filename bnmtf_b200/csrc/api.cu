@@ -220,8 +220,10 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
                        const double* Gpart, const double* SVpart, const double* Gfull, double* fac, double* var,
                        double* mu, double* tauf, const double* lambda, const double* scalars, const int* order,
                        int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
-                       int64_t row_offset, double* sterm, double* extra, double* mstat, void* stream) {
+                       int64_t row_offset, double* sterm, double* extra, double* mstat, const uint64_t* peer_fac,
+                       const uint64_t* peer_var, int n_peers, int my_rank, void* stream) {
   if (check_k(K)) return -2;
+  if (peer_fac && (n_peers < 2 || my_rank < 0 || my_rank >= n_peers || !apply)) { set_error("row_solve: bad peer arguments"); return -2; }
   if (mode < 0 || mode > 2) { set_error("row_solve: bad mode %d", mode); return -2; }
   if (mode == BNMTF_MODE_VB && (!var || !SVpart)) { set_error("row_solve: VB needs var and SVpart"); return -2; }
   if (!polarity && !Gfull) { set_error("row_solve: polarity 0 needs Gfull"); return -2; }
@@ -231,6 +233,10 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
   a.fac = fac; a.var = var; a.mu = mu; a.tauf = tauf; a.lambda = lambda; a.scalars = scalars; a.order = order;
   a.min_tn = min_tn; a.seed = seed; a.iter = reinterpret_cast<const unsigned long long*>(iter); a.salt = salt;
   a.sterm = sterm; a.extra = extra; a.mstat = mstat; a.row_offset = row_offset;
+  a.peer_fac = reinterpret_cast<double* const*>(peer_fac);
+  a.peer_var = (mode == BNMTF_MODE_VB) ? reinterpret_cast<double* const*>(peer_var) : nullptr;
+  a.n_peers = peer_fac ? n_peers : 0; a.my_rank = my_rank;
+  if (a.peer_fac && mode == BNMTF_MODE_VB && !a.peer_var) { set_error("row_solve: VB peer exchange needs peer_var"); return -2; }
   return launch_row_solve(a, ST(stream));
 }
 

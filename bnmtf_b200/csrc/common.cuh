@@ -69,6 +69,9 @@ struct RowSolveArgs {
   double* sterm;   // optional: the masked-sum term s (rows x K), for the white-box muU()/muV() API
   double* extra;   // optional (VB): per-row sum_k [ var_k (g_kk + sv_k) + u_k^2 sv_k ] for exp_square_diff
   double* mstat;   // optional: rows x 4 {sum_obs r p, sum_obs p^2, sum_obs p, 0} of the row with its NEW factor values
+  // fused exchange of a row-sharded run: base pointers of every rank's replicated n x K factor (and variance) array,
+  // peer-mapped (NVLink P2P); a finished row is stored straight into each peer's copy at global row row_offset + row
+  double* const* peer_fac; double* const* peer_var; int n_peers, my_rank;
 };
 
 struct FinishArgs {

@@ -168,6 +168,21 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
     e = warp_sum(e);
     if (lane == 0) a.extra[row] = e;
   }
+  // fused exchange: the finished row goes straight into every peer's replicated copy (one coalesced K-double store per
+  // peer over NVLink) while the other warps are still in their chains; the host-side barrier follows the kernel
+  if (a.peer_fac) {
+    const size_t g0 = (size_t)(a.row_offset + row) * K;
+    for (int r = 0; r < a.n_peers; ++r) {
+      if (r == a.my_rank) continue;
+      double* pf = a.peer_fac[r] + g0;
+      double* pv = a.peer_var ? a.peer_var[r] + g0 : nullptr;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        if (c < K) { pf[c] = u[q]; if (pv) pv[c] = vr[q]; }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -191,10 +206,11 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) 
   __shared__ double u_s[KP][32];
   __shared__ double acc_s[KP][32];
   const int lane = threadIdx.x;
-  const int row = blockIdx.x * 32 + lane;
-  if (row >= a.rows) return;
+  const int row0 = blockIdx.x * 32;
+  const int row = row0 + lane;
   const int K = a.K;
   const bool vb = a.mode == MODE_VB;
+  if (row < a.rows) {                                  // (threads past the end only join the cooperative exchange below)
   for (int c = 0; c < KP; ++c) {
     u_s[c][lane] = c < K ? a.fac[(size_t)row * K + c] : 0.0;
     acc_s[c][lane] = 0.0;
@@ -298,6 +314,24 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) 
   }
   if (a.mstat) *reinterpret_cast<double4*>(a.mstat + (size_t)row * 4) = make_double4(rp, pp, sp, 0.0);
   if (a.extra) a.extra[row] = ex;
+  }
+  // fused exchange: the warp's 32 finished rows are contiguous (32 K doubles); store them into every peer's replicated
+  // copy with fully coalesced 256-byte stores over NVLink (values re-read from this rank's own copy, written above by
+  // the lanes of this warp)
+  if (a.peer_fac) {
+    __syncwarp();
+    const int nrow = min(32, a.rows - row0);
+    const size_t l0 = (size_t)row0 * K, g0 = (size_t)(a.row_offset + row0) * K;
+    for (int r = 0; r < a.n_peers; ++r) {
+      if (r == a.my_rank) continue;
+      double* pf = a.peer_fac[r] + g0;
+      for (int e = lane; e < nrow * K; e += 32) pf[e] = __ldcg(a.fac + l0 + e);
+      if (a.peer_var) {
+        double* pv = a.peer_var[r] + g0;
+        for (int e = lane; e < nrow * K; e += 32) pv[e] = __ldcg(a.var + l0 + e);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -685,15 +719,17 @@ int launch_pad_factor(const double* X, const double* Var, int n, int K, int n_al
   return check_launch("pad_factor");
 }
 
-// Default: thread-per-row whenever the columns are updated in their natural order -- at every size, so that a sharded
-// run uses the same kernel (and draws bit-identical Gibbs chains) as the unsharded one; both kernels are bound by the
-// same serial chain when the rows fit one wave.  White-box single-column calls and explicit orders use the
-// warp-per-row kernel.  BNMTF_SOLVE=warp forces it everywhere (tests compare the two).
+// Which solver: both are bound by the serial chain of a row's K updates.  A thread per row runs the whole phase as one
+// wave, ~0.2 ms + 2.5 us per 1024 rows (uncoalesced per-row loads); a warp per row needs a wave per ~6500 rows, ~16 us
+// per 1024 rows.  They cross near 14 000 rows: thread-per-row from 16384 rows on (the full matrix on 1-2 GPUs),
+// warp-per-row below (toy / GDSC sizes, 4-8 way shards), and always for explicit column orders and the white-box
+// single-column calls.  Same Philox counters in both, so the choice changes a Gibbs chain only by the rounding of the
+// K-term dot products (tests: 1e-8 after 4 sweeps).  BNMTF_SOLVE=lane | warp forces one (tests compare the two).
 int launch_row_solve(const RowSolveArgs& a, cudaStream_t st) {
   const int nt = tiles_for(a.K);
   const char* pref = getenv("BNMTF_SOLVE");
   const bool natural = a.order == nullptr && a.n_order == a.K;
-  const bool lane = natural && !(pref && pref[0] == 'w');
+  const bool lane = natural && (pref && pref[0] == 'l' ? true : pref && pref[0] == 'w' ? false : a.rows >= 16384);
   if (lane) {
     const int grid = (a.rows + 31) / 32;
     switch (nt) {

@@ -106,6 +106,42 @@ class Comm:
         import torch.distributed as dist
         dist.all_reduce(t, group=self.group)
 
+    # ---- fused exchange over peer memory (NVLink P2P stores from inside the solver kernel) ------------------------
+    def peer_enabled(self, device):
+        """True when the updated factor rows are exchanged by the solver kernel itself: world > 1, CUDA + NCCL group,
+        BNMTF_PEER != 0.  The NCCL all-gather of gather_rows() stays as the path for everything else (mu / tau on
+        demand, gloo on CPU) and as the fallback when symmetric memory cannot be set up on this system."""
+        if self.world == 1 or device.type != "cuda" or os.environ.get("BNMTF_PEER", "1") == "0":
+            return False
+        import torch.distributed as dist
+        return dist.is_initialized() and dist.get_backend(self.group) == "nccl"
+
+    def symmetric(self, shape, device):
+        """A zeroed fp64 tensor of `shape` allocated in symmetric memory and peer-mapped on every rank of the group
+        (torch.distributed._symmetric_memory: allocation, handle exchange and the cross-GPU barrier are torch's; the
+        stores into the peers' copies are ours, csrc/solve.cu).  Returns (tensor, handle, device array of the world
+        base pointers of this tensor on every rank).  The mapping is verified once by reading a probe value each rank
+        writes into its own copy."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        t = symm.empty(tuple(shape), dtype=torch.float64, device=device)
+        hdl = symm.rendezvous(t, group)
+        flat = t.view(-1)
+        flat.zero_()
+        flat[0] = float(self.rank + 1)
+        hdl.barrier(channel=0)
+        peers = [t if r == self.rank else hdl.get_remote_tensor(r, tuple(shape), torch.float64) for r in range(self.world)]
+        seen = [float(p.view(-1)[0].item()) for p in peers]
+        if seen != [float(r + 1) for r in range(self.world)]:
+            raise _lib.BnmtfError("symmetric-memory peer mapping check failed: read %s" % seen)
+        hdl.barrier(channel=0)
+        flat[0] = 0.0
+        torch.cuda.synchronize(device)
+        hdl.barrier(channel=0)
+        ptrs = torch.tensor([p.data_ptr() for p in peers], dtype=torch.int64, device=device)
+        return t, hdl, ptrs, peers
+
 
 class Dataset:
     """This rank's shards of R and of its observation mask on the device, in both orientations (row phase:
@@ -199,13 +235,30 @@ class Factor:
     """One factor matrix (n x K, replicated on every rank) with its variational / conditional parameters and its
     padded image.  Arrays have part.n_pad rows so that equal-size shards can be all-gathered in place."""
 
-    def __init__(self, part, K, device, vb):
+    def __init__(self, part, K, device, vb, comm=None):
         self.part, self.n, self.K = part, part.n, K
         z = lambda: torch.zeros((part.n_pad, K), dtype=torch.float64, device=device)
-        self.fac, self.lam = z(), z()
+        self.peer = None           # (handle, device array of peer base pointers of fac, ... of var) when the solver
+        if comm is not None and comm.peer_enabled(device):          # kernel exchanges the rows itself
+            try:
+                self.fac, hdl, pf, keep_f = comm.symmetric((part.n_pad, K), device)
+                self.var = pv = keep_v = None
+                if vb:
+                    self.var, _, pv, keep_v = comm.symmetric((part.n_pad, K), device)
+                self.peer = (hdl, pf, pv, keep_f, keep_v)
+            except _lib.BnmtfError:
+                raise
+            except Exception as exc:                                  # no symmetric memory on this system: NCCL all-gather
+                import warnings
+                warnings.warn("bnmtf_b200: symmetric memory unavailable (%s: %s); factor rows are exchanged with NCCL "
+                              "all-gathers instead of in-kernel peer stores" % (type(exc).__name__, exc))
+                self.peer = None
+        if self.peer is None:
+            self.fac = z()
+            self.var = z() if vb else None
+        self.lam = z()
         self.lam.fill_(1.0)
         self.mu, self.tauf = z(), z()
-        self.var = z() if vb else None
         self.n_alloc = ld_for(self.n) + 8
         KP = kp_for(K)
         self.Xp = torch.zeros((self.n_alloc, KP), dtype=torch.float64, device=device)
@@ -238,7 +291,9 @@ class BNMFEngine:
         self.umma_stages = int(os.environ.get("BNMTF_UMMA_STAGES", "3" if self.overlap else "0"))
         # 1: replay the sweep as a CUDA graph (single-GPU runs); 2: also when sharded (NCCL collectives captured)
         g = int(os.environ.get("BNMTF_GRAPH", "1"))
-        self.use_graph = g >= 2 or (g == 1 and dataset.world == 1)
+        # one GPU only: with the NCCL all-reduce and the symmetric-memory barriers captured (tried as BNMTF_GRAPH=2 on
+        # 2 GPUs: +1.5 %) the process group does not shut down cleanly
+        self.use_graph = g >= 1 and dataset.world == 1
         self._graph = self._graph_key = self._graph_seen = None
         self.split = int(os.environ.get("BNMTF_SPLIT", "72"))    # SMs given to the R.X kernel when both run concurrently (0: one after the other)
         self.umma_pair = int(os.environ.get("BNMTF_UMMA_PAIR", "1"))   # CTA pairs (cta_group::2) in the Gram kernel
@@ -249,8 +304,8 @@ class BNMFEngine:
         self.comm = comm if comm is not None else Comm(dataset.world, dataset.rank)
         dev = dataset.device
         I, J = dataset.I, dataset.J
-        self.U = Factor(dataset.partI, K, dev, self.vb)
-        self.V = Factor(dataset.partJ, K, dev, self.vb)
+        self.U = Factor(dataset.partI, K, dev, self.vb, self.comm)
+        self.V = Factor(dataset.partJ, K, dev, self.vb, self.comm)
         self.scalars = torch.zeros(16, dtype=torch.float64, device=dev)
         self.iter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.iter_scratch = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -441,6 +496,7 @@ class BNMFEngine:
         if want_sterm and self.sterm is None:
             self.sterm = torch.zeros((max(self.U.part.n_pad, self.V.part.n_pad), self.K), dtype=torch.float64,
                                      device=self.ds.device)
+        fused = gather and apply and me.peer is not None     # the kernel stores the finished rows into the peers' copies
         if rows > 0:
             _lib.call("bnmf_row_solve_f64", self.m, rows, self.K, nrx, ng, self.polarity,
                       _ptr(self.RXpart), _ptr(self.Gpart), _ptr(self.SVpart), _ptr(self.Gfull),
@@ -448,8 +504,12 @@ class BNMFEngine:
                       _ptr(self.scalars), order_ptr, n_order, 1 if apply else 0, float(minimum_TN),
                       self.seed, _ptr(self.iter if use_iter else self.iter_scratch), side, lo,
                       _ptr(self.sterm, lo) if want_sterm else 0, _ptr(self.extra) if want_extra else 0,
-                      _ptr(self.mstat) if want_mstat else 0, _stream())
-        if gather and self.comm.world > 1:
+                      _ptr(self.mstat) if want_mstat else 0,
+                      _ptr(me.peer[1]) if fused else 0, _ptr(me.peer[2]) if (fused and self.vb) else 0,
+                      self.comm.world if fused else 0, self.comm.rank, _stream())
+        if fused:
+            me.peer[0].barrier(channel=side)          # every rank's rows have landed in every copy before anyone reads
+        elif gather and self.comm.world > 1:
             if apply:
                 self.comm.gather_rows(me.fac, me.part)
                 if self.vb:

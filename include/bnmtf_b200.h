@@ -129,13 +129,21 @@ int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t 
  *   row_offset    : global index of row 0 of the arrays passed (0 unless the rows are sharded across GPUs)
  *   mstat         : optional rows x 4 doubles: {sum r p, sum p^2, sum p, 0} over the observed entries of the row with
  *                   its factor values after the update, p = fac_i . X_j -- computed from the row's statistics
- *                   (needs the masked column sums in slot (k, K) of the Gram tiles), no pass over R */
+ *                   (needs the masked column sums in slot (k, K) of the Gram tiles), no pass over R
+ *   peer_fac, peer_var, n_peers, my_rank : fused exchange of a row-sharded run (replaces the all-gather of the updated
+ *                   factor column that SURVEY.md section 8e describes).  peer_fac / peer_var: DEVICE arrays of n_peers
+ *                   device pointers, entry r = base of rank r's replicated n x K factor / variance array, peer-mapped
+ *                   into this process (CUDA IPC / symmetric memory; NVLink P2P stores).  Each finished row is stored
+ *                   into every other rank's copy at global row row_offset + row; fac / var passed above are this rank's
+ *                   own copy offset to its first row.  The caller runs a cross-GPU barrier before any rank reads the
+ *                   factor.  NULL: no exchange.  Requires apply != 0. */
 int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, int polarity,
                        const double* RXpart, const double* Gpart, const double* SVpart, const double* Gfull,
                        double* fac, double* var, double* mu, double* tauf, const double* lambda,
                        const double* scalars, const int* order, int n_order, int apply, double min_tn,
                        uint64_t seed, const uint64_t* iter, uint64_t salt, int64_t row_offset, double* sterm,
-                       double* extra, double* mstat, void* stream);
+                       double* extra, double* mstat, const uint64_t* peer_fac, const uint64_t* peer_var, int n_peers,
+                       int my_rank, void* stream);
 /* Sums over the set bits of `bits` of {e^2, p, p^2, r p, r, r^2, 1}, p = A_i.B_j  ->  out8 (predict(),
  * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8.
  * statics3 = {sum r, sum r^2, count} of this mask if already known (training mask; selects the lean kernel that

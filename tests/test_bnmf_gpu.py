@@ -177,11 +177,11 @@ def test_tn_moments_in_the_tail_follow_scipys_erfc():
     np.testing.assert_allclose(D.TN_vector_variance(mu, tau), (1.0 / (np.abs(mu) * tau)) ** 2, rtol=1e-15)
 
 
-# ---- the thread-per-row solver (k_bnmf_row_solve_lane, the default for run()) vs the warp-per-row one ---------------
+# ---- the thread-per-row solver (k_bnmf_row_solve_lane, the default from 16384 rows on) vs the warp-per-row one --------
 @pytest.mark.parametrize("name", ["toy_bnmf_vb", "gdsc_bnmf_vb"])
-def test_warp_solver_vb_trajectory_matches_reference(models, golden, name, monkeypatch):
-    """The same golden VB trajectories with the warp-per-row solver forced (BNMTF_SOLVE=warp), 1e-9 as above."""
-    monkeypatch.setenv("BNMTF_SOLVE", "warp")
+def test_lane_solver_vb_trajectory_matches_reference(models, golden, name, monkeypatch):
+    """The same golden VB trajectories with the thread-per-row solver forced (BNMTF_SOLVE=lane), 1e-9 as above."""
+    monkeypatch.setenv("BNMTF_SOLVE", "lane")
     g = golden(name)
     m = vb_from_golden(models, g)
     m.run(int(g["its"]))
@@ -193,8 +193,8 @@ def test_warp_solver_vb_trajectory_matches_reference(models, golden, name, monke
         close(getattr(m, k), g["final_" + k], what=k)
 
 
-def test_warp_solver_icm_trajectory_matches_reference(models, golden, monkeypatch):
-    monkeypatch.setenv("BNMTF_SOLVE", "warp")
+def test_lane_solver_icm_trajectory_matches_reference(models, golden, monkeypatch):
+    monkeypatch.setenv("BNMTF_SOLVE", "lane")
     g = golden("toy_nmf_icm")
     m = models.nmf_icm(g["R"], g["M"], int(g["K"]), priors2(g))
     m.initialise("exp")
@@ -224,3 +224,19 @@ def test_lane_and_warp_solvers_draw_the_same_gibbs_chain(models, shape, K, monke
         out[solver] = (m.U.copy(), m.V.copy(), m.tau, list(m.all_performances["MSE"]))
     for a, b in zip(out["lane"], out["warp"]):
         close(a, b, rtol=1e-8)
+
+
+def test_uploaded_dataset_is_shared_between_models(models, golden):
+    """data.upload() -> one resident copy of (R, M) for several models (from_dataset), same results as the host path."""
+    from bnmtf_b200 import data
+    g = golden("toy_bnmf_vb")
+    ds = data.upload(g["R"], g["M"])
+    K, pri = int(g["K"]), priors2(g)
+    a = models.bnmf_vb_optimised.from_dataset(ds, K, pri)
+    b = models.bnmf_vb_optimised(g["R"], g["M"], K, pri)
+    c = models.nmf_icm.from_dataset(ds, K, pri)
+    for m in (a, b, c):
+        m.initialise("exp")
+        m.run(3)
+    close(a.expU, b.expU, rtol=1e-13), close(a.all_performances["MSE"], b.all_performances["MSE"], rtol=1e-13)
+    assert len(c.all_performances["MSE"]) == 3 and a._engine().ds is c._engine().ds
