@@ -335,6 +335,207 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_bnmf_row_solve_sub<NT, W>: the same update with W lanes per row (W = 1, 2, 4, ..., 32), natural column order.
+//
+// The phase is bound by the serial chain of a row's K updates, so the only useful parallelism is ACROSS rows: W is
+// chosen by the launcher so that the rows of this shard make about one wave of warps on the chip (65536 rows: W = 1,
+// a thread per row; 8192 rows on an 8-way shard: W = 8; toy sizes: W = 32, a warp per row).  Fewer rows then mean
+// more lanes per row, fewer columns per lane and a shorter chain: the solver keeps scaling when the matrix is sharded,
+// which neither fixed mapping does (warp per row: a wave per ~6500 rows; thread per row: a 0.2 ms floor).
+//
+// Lane j of a row's group owns columns c = j, j+W, j+2W, ...: their u_c and acc_c live in registers, statically
+// indexed because the k loop is fully unrolled (the thread-per-row kernel above spends most of its ~1300 instructions
+// per column on predicated loops over the padded columns and on address arithmetic; here both are resolved at compile
+// time).  Per column k: every lane loads its columns c >= k of row k of the packed Gram tiles, the group reduces
+//     dot_k = acc[k] + sum_{c>k} G[k][c] u_c(old)        (acc[k] = sum_{c<k} G[c][k] u_c(new), pushed earlier)
+// with log2 W shuffles, all W lanes evaluate the truncated-normal update redundantly (same inputs, same result), the
+// owner of column k keeps u_k, and every lane pushes acc_c += G[k][c] u_k(new) for its columns c > k.  W = 1 performs
+// exactly the operations of the thread-per-row kernel in the same order.
+// ---------------------------------------------------------------------------------------------------
+__device__ __noinline__ void row_update_value(int mode, double mu_k, double tau_k, double min_tn, unsigned long long seed,
+                                              unsigned long long stream, unsigned long long index, double& val, double& vv) {
+  vv = 0.0;
+  if (mode == MODE_GIBBS) {
+    Philox rng(seed, stream, index);
+    val = tn_draw(mu_k, tau_k, rng);
+  } else if (mode == MODE_VB) {
+    tn_moments(mu_k, tau_k, val, vv);
+  } else {
+    val = (mu_k != mu_k) ? mu_k : fmax(mu_k, 0.0);   // numpy.maximum propagates NaN (nmf_icm.py:129)
+    val = (val != val) ? val : fmax(val, min_tn);
+  }
+}
+
+template <int NT, int W>
+__global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_sub(RowSolveArgs a) {
+  constexpr int KP = 8 * NT;
+  constexpr int NTP = NT * (NT + 1) / 2;
+  constexpr int CPL = (KP + W - 1) / W;       // columns per lane
+  constexpr int RPW = 32 / W;                 // rows per warp
+  const int lane = threadIdx.x;
+  const int j = lane % W, g = lane / W;
+  const int row0 = blockIdx.x * RPW;
+  const bool live = row0 + g < a.rows;
+  const int row = live ? row0 + g : a.rows - 1;   // groups past the end shadow the last row and store nothing
+  const int K = a.K;
+  const bool vb = a.mode == MODE_VB;
+  double u[CPL], acc[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = j + i * W;
+    u[i] = c < K ? a.fac[(size_t)row * K + c] : 0.0;
+    acc[i] = 0.0;
+  }
+  const double tau = a.scalars[S_TAU];
+  const unsigned long long it = a.iter ? *a.iter : 0ull;
+  const size_t gstride = (size_t)a.rows * (NTP * 64);
+  const double* grow = a.Gpart + (size_t)row * (NTP * 64);
+  const double* rxrow = a.RXpart + (size_t)row * KP;
+  const size_t rxstride = (size_t)a.rows * KP;
+  double rp = 0.0, pp = 0.0, sp = 0.0, ex = 0.0;
+  {
+    const char* l0 = reinterpret_cast<const char*>(a.lambda + (size_t)row * K);
+    for (int off = j * 128; off < K * 8; off += W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l0 + off));
+    for (int sgm = 0; sgm < a.nseg_rx; ++sgm)
+      for (int off = j * 128; off < KP * 8; off += W * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rxrow + sgm * rxstride) + off));
+  }
+
+  // column k = ik * W + jk: register slot ik (unrolled: every register index below is a compile-time constant),
+  // owner lane jk (a run-time loop: it only enters comparisons with j and the shuffle source)
+#pragma unroll
+  for (int ik = 0; ik < CPL; ++ik) {
+    for (int jk = 0; jk < W; ++jk) {
+      const int k = ik * W + jk;
+      if (k >= K) break;
+      const int ta = k >> 3, r = k & 7;
+      if (k + 1 < K) {                         // next row of the Gram tiles -> L2
+        const int tn = (k + 1) >> 3, rn = (k + 1) & 7;
+        for (int sgm = 0; sgm < a.nseg_g; ++sgm)
+          for (int tb = tn + j; tb < NT; tb += W)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + sgm * gstride + tile_pair(tn, tb, NT) * 64 + rn * 8));
+      }
+      // this lane's columns c >= k of row k: the diagonal, the columns still to be updated, and the column-sum slot K
+      double gv[CPL];
+      if constexpr (W == 1) {
+        // a thread per row owns every column: whole tile rows, two 32-byte loads each (one sector per lane and load)
+#pragma unroll
+        for (int tb = 0; tb < NT; ++tb) {
+          if (8 * tb + 7 >= ik) {                            // (ik == k here: compile-time)
+            const int off = tile_pair(ta, tb, NT) * 64 + r * 8;
+            double4 lo = make_double4(0, 0, 0, 0), hi = make_double4(0, 0, 0, 0);
+            for (int sgm = 0; sgm < a.nseg_g; ++sgm) {
+              const double4 x = *reinterpret_cast<const double4*>(grow + sgm * gstride + off);
+              const double4 y = *reinterpret_cast<const double4*>(grow + sgm * gstride + off + 4);
+              lo.x += x.x; lo.y += x.y; lo.z += x.z; lo.w += x.w;
+              hi.x += y.x; hi.y += y.y; hi.z += y.z; hi.w += y.w;
+            }
+            if (!a.polarity) {
+              const double4 x = *reinterpret_cast<const double4*>(a.Gfull + off);
+              const double4 y = *reinterpret_cast<const double4*>(a.Gfull + off + 4);
+              lo.x = x.x - lo.x; lo.y = x.y - lo.y; lo.z = x.z - lo.z; lo.w = x.w - lo.w;
+              hi.x = y.x - hi.x; hi.y = y.y - hi.y; hi.z = y.z - hi.z; hi.w = y.w - hi.w;
+            }
+            gv[8 * tb + 0] = lo.x; gv[8 * tb + 1] = lo.y; gv[8 * tb + 2] = lo.z; gv[8 * tb + 3] = lo.w;
+            gv[8 * tb + 4] = hi.x; gv[8 * tb + 5] = hi.y; gv[8 * tb + 6] = hi.z; gv[8 * tb + 7] = hi.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gv[8 * tb + q] = 0.0;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const int c = j + i * W;
+          gv[i] = 0.0;
+          if (i >= ik && c >= k && c <= K) {                 // (first test: compile-time)
+            const int off = tile_pair(ta, c >> 3, NT) * 64 + r * 8 + (c & 7);
+            double t = 0.0;
+            for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += grow[sgm * gstride + off];
+            gv[i] = a.polarity ? t : a.Gfull[off] - t;
+          }
+        }
+      }
+      double rxk = 0.0, svk = 0.0;
+      for (int sgm = 0; sgm < a.nseg_rx; ++sgm) rxk += rxrow[sgm * rxstride + k];
+      if (vb) {
+        double t = 0.0;
+        for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += a.SVpart[((size_t)sgm * a.rows + row) * KP + k];
+        svk = a.polarity ? t : a.Gfull[NTP * 64 + k] - t;
+      }
+      const size_t idx = (size_t)row * K + k;
+      const double lam = a.lambda[idx];
+      double part = 0.0;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = j + i * W;
+        if (i >= ik && c > k && c < K) part = fma(gv[i], u[i], part);
+      }
+      double gkk = gv[ik], acck = acc[ik], uold = u[ik], colsum = 0.0;
+      if (W > 1) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, W);
+        gkk = __shfl_sync(0xffffffffu, gkk, jk, W);
+        acck = __shfl_sync(0xffffffffu, acck, jk, W);
+        uold = __shfl_sync(0xffffffffu, uold, jk, W);
+      }
+      if (a.mstat) {                           // slot (k, K): the masked column sum of the other factor's column k
+        const int off = tile_pair(ta, K >> 3, NT) * 64 + r * 8 + (K & 7);
+        double t = 0.0;
+        for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += grow[sgm * gstride + off];
+        colsum = a.polarity ? t : a.Gfull[off] - t;
+      }
+      const double s = rxk - (acck + part);
+      const double b = vb ? gkk + svk : gkk;
+      const double tau_k = tau * b;
+      const double mu_k = (1.0 / tau_k) * (-lam + tau * s);
+      double unew = uold, vv = 0.0;
+      if (a.apply) {
+        row_update_value(a.mode, mu_k, tau_k, a.min_tn, a.seed, it * 16ull + a.salt,
+                         (unsigned long long)(a.row_offset + row) * K + k, unew, vv);
+        if (j == jk) u[ik] = unew;
+      } else if (vb) {
+        vv = a.var[idx];
+      }
+      if (live && j == jk) {
+        if (a.apply) { a.fac[idx] = unew; if (vb) a.var[idx] = vv; }
+        if (a.mu) a.mu[idx] = mu_k;
+        if (a.tauf) a.tauf[idx] = tau_k;
+        if (a.sterm) a.sterm[idx] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = j + i * W;
+        if (i >= ik && c > k && c < K) acc[i] = fma(gv[i], unew, acc[i]);
+      }
+      rp = fma(unew, rxk, rp);
+      sp = fma(unew, colsum, sp);
+      pp = fma(unew, fma(gkk, unew, 2.0 * acck), pp);
+      ex += vv * (gkk + svk) + unew * unew * svk;
+    }
+  }
+  if (live && j == 0) {
+    if (a.mstat) *reinterpret_cast<double4*>(a.mstat + (size_t)row * 4) = make_double4(rp, pp, sp, 0.0);
+    if (a.extra) a.extra[row] = ex;
+  }
+  // fused exchange (see k_bnmf_row_solve_lane): the warp's RPW finished rows are contiguous
+  if (a.peer_fac) {
+    __syncwarp();
+    const int nrow = min(RPW, a.rows - row0);
+    const size_t l0 = (size_t)row0 * K, g0 = (size_t)(a.row_offset + row0) * K;
+    for (int r = 0; r < a.n_peers; ++r) {
+      if (r == a.my_rank) continue;
+      double* pf = a.peer_fac[r] + g0;
+      for (int e = lane; e < nrow * K; e += 32) pf[e] = __ldcg(a.fac + l0 + e);
+      if (a.peer_var) {
+        double* pv = a.peer_var[r] + g0;
+        for (int e = lane; e < nrow * K; e += 32) pv[e] = __ldcg(a.var + l0 + e);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_masked_metrics: partial sums over the set bits of `bits` of  e^2, p, p^2 (and, FULL, r*p, r, r^2, 1)  with
 // p = A_i . B_j (predict / predict_while_running, bnmf_gibbs_optimised.py:199-223).  The prediction tile is a
 // DMMA product of padded factor rows; a warp owns 16 rows and walks 32 columns at a time (4 column tiles
@@ -719,17 +920,46 @@ int launch_pad_factor(const double* X, const double* Var, int n, int K, int n_al
   return check_launch("pad_factor");
 }
 
-// Which solver: both are bound by the serial chain of a row's K updates.  A thread per row runs the whole phase as one
-// wave, ~0.2 ms + 2.5 us per 1024 rows (uncoalesced per-row loads); a warp per row needs a wave per ~6500 rows, ~16 us
-// per 1024 rows.  They cross near 14 000 rows: thread-per-row from 16384 rows on (the full matrix on 1-2 GPUs),
-// warp-per-row below (toy / GDSC sizes, 4-8 way shards), and always for explicit column orders and the white-box
-// single-column calls.  Same Philox counters in both, so the choice changes a Gibbs chain only by the rounding of the
-// K-term dot products (tests: 1e-8 after 4 sweeps).  BNMTF_SOLVE=lane | warp forces one (tests compare the two).
+// Which solver, for the natural column order (K <= 31):
+//   rows >= 24576        k_bnmf_row_solve_lane, a thread per row (one wave of warps from 65536 rows; 0.2 ms floor)
+//   fewer rows           k_bnmf_row_solve_sub with W = 4, 8, 16 or 32 lanes per row, the smallest W that turns the rows
+//                        of this launch into about one wave (>= 1536 warps): 16384 rows -> 4, 8192 -> 8, <= 2048 -> 32
+// (W = 1, 2 of the sub-warp kernel would be the thread-per-row case again, but 24-32 fully unrolled column bodies per
+// instantiation spill at 128 registers and take minutes to compile, so the older kernel keeps that range.)
+// Explicit column orders, the white-box single-column calls and K > 31 use the warp-per-row kernel k_bnmf_row_solve.
+// Same Philox counters everywhere, so the choice changes a Gibbs chain only by the rounding of the K-term dot
+// products (tests: 1e-8 after 4 sweeps).  BNMTF_SOLVE = warp | lane | sub<W> forces a kernel (tests compare them).
+template <int NT>
+static int launch_row_solve_sub(const RowSolveArgs& a, int W, cudaStream_t st) {
+  const int rpw = 32 / W, grid = (a.rows + rpw - 1) / rpw;
+  switch (W) {
+#define BNMTF_SUB(WW) case WW: k_bnmf_row_solve_sub<NT, WW><<<grid, 32, 0, st>>>(a); break;
+    BNMTF_SUB(4) BNMTF_SUB(8) BNMTF_SUB(16) BNMTF_SUB(32)
+#undef BNMTF_SUB
+    default: set_error("row_solve: W=%d is not one of 4, 8, 16, 32", W); return -2;
+  }
+  return check_launch("row_solve_sub");
+}
+
 int launch_row_solve(const RowSolveArgs& a, cudaStream_t st) {
   const int nt = tiles_for(a.K);
   const char* pref = getenv("BNMTF_SOLVE");
   const bool natural = a.order == nullptr && a.n_order == a.K;
-  const bool lane = natural && (pref && pref[0] == 'l' ? true : pref && pref[0] == 'w' ? false : a.rows >= 16384);
+  int W = 0;                                             // 0: not the sub-warp kernel
+  bool lane = natural && pref && pref[0] == 'l';
+  if (natural && nt <= 4 && !(pref && (pref[0] == 'w' || pref[0] == 'l'))) {
+    if (pref && pref[0] == 's' && pref[1] == 'u' && pref[2] == 'b') W = atoi(pref + 3);
+    else if (a.rows >= 24576) lane = true;
+    else { W = 4; while (W < 32 && (long long)a.rows * W < 1536ll * 32) W *= 2; }
+  }
+  if (W > 0) {
+    switch (nt) {
+      case 1: return launch_row_solve_sub<1>(a, W, st);
+      case 2: return launch_row_solve_sub<2>(a, W, st);
+      case 3: return launch_row_solve_sub<3>(a, W, st);
+      default: return launch_row_solve_sub<4>(a, W, st);
+    }
+  }
   if (lane) {
     const int grid = (a.rows + 31) / 32;
     switch (nt) {

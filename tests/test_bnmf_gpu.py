@@ -177,11 +177,16 @@ def test_tn_moments_in_the_tail_follow_scipys_erfc():
     np.testing.assert_allclose(D.TN_vector_variance(mu, tau), (1.0 / (np.abs(mu) * tau)) ** 2, rtol=1e-15)
 
 
-# ---- the thread-per-row solver (k_bnmf_row_solve_lane, the default from 16384 rows on) vs the warp-per-row one --------
+# ---- the row solvers: sub-warp (W lanes per row, the default below 24576 rows), thread per row (from 24576 rows on),
+# ---- warp per row (explicit orders) -- csrc/solve.cu::launch_row_solve; BNMTF_SOLVE forces one of them
+SOLVERS = ["warp", "lane", "sub4", "sub8", "sub16", "sub32"]
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
 @pytest.mark.parametrize("name", ["toy_bnmf_vb", "gdsc_bnmf_vb"])
-def test_lane_solver_vb_trajectory_matches_reference(models, golden, name, monkeypatch):
-    """The same golden VB trajectories with the thread-per-row solver forced (BNMTF_SOLVE=lane), 1e-9 as above."""
-    monkeypatch.setenv("BNMTF_SOLVE", "lane")
+def test_every_solver_follows_the_golden_vb_trajectory(models, golden, name, solver, monkeypatch):
+    """The golden VB trajectories with each row-solver kernel forced, 1e-9 as above."""
+    monkeypatch.setenv("BNMTF_SOLVE", solver)
     g = golden(name)
     m = vb_from_golden(models, g)
     m.run(int(g["its"]))
@@ -193,8 +198,9 @@ def test_lane_solver_vb_trajectory_matches_reference(models, golden, name, monke
         close(getattr(m, k), g["final_" + k], what=k)
 
 
-def test_lane_solver_icm_trajectory_matches_reference(models, golden, monkeypatch):
-    monkeypatch.setenv("BNMTF_SOLVE", "lane")
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_every_solver_follows_the_golden_icm_trajectory(models, golden, solver, monkeypatch):
+    monkeypatch.setenv("BNMTF_SOLVE", solver)
     g = golden("toy_nmf_icm")
     m = models.nmf_icm(g["R"], g["M"], int(g["K"]), priors2(g))
     m.initialise("exp")
@@ -205,25 +211,29 @@ def test_lane_solver_icm_trajectory_matches_reference(models, golden, monkeypatc
     close(m.U, g["final_U"]), close(m.V, g["final_V"])
 
 
-@pytest.mark.parametrize("shape,K", [((300, 170), 7), ((2500, 96), 20), ((130, 2300), 33)])
-def test_lane_and_warp_solvers_draw_the_same_gibbs_chain(models, shape, K, monkeypatch):
-    """Same Philox counters, same statistics: the two solvers differ only in the summation order of the K-term dot
-    products, so a short Gibbs chain agrees to ~1e-10 (a draw that lands on a branch boundary of the sampler would
-    show up as an O(1) difference)."""
+@pytest.mark.parametrize("shape,K", [((300, 170), 7), ((2500, 96), 20), ((130, 2300), 31), ((37, 45), 3)])
+def test_all_solvers_draw_the_same_gibbs_chain(models, shape, K, monkeypatch):
+    """Same Philox counters, same statistics: the solvers differ only in the summation order of the K-term dot
+    products, so a short Gibbs chain agrees to ~1e-10 between any two of them (a draw that lands on a branch boundary
+    of the sampler would show up as an O(1) difference).  Ragged row counts exercise the partial last warp."""
     rng = np.random.RandomState(5)
     I, J = shape
     R = rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (J, K)).T + rng.normal(size=(I, J))
     M = (rng.rand(I, J) >= 0.25).astype(float)
     pri = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
     out = {}
-    for solver in ("warp", "lane"):
-        monkeypatch.setenv("BNMTF_SOLVE", solver)
+    for solver in SOLVERS + [""]:
+        if solver:
+            monkeypatch.setenv("BNMTF_SOLVE", solver)
+        else:
+            monkeypatch.delenv("BNMTF_SOLVE")              # the launcher's own choice
         m = models.bnmf_gibbs_optimised(R, M, K, pri, seed=3)
         m.initialise("exp")
         m.run(4)
         out[solver] = (m.U.copy(), m.V.copy(), m.tau, list(m.all_performances["MSE"]))
-    for a, b in zip(out["lane"], out["warp"]):
-        close(a, b, rtol=1e-8)
+    for solver in SOLVERS[1:] + [""]:
+        for a, b in zip(out[solver], out["warp"]):
+            close(a, b, rtol=1e-8, what=solver or "default")
 
 
 def test_uploaded_dataset_is_shared_between_models(models, golden):
