@@ -12,7 +12,7 @@ one after the other (or, for ParallelMatrixCrossValidation, in a multiprocessing
 `DevicePool` hands the fits to the GPUs of the box, one worker thread per GPU (BASELINE.json, config 5: "folds x grid
 points across 8 B200").  With one GPU -- or `devices=1` -- the fits run inline in exactly the reference's order, so the
 host random streams (numpy for the initialisations, python's `random` for folds, K-means and the VB-NMTF update order)
-are consumed identically and seeded runs reproduce the reference's numbers (tests/test_model_selection_gpu.py).  With
+are consumed identically and seeded runs reproduce the reference's numbers (tests/test_model_selection.py).  With
 several GPUs the candidate models are still built and initialised in that order, but they run concurrently: models
 that draw host random numbers inside run() are then no longer bit-reproducible.
 
