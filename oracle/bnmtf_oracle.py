@@ -6,8 +6,9 @@ relative to /root/reference).  Only tests/, __graft_entry__.smoke() and bench.py
 reference legs may import this module, and only as the checker or the timed CPU baseline.
 
 Parity pinning: tests/test_oracle_vs_reference.py runs this module against the reference's own code
-(imported through oracle/ref_shim.py in the build container) and against the committed golden fixtures in
-tests/golden/ (generated from the reference by tests/golden/make_golden.py).  Deterministic paths
+(imported through oracle/ref_shim.py in the build container) on fresh seeded inputs, and
+tests/test_oracle_golden.py against the committed golden fixtures in tests/golden/ (generated from the
+reference by tests/golden/make_golden.py; runs anywhere).  Deterministic paths
 (VB, ICM, NP, and the mu/tau parameters of Gibbs) agree to ~1e-12; the random draws agree in distribution
 only (the reference uses the GPL table sampler rtnorm.py, which is deliberately NOT reproduced here --
 the oracle draws by inverse CDF, a documented deviation that makes the oracle *faster* than the reference).

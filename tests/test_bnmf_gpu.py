@@ -250,3 +250,43 @@ def test_uploaded_dataset_is_shared_between_models(models, golden):
         m.run(3)
     close(a.expU, b.expU, rtol=1e-13), close(a.all_performances["MSE"], b.all_performances["MSE"], rtol=1e-13)
     assert len(c.all_performances["MSE"]) == 3 and a._engine().ds is c._engine().ds
+
+
+@pytest.mark.parametrize("I,J,K,frac", [(23, 17, 4, 0.3), (40, 155, 7, 0.6), (513, 64, 20, 0.2), (64, 1030, 31, 0.45)])
+def test_vb_and_icm_against_the_oracle_on_fresh_inputs(models, I, J, K, frac):
+    """Shapes, ranks and missing fractions the golden fixtures do not contain (ragged tiles, K = 31, 60 % missing, so
+    both polarities of the Gram kernel): 8 VB sweeps and 8 ICM sweeps from a seeded random start against the CPU oracle
+    (itself checked against the live reference on such inputs by tests/test_oracle_vs_reference.py), 1e-9."""
+    from oracle import bnmtf_oracle as orc
+    rng = np.random.RandomState(I + J)
+    R = np.abs(rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (J, K)).T + rng.normal(size=(I, J)) + 3.0)
+    M = (rng.rand(I, J) >= frac).astype(float)
+    M[np.arange(I), rng.randint(0, J, I)] = 1.0
+    M[rng.randint(0, I, J), np.arange(J)] = 1.0
+    pri = {"alpha": 2.0, "beta": 0.5, "lambdaU": 0.3, "lambdaV": 0.7}
+    np.random.seed(4)
+    m = models.bnmf_vb_optimised(R, M, K, pri)
+    m.initialise("random")
+    o = orc.OracleBNMF(R, M, K, pri, mode="vb")
+    o.init_vb(m.muU.copy(), m.muV.copy())
+    close(m.expU, o.U), close(m.exptau, o.exptau)
+    mse = [o.sweep()["MSE"] for _ in range(8)]
+    m.run(8)
+    close(m.all_performances["MSE"], mse, what="MSE trace")
+    close(m.exptau, o.exptau), close(m.quality("ELBO"), o.elbo()), close(m.quality("BIC"), o.quality("BIC"))
+    # factors: 1e-9, except the 64 x 1030 case, whose VB iteration doubles a perturbation every sweep: 3e-11 after one
+    # sweep, 2e-8 after eight -- the same figures with the fp64 mma.sync statistics (BNMTF_GRAM=dmma BNMTF_RX=dmma) as
+    # with the tcgen05 fixed-point ones and with either solver (tools/fresh_debug.py), i.e. the conditioning of that
+    # problem, not a property of a kernel.  Checked at 1e-7 there; its traces above still hold 1e-9
+    ftol = 1e-7 if min(I, J) < 100 and max(I, J) > 1000 else 1e-9
+    close(m.expU, o.U, rtol=ftol, what="expU"), close(m.expV, o.V, rtol=ftol, what="expV")
+    close(m.varU, o.varU, rtol=ftol, what="varU")
+    np.random.seed(5)
+    c = models.nmf_icm(R, M, K, pri)
+    c.initialise("random")
+    oc = orc.OracleBNMF(R, M, K, pri, mode="icm")
+    oc.set_state(c.U.copy(), c.V.copy(), tau=c.tau)
+    for _ in range(8):
+        oc.sweep(minimum_TN=0.05)
+    c.run(8, minimum_TN=0.05)
+    close(c.U, oc.U, what="ICM U"), close(c.V, oc.V, what="ICM V"), close(c.tau, oc.tau)
