@@ -9,16 +9,13 @@ reference.  State attributes (U, V, tau, expU, muU, ...) are host numpy arrays, 
 white-box tests; every method uploads them, runs CUDA kernels through the C ABI and downloads the result.
 run(iterations) keeps the whole loop on the device (no host round trip per column or per iteration).
 """
-import itertools
 import math
-import time
 
 import numpy as np
 import torch
 
 from . import _lib
-from .engine import (BNMFEngine, Dataset, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_MSE, S_R2, S_RP, S_SUM_E2, S_TAU,
-                     _ptr, _stream, require_cuda)
+from .engine import BNMFEngine, Dataset, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_TAU, _ptr, _stream, require_cuda
 
 METRICS = ['MSE', 'R^2', 'Rp']
 QUALITY = ['loglikelihood', 'BIC', 'AIC', 'MSE', 'ELBO']

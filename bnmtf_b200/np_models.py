@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .bnmf import METRICS, _metrics_from_sums
+from .bnmf import _metrics_from_sums
 from .engine import Dataset, _ptr, _stream, require_cuda
 
 

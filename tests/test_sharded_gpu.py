@@ -1,5 +1,4 @@
 """2-GPU run of the row-sharded engine against the single-GPU engine (skipped on a 1-GPU box)."""
-import json
 import os
 import subprocess
 import sys

@@ -1,8 +1,6 @@
 """tcgen05 statistics kernels (csrc/gram_umma.cu, csrc/rx_umma.cu) against numpy restatements of the sums they replace
 (the masked row sums of bnmf_gibbs_optimised.py:167-177 / bnmf_vb_optimised.py:189-195), against the fp64 mma.sync
 kernels, and -- through the model classes -- against each other over whole trajectories.  All through the C ABI."""
-import os
-
 import numpy as np
 import pytest
 
