@@ -164,6 +164,66 @@ def test_drivers_with_the_reference_models_reproduce_the_reference_drivers():
         assert_same(res, GOLDEN[name], 0.0, name)
 
 
+CV_SCRIPT = r"""
+import contextlib, importlib, io, json, os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {here!r}); sys.path.insert(0, os.path.join({here!r}, "golden"))
+import numpy as np
+import selection_cases as cases
+import cv_standin
+which, outdir = sys.argv[1], sys.argv[2]
+if which == "ref":
+    from oracle import ref_shim
+    ref_shim.load()
+    cv = "BNMTF.code.cross_validation."
+    par = importlib.import_module(cv + "parallel_matrix_cross_validation").ParallelMatrixCrossValidation
+    nest = importlib.import_module(cv + "nested_matrix_cross_validation").MatrixNestedCrossValidation
+else:
+    from bnmtf_b200 import model_selection as ms
+    par, nest = ms.ParallelMatrixCrossValidation, ms.MatrixNestedCrossValidation
+rng = np.random.RandomState(0)
+X = rng.exponential(1.0, (24, 3)) @ rng.exponential(1.0, (18, 3)).T + 0.1 * rng.normal(size=(24, 18))
+M = (rng.rand(24, 18) >= 0.15).astype(float)
+search = [{{'rank': 1}}, {{'rank': 3, 'shrink': 0.1}}, {{'rank': 6}}]
+cfg = {{'iterations': 3}}
+cases.seed_all(11)
+with contextlib.redirect_stdout(io.StringIO()):
+    a = par(method=cv_standin.SVDModel, X=X, M=M, K=4, parameter_search=search, train_config=cfg,
+            file_performance=os.path.join(outdir, "par.txt"), P=2)
+    a.run()
+    best = a.find_best_parameters('MSE', True)
+    a.fout.close()
+    files = [os.path.join(outdir, "nested%d.txt" % i) for i in range(3)]
+    b = nest(method=cv_standin.SVDModel, X=X, M=M, K=3, P=2, parameter_search=search, train_config=cfg,
+             file_performance=os.path.join(outdir, "nest.txt"), files_nested_performances=files)
+    b.run()
+    b.fout.close()
+res = {{"performances": a.performances, "best": [best[0], best[1]], "nested_all": b.all_performances,
+       "nested_average": b.average_performances, "par_log": open(os.path.join(outdir, "par.txt")).read(),
+       "nest_log": open(os.path.join(outdir, "nest.txt")).read(), "inner_logs": [open(f).read() for f in files]}}
+json.dump(cases._listify(res), open(os.path.join(outdir, "result.json"), "w"))
+"""
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/models"), reason="reference tree not present")
+def test_parallel_and_nested_cross_validation_reproduce_the_reference(tmp_path):
+    """ParallelMatrixCrossValidation (the reference: a multiprocessing.Pool over the folds) and
+    MatrixNestedCrossValidation against the reference's own classes, with a deterministic CPU stand-in model
+    (tests/cv_standin.py) and seeded fold generation: same per-fold numbers, same choices, same log files.  Each side
+    runs in a fresh interpreter (the reference forks its pool; not from inside the multi-threaded test process)."""
+    import subprocess
+    out = {}
+    for tag in ("ref", "ours"):
+        d = tmp_path / tag
+        d.mkdir()
+        code = CV_SCRIPT.format(root=os.path.join(HERE, ".."), here=HERE)
+        res = subprocess.run([sys.executable, "-c", code, tag, str(d)], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-3000:]
+        out[tag] = json.load(open(str(d / "result.json")))
+    for key in ("performances", "best", "nested_all", "nested_average", "par_log", "nest_log", "inner_logs"):
+        assert_same(out["ours"][key], out["ref"][key], 1e-12, key)
+
+
 # ---- GPU -----------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["line_search_vb", "line_search_icm", "grid_search_vb", "greedy_search_vb", "line_search_cv",
