@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .bnmf import METRICS, QUALITY, _TwoFactorBase, _metrics_from_sums
+from .bnmf import METRICS, QUALITY, _TwoFactorBase, _elbo_alpha_s_correction, _metrics_from_sums
 from .engine import (MODE, Dataset, Factor, Partition, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_TAU, _ptr, _stream, gram_len,
                      kp_for, require_cuda)
 
@@ -503,13 +503,19 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
 
     def _push(self):
         eng = self._engine()
+        # (attributes the caller has not set yet are not uploaded -- see bnmf.bnmf_vb_optimised._push)
         for f, s in ((eng.F, 'F'), (eng.G, 'G')):
-            self._up(f.fac, getattr(self, 'exp' + s)), self._up(f.var, getattr(self, 'var' + s))
-            self._up(f.mu, getattr(self, 'mu' + s)), self._up(f.tauf, getattr(self, 'tau' + s))
+            for attr, t in (('exp', f.fac), ('var', f.var), ('mu', f.mu), ('tau', f.tauf)):
+                value = getattr(self, attr + s, None)
+                if value is not None:
+                    self._up(t, value)
             self._up(f.lam, getattr(self, 'lambda' + s))
         S = eng.S
-        self._up(S["fac"], self.expS), self._up(S["var"], self.varS), self._up(S["mu"], self.muS)
-        self._up(S["tauf"], self.tauS), self._up(S["lam"], self.lambdaS)
+        for attr, key in (('exp', 'fac'), ('var', 'var'), ('mu', 'mu'), ('tau', 'tauf')):
+            value = getattr(self, attr + 'S', None)
+            if value is not None:
+                self._up(S[key], value)
+        self._up(S["lam"], self.lambdaS)
         self._set_scalars(eng, {S_TAU: float(getattr(self, 'exptau', 1.0)), S_LOGTAU: float(getattr(self, 'explogtau', 0.0)),
                                 S_BETA_S: float(getattr(self, 'beta_s', 1.0))})
         return eng
@@ -562,7 +568,7 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
         return eng.scalars.cpu().numpy()
 
     def elbo(self):
-        return float(self._refreshed_scalars(False)[S_ELBO])
+        return float(self._refreshed_scalars(False)[S_ELBO]) + _elbo_alpha_s_correction(self)
 
     def exp_square_diff(self):
         return float(self._refreshed_scalars(False)[S_ESD])
