@@ -3,12 +3,22 @@
 (BASELINE.json config 4).  One JSON line on stdout; see DESIGN.md section "Measurement".
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows I --cols J --K K]
+                    [--workload sweep|cv|small]
 
 A "step" is one Gibbs sweep plus one VB sweep (all U columns, all V columns, tau, train metrics each);
 value = sweeps per second over both.  N>1 (torchrun): rows of R / R^T are sharded across ranks
 (bnmtf_b200/parallel.py) -- strong scaling of the same matrix.
+
+Besides the timing the line carries a PARITY block: the GPU classes and the CPU checker (the reference's own classes
+from baseline/_ref when that copy exists, else the oracle port) run the same 4096 x 2048, K=20 problem from the same
+seeded 'random' start, and the largest relative differences of factors, MSE, ELBO and tau are printed.  The CPU side
+of that run is also the cpu_baseline sample.
+
+--workload cv / small: the replica decomposition (independent fits, one per GPU) -- see bench_replicas.py.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -22,10 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HBM_FALLBACK_GBS = 6650.0
-# ncu dram bytes (read + write) per matrix entry of one k_rx_umma launch, by digit count (profiles/r01_ncu_summary_final.txt: 7, profiles/r01d_ncu_summary.txt: 6)
+# ncu dram bytes (read + write) per launch at the full 65536 x 32768 shape on one GPU, by digit count
+# (profiles/r01d_ncu_summary.txt, re-measured in profiles/r02_ncu_summary.txt); scaled by 1/world for a shard
 RX_TRAFFIC_PER_ENTRY = {7: 15.15e9 / 2.0 ** 31, 6: 12.98e9 / 2.0 ** 31}
-GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9, 6: 1.29e9}       # mean of the two phases, at the full 65536 x 32768 shape on one GPU
+GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9, 6: 1.29e9}
+TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch at the full shape on one GPU (profiles/r01d_ncu_summary.txt), not re-measured in this run"
 FP64_PEAK_TFLOPS = 37.1   # measured here: tools/microbench/fp64_pipes.cu -> profiles/r01_microbench_fp64_pipes.txt
+DTYPE = "f64 (statistics: 48-bit fixed point, exact int8 tcgen05 accumulation; solver, moments, draws: IEEE fp64)"
+PRIORS = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+PARITY_SHAPE = (4096, 2048)
+PARITY_TOL = 1e-9
 
 
 def measured_peaks():
@@ -132,12 +149,13 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
         mean_ach = sum(ach.values()) / len(ach)
         peak = 2.0 * bf16
         out.update({"bound": "tensor", "kernel": "k_gram_umma (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed)",
-                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak, "traffic": (GRAM_TRAFFIC_PER_LAUNCH.get(digits) / world if GRAM_TRAFFIC_PER_LAUNCH.get(digits) else None),
+                    "achieved": mean_ach, "peak": peak, "unit": "TFLOP/s", "frac": mean_ach / peak,
+                    "traffic": (GRAM_TRAFFIC_PER_LAUNCH.get(digits) / world if GRAM_TRAFFIC_PER_LAUNCH.get(digits) else None),
                     "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s): the int8 tensor rate of B200 is "
                                    "twice the bf16 rate; ops are int8 multiply-adds x 2; the kernel is timed inside the "
                                    "power-capped sweep loop" % bf16_kind,
                     "frac_of_burst_peak": mean_ach / (2.0 * bf16_burst),
-                    "traffic_source": "ncu dram__bytes_read+write per launch at the full shape on one GPU, profiles/r01d_ncu_summary.txt",
+                    "traffic_source": TRAFFIC_SOURCE,
                     "per_mode_achieved_tops": ach})
     else:
         miss = N - n_obs
@@ -149,75 +167,314 @@ def build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world=1):
                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": mean_ach / FP64_PEAK_TFLOPS, "traffic": None,
                     "peak_source": "fp64 DMMA peak measured by tools/microbench/fp64_pipes.cu"})
     # the HBM-bound kernel: streams R once per phase (`digits` digit-plane bytes per entry for the tcgen05 kernel,
-    # 8 + 1/8 bytes for the fp64 kernel)
+    # 8 + 1/8 bytes for the fp64 kernel).  Two durations: alone on all SMs, and inside the sweep, where it runs on
+    # `split` SMs beside the Gram kernel
     bpe = float(digits) if e0.rx == "umma" else 8.125
     rx_ms = sum(prof[k]["stats_rx"] for k in engs) / len(engs)
+    rx_in = sum(prof[k].get("stats_rx_in_sweep", 0.0) for k in engs) / len(engs)
     rx_gbs = N * bpe / (rx_ms * 1e-3) / 1e9
-    out["hbm_kernel"] = {"bound": "hbm", "kernel": "k_rx_umma (tcgen05 digit planes)" if e0.rx == "umma" else "k_stats_rx (fp64 DMMA)",
-                         "achieved": rx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rx_gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)",
-                         "traffic": RX_TRAFFIC_PER_ENTRY.get(digits, 0) * N if (e0.rx == "umma" and digits in RX_TRAFFIC_PER_ENTRY) else None,
-                         "traffic_source": "ncu dram__bytes_read+write per launch / entries, profiles/r01d_ncu_summary.txt"}
+    hk = {"bound": "hbm", "kernel": "k_rx_umma (tcgen05 digit planes)" if e0.rx == "umma" else "k_stats_rx (fp64 DMMA)",
+          "achieved": rx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rx_gbs / hbm_peak,
+          "duration": "timed alone on all SMs",
+          "algorithmic_bytes_per_launch": N * bpe, "peak_kind": hbm_kind + " (copy bandwidth)",
+          "traffic": RX_TRAFFIC_PER_ENTRY.get(digits, 0) * N if (e0.rx == "umma" and digits in RX_TRAFFIC_PER_ENTRY) else None,
+          "traffic_source": TRAFFIC_SOURCE}
+    if rx_in > 0:
+        hk["in_sweep"] = {"ms": rx_in, "achieved": N * bpe / (rx_in * 1e-3) / 1e9,
+                          "frac": N * bpe / (rx_in * 1e-3) / 1e9 / hbm_peak,
+                          "note": "same kernel inside the sweep: %d SMs, the Gram kernel on the others" % e0.split}
+    out["hbm_kernel"] = hk
     return out
 
 
-def cpu_baseline(K, seed=0, budget_s=8.0, sizes=((1024, 512), (2048, 1024), (4096, 2048))):
-    """Time the CPU oracle (numpy restatement of the reference's sweep, same per-column full-GEMM cost structure) on
-    bounded samples of the same synthetic workload and extrapolate linearly in I*J to the full shape.  A size is
-    started while less than budget_s seconds have been used: the last one (4096 x 2048, ~10-20 s for the two sweeps
-    on 8-16 cores) brings the sample to the 10-30 s the bench contract asks for."""
-    from oracle import bnmtf_oracle as orc
+# ------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own classes (baseline/_ref, made by __graft_entry__.build() from /root/reference with
+# oracle/ref_shim.py) or, when that copy is absent, the oracle port.  Test/measurement infrastructure only.
+# ------------------------------------------------------------------------------------------------------
+def load_reference():
+    if not os.path.isdir(os.path.join(REF_DIR, "BNMTF", "code", "models")):
+        return None
+    try:
+        from oracle import ref_shim
+        return ref_shim.load(REF_DIR)
+    except Exception as exc:                                   # a broken copy must not take the benchmark down
+        sys.stderr.write("bench: baseline/_ref present but not importable (%s: %s); using the oracle port\n" % (type(exc).__name__, exc))
+        return None
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def sample_problem(I, J, K, seed=0):
+    rng = np.random.RandomState(seed)
+    U0, V0 = rng.exponential(1.0, size=(I, K)), rng.exponential(1.0, size=(J, K))
+    R = U0 @ V0.T + rng.normal(size=(I, J))
+    M = (rng.rand(I, J) >= 0.2).astype(float)
+    return R, M
+
+
+def blas_threads():
     try:
         import threadpoolctl
-        cores = max(i.get("num_threads", 1) for i in threadpoolctl.threadpool_info()) if threadpoolctl.threadpool_info() else 1
+        info = threadpoolctl.threadpool_info()
+        return max(i.get("num_threads", 1) for i in info) if info else 1
     except Exception:
-        cores = os.cpu_count() or 1
-    per_elem = {}
-    used = 0.0
-    desc = []
-    for (I, J) in sizes:
-        if used > budget_s:
-            break
-        rng = np.random.RandomState(seed)
-        U0, V0 = rng.exponential(1.0, size=(I, K)), rng.exponential(1.0, size=(J, K))
-        R = U0 @ V0.T + rng.normal(size=(I, J))
-        M = (rng.rand(I, J) >= 0.2).astype(float)
-        pri = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
-        for mode in ("gibbs", "vb"):
-            o = orc.OracleBNMF(R, M, K, pri, mode=mode, seed=seed)
-            if mode == "vb":
-                o.init_vb(1.0 / o.lambdaU, 1.0 / o.lambdaV)
-            else:
-                o.set_state(1.0 / o.lambdaU, 1.0 / o.lambdaV)
-            t0 = time.time()
-            o.sweep()
-            dt = time.time() - t0
-            used += dt
-            per_elem[(mode, I * J)] = dt / (I * J)
-        desc.append("%dx%d" % (I, J))
-    return per_elem, cores, desc, used
+        return os.cpu_count() or 1
 
 
+class CpuTimer:
+    """Wall and process-CPU seconds of a region: cpu/wall = the number of cores the region really kept busy."""
+
+    def __init__(self):
+        self.wall = self.cpu = 0.0
+
+    def __enter__(self):
+        self._w, self._c = time.time(), time.process_time()
+        return self
+
+    def __exit__(self, *a):
+        self.wall += time.time() - self._w
+        self.cpu += time.process_time() - self._c
+
+
+class CpuModels:
+    """The three BNMF models of the CPU side behind one interface (reference classes or oracle port)."""
+
+    def __init__(self, R, M, K, ref):
+        self.R, self.M, self.K, self.ref = R, M, K, ref
+        self.kind = "reference" if ref is not None else "port"
+
+    # Each start_* seeds numpy exactly like gpu_parity_run() does before the GPU class's initialise('random').
+    def start_vb(self, seed):
+        np.random.seed(seed)
+        if self.ref is not None:
+            m = self.ref.bnmf_vb_optimised(self.R, self.M, self.K, PRIORS)
+            with quiet():
+                m.initialise("random")
+            return m
+        from oracle import bnmtf_oracle as orc
+        o = orc.OracleBNMF(self.R, self.M, self.K, PRIORS, mode="vb")
+        muU = np.random.exponential(scale=1.0 / o.lambdaU)
+        muV = np.random.exponential(scale=1.0 / o.lambdaV)
+        o.init_vb(muU, muV)
+        return o
+
+    def sweep_vb(self, m):
+        if self.ref is not None:
+            with quiet():
+                m.run(1)
+            return {"MSE": m.all_performances["MSE"][-1]}
+        return m.sweep()
+
+    def state_vb(self, m):
+        if self.ref is not None:
+            return {"expU": m.expU, "expV": m.expV, "varU": m.varU, "varV": m.varV, "exptau": m.exptau, "elbo": m.elbo()}
+        return {"expU": m.U, "expV": m.V, "varU": m.varU, "varV": m.varV, "exptau": m.exptau, "elbo": m.elbo()}
+
+    def start_point(self, seed, mode):
+        """Gibbs / ICM model at a seeded 'random' start."""
+        np.random.seed(seed)
+        if self.ref is not None:
+            m = (self.ref.bnmf_gibbs_optimised if mode == "gibbs" else self.ref.nmf_icm)(self.R, self.M, self.K, PRIORS)
+            with quiet():
+                m.initialise("random")
+            return m
+        from oracle import bnmtf_oracle as orc
+        o = orc.OracleBNMF(self.R, self.M, self.K, PRIORS, mode=mode)
+        U = np.random.exponential(scale=1.0 / o.lambdaU)
+        V = np.random.exponential(scale=1.0 / o.lambdaV)
+        o.set_state(U, V)
+        return o
+
+    def conditionals(self, m, k):
+        if self.ref is not None:
+            tU = np.asarray(m.tauU(k), dtype=float)
+            tV = np.asarray(m.tauV(k), dtype=float)
+            return {"tauU": tU, "muU": np.asarray(m.muU(tU, k), dtype=float), "tauV": tV, "muV": np.asarray(m.muV(tV, k), dtype=float)}
+        tU, mU = m.column_params(k, "U")
+        tV, mV = m.column_params(k, "V")
+        return {"tauU": tU, "muU": mU, "tauV": tV, "muV": mV}
+
+    def sweep_point(self, m, mode):
+        if self.ref is not None:
+            with quiet():
+                m.run(1) if mode == "gibbs" else m.run(1, minimum_TN=0.0)
+            return {"MSE": m.all_performances["MSE"][-1]}
+        return m.sweep()
+
+
+def cpu_side(K, shape=PARITY_SHAPE, vb_sweeps=2, icm_sweeps=2, want_parity=True):
+    """Run the CPU checker on the parity problem; its timed VB and Gibbs sweeps are the cpu_baseline sample."""
+    I, J = shape
+    R, M = sample_problem(I, J, K)
+    cpu = CpuModels(R, M, K, load_reference())
+    res = {"kind": cpu.kind, "shape": shape}
+    t_vb, t_g = CpuTimer(), CpuTimer()
+    m = cpu.start_vb(11)
+    res["vb"] = []
+    for _ in range(vb_sweeps if want_parity else 1):
+        with t_vb:
+            perf = cpu.sweep_vb(m)
+        st = cpu.state_vb(m)
+        st = {k: (np.array(v, dtype=float).copy() if isinstance(v, np.ndarray) else float(v)) for k, v in st.items()}
+        st["MSE"] = float(perf["MSE"])
+        res["vb"].append(st)
+    res["vb_sweeps_timed"] = len(res["vb"])
+    g = cpu.start_point(12, "gibbs")
+    if want_parity:
+        res["gibbs_cond"] = cpu.conditionals(g, K // 2)
+    with t_g:
+        cpu.sweep_point(g, "gibbs")
+    if want_parity:
+        c = cpu.start_point(13, "icm")
+        res["icm"] = []
+        for _ in range(icm_sweeps):
+            perf = cpu.sweep_point(c, "icm")
+            res["icm"].append({"U": np.array(c.U, dtype=float).copy(), "V": np.array(c.V, dtype=float).copy(),
+                               "tau": float(c.tau), "MSE": float(perf["MSE"])})
+    res["s_vb"], res["s_gibbs"] = t_vb.wall / res["vb_sweeps_timed"], t_g.wall
+    res["cores_busy"] = (t_vb.cpu + t_g.cpu) / max(1e-9, t_vb.wall + t_g.wall)
+    res["cpu_seconds"] = t_vb.wall + t_g.wall
+    return res
+
+
+def gpu_parity_run(K, distributed, shape=PARITY_SHAPE, vb_sweeps=2, icm_sweeps=2):
+    """The GPU classes on the parity problem from the same seeded 'random' starts (every rank when sharded)."""
+    import bnmtf_b200
+    I, J = shape
+    R, M = sample_problem(I, J, K)
+    kw = {"distributed": True} if distributed else {}
+    out = {"vb": [], "icm": []}
+    np.random.seed(11)
+    m = bnmtf_b200.bnmf_vb_optimised(R, M, K, PRIORS, seed=5, **kw)
+    m.initialise("random")
+    for _ in range(vb_sweeps):
+        m.run(1)
+        out["vb"].append({"expU": m.expU.copy(), "expV": m.expV.copy(), "varU": m.varU.copy(), "varV": m.varV.copy(),
+                          "exptau": float(m.exptau), "elbo": float(m.all_elbo[-1]), "MSE": float(m.all_performances["MSE"][-1])})
+    np.random.seed(12)
+    g = bnmtf_b200.bnmf_gibbs_optimised(R, M, K, PRIORS, seed=6, **kw)
+    g.initialise("random")
+    k = K // 2
+    tU, tV = g.tauU(k), g.tauV(k)
+    out["gibbs_cond"] = {"tauU": tU, "muU": g.muU(tU, k), "tauV": tV, "muV": g.muV(tV, k)}
+    np.random.seed(13)
+    c = bnmtf_b200.nmf_icm(R, M, K, PRIORS, seed=7, **kw)
+    c.initialise("random")
+    for _ in range(icm_sweeps):
+        c.run(1, minimum_TN=0.0)
+        out["icm"].append({"U": c.U.copy(), "V": c.V.copy(), "tau": float(c.tau), "MSE": float(c.all_performances["MSE"][-1])})
+    del m, g, c
+    return out
+
+
+def rel_err(a, b):
+    """max |a - b| / (|b| + 0.01 max|b|): relative, with entries near zero measured against 1 % of the largest."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = float(np.abs(b).max()) if b.size else 0.0
+    if scale == 0.0:
+        return float(np.abs(a - b).max()) if a.size else 0.0
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 0.01 * scale)))
+
+
+def parity_block(gpu, cpu, K, world):
+    I, J = cpu["shape"]
+    blk = {"problem": "%dx%d, K=%d, 20%% missing, seeded 'random' starts; same kernels as the headline run "
+                      "(tcgen05 Gram + R.X, SM split, CUDA graph%s)" % (I, J, K, ", %d-way sharded" % world if world > 1 else ""),
+           "checker": "reference classes (baseline/_ref)" if cpu["kind"] == "reference" else "oracle port (oracle/bnmtf_oracle.py)",
+           "measure": "max |gpu - cpu| / (|cpu| + 0.01 max|cpu|)", "tolerance": PARITY_TOL}
+    worst = 0.0
+    vb = {"sweeps": len(cpu["vb"]), "max_rel_factors": 0.0, "max_rel_variances": 0.0, "max_rel_mse": 0.0, "max_rel_elbo": 0.0,
+          "max_rel_exptau": 0.0}
+    for a, b in zip(gpu["vb"], cpu["vb"]):
+        vb["max_rel_factors"] = max(vb["max_rel_factors"], rel_err(a["expU"], b["expU"]), rel_err(a["expV"], b["expV"]))
+        vb["max_rel_variances"] = max(vb["max_rel_variances"], rel_err(a["varU"], b["varU"]), rel_err(a["varV"], b["varV"]))
+        vb["max_rel_mse"] = max(vb["max_rel_mse"], abs(a["MSE"] / b["MSE"] - 1.0))
+        vb["max_rel_elbo"] = max(vb["max_rel_elbo"], abs(a["elbo"] / b["elbo"] - 1.0))
+        vb["max_rel_exptau"] = max(vb["max_rel_exptau"], abs(a["exptau"] / b["exptau"] - 1.0))
+    blk["vb"] = vb
+    worst = max(worst, *[v for k, v in vb.items() if k.startswith("max_")])
+    icm = {"sweeps": len(cpu["icm"]), "max_rel_factors": 0.0, "max_rel_mse": 0.0, "max_rel_tau": 0.0}
+    for a, b in zip(gpu["icm"], cpu["icm"]):
+        icm["max_rel_factors"] = max(icm["max_rel_factors"], rel_err(a["U"], b["U"]), rel_err(a["V"], b["V"]))
+        icm["max_rel_mse"] = max(icm["max_rel_mse"], abs(a["MSE"] / b["MSE"] - 1.0))
+        icm["max_rel_tau"] = max(icm["max_rel_tau"], abs(a["tau"] / b["tau"] - 1.0))
+    blk["icm"] = icm
+    worst = max(worst, *[v for k, v in icm.items() if k.startswith("max_")])
+    gc = {"column": K // 2}
+    for name in ("tauU", "muU", "tauV", "muV"):
+        gc["max_rel_" + name] = rel_err(gpu["gibbs_cond"][name], cpu["gibbs_cond"][name])
+        worst = max(worst, gc["max_rel_" + name])
+    blk["gibbs_conditionals"] = gc
+    blk["worst"] = worst
+    blk["pass"] = bool(worst <= PARITY_TOL)
+    return blk
+
+
+# ------------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """--impl reference: the reference's own classes (baseline/_ref; the oracle port if that copy is missing) on the
+    host cores.  A step = one Gibbs + one VB sweep, as in our arm, on a bounded sample of the workload: the largest
+    rung of 512x256 ... 4096x2048 for which warmup + steps fit about 150 s; value = sweeps/s at the full shape by linear
+    extrapolation in I*J (the reference needs ~6 dense I x J temporaries per column update: the full shape does not
+    fit host RAM and would take ~45 minutes per sweep)."""
     I, J, K = args.rows, args.cols, args.K
-    t0 = time.time()
-    per_elem, cores, desc, used = cpu_baseline(K)
-    biggest = max(n for (_, n) in per_elem)
-    s_gibbs, s_vb = per_elem[("gibbs", biggest)] * I * J, per_elem[("vb", biggest)] * I * J
-    value = 2.0 / (s_gibbs + s_vb)
+    t_start = time.time()
+    ref = load_reference()
+    n_steps = args.warmup + args.steps
+    per_entry_step = 2.8e-6                                    # s per matrix entry per (Gibbs + VB) step, K=20, measured here
+    rung = (256, 128)
+    for cand in ((512, 256), (1024, 512), (2048, 1024), (4096, 2048)):
+        if cand[0] * cand[1] * per_entry_step * (K / 20.0) * n_steps <= 150.0:
+            rung = cand
+    Is, Js = min(rung[0], I), min(rung[1], J)
+    R, M = sample_problem(Is, Js, K)
+    cpu = CpuModels(R, M, K, ref)
+    vb = cpu.start_vb(11)
+    gb = cpu.start_point(12, "gibbs")
+    for _ in range(args.warmup):
+        cpu.sweep_point(gb, "gibbs"), cpu.sweep_vb(vb)
+    tm = CpuTimer()
+    with tm:
+        for _ in range(args.steps):
+            cpu.sweep_point(gb, "gibbs"), cpu.sweep_vb(vb)
+    step_s = tm.wall / max(1, args.steps)
+    scale = (float(I) * J) / (float(Is) * Js)
+    value = 2.0 / (step_s * scale)
+    cores_busy = tm.cpu / max(1e-9, tm.wall)
+    sample = ("%d steps of one Gibbs + one VB sweep of the %s at %dx%d, K=%d (%.1f s); sweeps/s at %dx%d by linear extrapolation "
+              "in I*J" % (args.steps, "reference's bnmf_gibbs_optimised / bnmf_vb_optimised (baseline/_ref)" if ref is not None
+                          else "oracle port", Is, Js, K, tm.wall, I, J))
     line = {"impl": "reference", "metric": "BNMF Gibbs+VB sweeps/sec at %dx%d K=%d" % (I, J, K), "value": value,
             "unit": "sweeps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BNMF Gibbs+VB sweep, %dx%d fp64, 20%% missing, K=%d" % (I, J, K),
-                       "note": "oracle port of the reference's numpy sweep; the full shape does not fit host RAM, "
-                               "value is the linear extrapolation in I*J from the largest sample"},
-            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port",
-                             "sample": "one Gibbs + one VB sweep at " + ", ".join(desc) + "; extrapolated linearly in I*J",
-                             "seconds_per_sweep_extrapolated": {"gibbs": s_gibbs, "vb": s_vb}},
+                       "sample_shape": [Is, Js], "extrapolation_factor": scale,
+                       "note": "ms_per_step is the measured time of one step on the sample; value is extrapolated to the full "
+                               "shape, which does not fit host RAM in the reference's formulation"},
+            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": max(1, int(round(cores_busy))), "kind": cpu.kind,
+                             "sample": sample, "cores_busy_measured": cores_busy, "blas_threads": blas_threads(),
+                             "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.time() - t0}
+            "wall_s": time.time() - t_start}
     print(json.dumps(line))
+
+
+def checksum(models, engs):
+    """State after a fixed number of sweeps from the same seeded start: identical for every sharding of the same
+    problem (Gibbs: bit for bit, the Philox counters are keyed by global row; VB: to rounding)."""
+    import torch
+    from bnmtf_b200 import engine
+    out = {}
+    for k, e in engs.items():
+        sc = e.scalars.cpu().numpy()
+        out[k] = {"sweeps": int(e.sweeps_done), "sum_U": float(e.U.fac[:e.U.n].sum().item()),
+                  "sum_V": float(e.V.fac[:e.V.n].sum().item()), "sum_U2": float((e.U.fac[:e.U.n] ** 2).sum().item()),
+                  "tau": float(sc[engine.S_TAU]), "train_MSE": float(sc[engine.S_MSE])}
+    torch.cuda.synchronize()
+    return out
 
 
 def main():
@@ -226,14 +483,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "cv", "small"])
     ap.add_argument("--rows", type=int, default=65536)
     ap.add_argument("--cols", type=int, default=32768)
     ap.add_argument("--K", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sustained-s", type=float, default=2.5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload != "sweep":
+        import bench_replicas
+        return bench_replicas.main(args, rank, world)
     if args.impl == "reference":
         if rank == 0:
             run_reference(args)
@@ -245,19 +508,29 @@ def main():
     device = torch.device("cuda", local_rank)
     from bnmtf_b200 import _lib, bnmf, engine
     I, J, K = args.rows, args.cols, args.K
-    pri = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
-
+    dist = None
     if world > 1:
+        import torch.distributed as dist
         from bnmtf_b200 import parallel
-        return parallel.bench_sharded(args, rank, world, device, ClockSampler, measured_peaks, build_roofline)
-
-    R, bits, n_obs = make_synthetic(I, J, K, device)
-    ds = engine.Dataset.from_device(R, bits, I, J, n_obs=n_obs)
+        parallel.init_process_group("nccl")
+        R, bits, RT, bitsT, n_obs = parallel.make_synthetic_shards(I, J, K, device, rank, world)
+        ds = engine.Dataset.from_device(R, bits, I, J, RT, bitsT, n_obs=n_obs, world=world, rank=rank)
+    else:
+        R, bits, n_obs = make_synthetic(I, J, K, device)
+        ds = engine.Dataset.from_device(R, bits, I, J, n_obs=n_obs)
     torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # seeded 'random' start (numpy seeds 1, 2: the same host draws on every rank and for every world size)
     models = {}
-    for mode, cls in (("gibbs", bnmf.bnmf_gibbs_optimised), ("vb", bnmf.bnmf_vb_optimised)):
-        m = cls.from_dataset(ds, K, pri, seed=1)
-        m.initialise("exp")
+    for i, (mode, cls) in enumerate((("gibbs", bnmf.bnmf_gibbs_optimised), ("vb", bnmf.bnmf_vb_optimised))):
+        m = cls.from_dataset(ds, K, PRIORS, seed=1)
+        np.random.seed(1 + i)
+        m.initialise("random")
         models[mode] = m
     engs = {k: m._engine() for k, m in models.items()}
     for m in models.values():
@@ -268,7 +541,7 @@ def main():
     for _ in range(args.warmup):
         for e in engs.values():
             e.sweep()
-    torch.cuda.synchronize()
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in engs}
@@ -282,15 +555,39 @@ def main():
             e.sweep()
         ev[k][1].record()
     t_all1.record()
-    torch.cuda.synchronize()
+    barrier()
     launches = _lib.launch_count[0] - launches0
-    ms = {k: ev[k][0].elapsed_time(ev[k][1]) for k in engs}
-    total_ms = t_all0.elapsed_time(t_all1)
+    times = torch.tensor([t_all0.elapsed_time(t_all1)] + [ev[k][0].elapsed_time(ev[k][1]) for k in ("gibbs", "vb")],
+                         dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, g_ms, v_ms = (float(x) for x in times.cpu())
     value = 2.0 * args.steps / (total_ms / 1e3)
-    mse = {k: float(e.scalars.cpu()[engine.S_MSE]) for k, e in engs.items()}
+    state = checksum(models, engs)                     # after exactly warmup + steps sweeps, for every N
+
+    # ---- sustained figure: the same loop for >= sustained_s seconds (the board settles at its power cap) ----------
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = max(args.steps, int(args.sustained_s / max(1e-4, total_ms / 1e3 / (2.0 * args.steps)) / 2.0) + 1)
+        for e in engs.values():
+            e.alloc_trace(n_sus + 8)
+        for e in engs.values():
+            e.sweep()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for e in engs.values():
+            for _ in range(n_sus):
+                e.sweep()
+        s1.record()
+        barrier()
+        st = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        sustained = {"sweeps_per_s": 2.0 * n_sus / (float(st.item()) / 1e3), "seconds": float(st.item()) / 1e3, "sweeps": 2 * n_sus}
 
     # ---- per-kernel timings for the roofline block -----------------------------------------------------------
-    prof = {k: e.profile_sweep(reps=2) for k, e in engs.items()}
+    prof = {k: e.profile_sweep(reps=2 if world == 1 else 1) for k, e in engs.items()}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -299,41 +596,85 @@ def main():
     if not args.no_e2e:
         for m in models.values():
             m.run(1)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.time()
         for m in models.values():
             for _ in range(args.steps):
                 m.run(1)
-        torch.cuda.synchronize()
-        dt = time.time() - t0
-        fU, fV = I * K * 8, J * K * 8
-        h2d = ((2 * (fU + fV)) + (5 * (fU + fV))) / 2.0        # gibbs: U,V,lambdaU,lambdaV; vb: exp,var,mu,tau,lambda
-        d2h = ((2 * (fU + fV)) + (4 * (fU + fV))) / 2.0        # gibbs: state + the kept sample; vb: exp,var,mu,tau
-        e2e = {"value": 2.0 * args.steps / dt, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h),
-               "note": "model.run(1) per step: factor state DMA'd from the model's page-locked host arrays, one sweep, state + "
-                       "trace read back into them; the priors come from pageable numpy; R itself (16 GiB) is resident like "
-                       "a dataset"}
+        barrier()
+        dt = torch.tensor([time.time() - t0], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = sum(m._xfer_bytes()[0] for m in models.values()) / 2.0
+        d2h = sum(m._xfer_bytes()[1] for m in models.values()) / 2.0
+        e2e = {"value": 2.0 * args.steps / float(dt.item()), "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d * world),
+               "d2h_bytes_per_step": int(d2h * world),
+               "note": "model.run(1) per step through the class API: factor state DMA'd from the model's page-locked host "
+                       "arrays, one sweep, state + trace read back into them; bytes are summed over ranks (each rank moves "
+                       "only its own rows of the factor state; the fused peer exchange replicates them); R itself "
+                       "(16 GiB) is resident like a dataset"}
+
+    # ---- parity at the benchmark's kernel configuration (every rank runs the GPU side; rank 0 the CPU side) ------
+    gpu_par = None
+    if not args.no_parity:
+        for m in models.values():
+            m._eng = None
+        del models, engs, ds, R, bits
+        if world > 1:
+            del RT, bitsT
+        torch.cuda.empty_cache()
+        gpu_par = gpu_parity_run(K, distributed=world > 1)
+    if dist is not None:
+        barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
 
     # ---- roofline ------------------------------------------------------------------------------------------------
-    roofline = build_roofline(engs, prof, I, J, K, n_obs, total_ms / 1e3 / (2.0 * args.steps))
     N = float(I) * J
+    sweep_s = total_ms / 1e3 / (2.0 * args.steps)
+    roofline = build_roofline_from(prof, I, J, K, n_obs, sweep_s, world)
+    par_txt = ("rows of R and of R^T sharded over %d ranks; each updated factor row is stored into every peer's copy by the "
+               "solver kernel itself (NVLink P2P stores into symmetric memory, one cross-GPU barrier per phase); one "
+               "24-double all-reduce per sweep (NCCL)" % world) if world > 1 else "single GPU"
     line = {"metric": "BNMF Gibbs+VB sweeps/sec at %dx%d K=%d" % (I, J, K), "value": value, "unit": "sweeps/s",
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / (2.0 * args.steps),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / (2.0 * args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": "BNMF Gibbs+VB sweep, %dx%d fp64, 20%% missing, K=%d" % (I, J, K),
-                       "l2": "inputs (2 x %.1f GiB) far larger than L2" % (N * 8 / 2 ** 30),
-                       "gibbs_sweeps_per_s": args.steps / (ms["gibbs"] / 1e3), "vb_sweeps_per_s": args.steps / (ms["vb"] / 1e3),
-                       "train_mse_after": mse, "observed_fraction": n_obs / N},
+                       "parallelism": par_txt, "init": "seeded 'random' start (numpy seeds 1, 2)",
+                       "l2": "inputs (2 x %.1f GiB of digit planes per sweep) far larger than L2" % (N * 6 / 2 ** 30),
+                       "gibbs_sweeps_per_s": args.steps / (g_ms / 1e3), "vb_sweeps_per_s": args.steps / (v_ms / 1e3),
+                       "sustained": sustained, "state_after_timed_region": state, "observed_fraction": n_obs / N},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
-    if not args.no_cpu_baseline:
-        per_elem, cores, desc, used = cpu_baseline(K)
-        biggest = max(n for (_, n) in per_elem)
-        s_g, s_v = per_elem[("gibbs", biggest)] * N, per_elem[("vb", biggest)] * N
-        line["cpu_baseline"] = {"value": 2.0 / (s_g + s_v), "unit": "sweeps/s", "cores": cores, "kind": "port",
-                                "sample": "one Gibbs + one VB sweep of the oracle at " + ", ".join(desc) +
-                                          " (%.1f s of CPU); extrapolated linearly in I*J -- the full shape needs >62 GB" % used}
+    if not (args.no_cpu_baseline and args.no_parity):
+        cpu = cpu_side(K, want_parity=not args.no_parity)
+        s_g, s_v = cpu["s_gibbs"] * N / (PARITY_SHAPE[0] * PARITY_SHAPE[1]), cpu["s_vb"] * N / (PARITY_SHAPE[0] * PARITY_SHAPE[1])
+        line["cpu_baseline"] = {"value": 2.0 / (s_g + s_v), "unit": "sweeps/s", "cores": max(1, int(round(cpu["cores_busy"]))),
+                                "kind": cpu["kind"],
+                                "sample": "%d VB + 1 Gibbs sweep of the %s at %dx%d, K=%d (%.1f s of CPU work); sweeps/s at the "
+                                          "full shape by linear extrapolation in I*J -- the full shape needs >62 GB in the "
+                                          "reference's formulation" % (cpu["vb_sweeps_timed"],
+                                                                      "reference's own classes (baseline/_ref)" if cpu["kind"] == "reference" else "oracle port",
+                                                                      PARITY_SHAPE[0], PARITY_SHAPE[1], K, cpu["cpu_seconds"]),
+                                "cores_busy_measured": cpu["cores_busy"], "blas_threads": blas_threads(), "host_cores": os.cpu_count(),
+                                "seconds_per_sweep_sample": {"gibbs": cpu["s_gibbs"], "vb": cpu["s_vb"]}}
+        if gpu_par is not None:
+            line["parity"] = parity_block(gpu_par, cpu, K, world)
     print(json.dumps(line))
+
+
+def build_roofline_from(prof, I, J, K, n_obs, sweep_s, world):
+    """build_roofline() needs only a few engine attributes: carried in prof['_meta'] so that the engines themselves can
+    be freed before the parity run."""
+    class E:
+        pass
+    engs = {}
+    for k, p in prof.items():
+        e = E()
+        e.gram, e.rx, e.vb, e.metrics_mode, e.split = p["_meta"]["gram"], p["_meta"]["rx"], k == "vb", p["_meta"]["metrics_mode"], p["_meta"]["split"]
+        engs[k] = e
+    prof = {k: {n: v for n, v in p.items() if n != "_meta"} for k, p in prof.items()}
+    return build_roofline(engs, prof, I, J, K, n_obs, sweep_s, world)
 
 
 if __name__ == "__main__":

@@ -31,6 +31,27 @@ def _elbo_alpha_s_correction(model):
     return f(a) - f(a0)
 
 
+# bytes moved host->device / device->host by the model classes of this process (bench.py's e2e block reports what one
+# run(1) really copied, counted where the copies are issued)
+XFER = [0, 0]
+
+
+
+def _shared_seed(seed, distributed):
+    """Philox seed of a model: the caller's, else one derived from numpy's global state (_lib.derive_seed: distinct for
+    successive models, reproducible after numpy.random.seed).  Sharded runs: rank 0's value is broadcast, so that the
+    replicated tau draw and the row-keyed factor draws are the same stream on every rank whatever each rank's numpy
+    state is."""
+    seed = int(seed) if seed is not None else _lib.derive_seed()
+    if distributed:
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            box = [seed]
+            dist.broadcast_object_list(box, src=0)
+            seed = int(box[0])
+    return seed
+
+
 METRICS = ['MSE', 'R^2', 'Rp']
 QUALITY = ['loglikelihood', 'BIC', 'AIC', 'MSE', 'ELBO']
 
@@ -94,7 +115,8 @@ class _TwoFactorBase(object):
             self.lambdaV = self.lambdaV * np.ones((self.J, self.K))
         self._device_arg, self._seed, self.verbose = dataset.device, seed, False
         self._distributed = dataset.world > 1
-        self._eng = BNMFEngine(dataset, K, cls._mode, self.alpha, self.beta, seed=0 if seed is None else seed)
+        self._eng = BNMFEngine(dataset, K, cls._mode, self.alpha, self.beta,
+                               seed=_shared_seed(seed, dataset.world > 1))
         return self
 
     def check_empty_rows_columns(self):
@@ -114,19 +136,30 @@ class _TwoFactorBase(object):
                 import torch.distributed as dist
                 world, rank = dist.get_world_size(), dist.get_rank()
             ds = Dataset.from_host(self.R, self.M, dev, world, rank)
-            # every rank must use the same Philox seed: draw it from numpy's (seeded) stream or pass seed=
-            seed = self._seed if self._seed is not None else _lib.derive_seed()
-            self._eng = BNMFEngine(ds, self.K, self._mode, self.alpha, self.beta, seed=seed)
+            self._eng = BNMFEngine(ds, self.K, self._mode, self.alpha, self.beta,
+                                   seed=_shared_seed(self._seed, self._distributed))
         return self._eng
 
     @staticmethod
     def _up(dst, src):
         src = np.ascontiguousarray(src, dtype=np.float64)
+        XFER[0] += src.nbytes
         dst[:src.shape[0]].copy_(torch.from_numpy(src), non_blocking=False)
 
     @staticmethod
     def _down(src, n=None):
-        return (src if n is None else src[:n]).detach().cpu().numpy().copy()
+        t = (src if n is None else src[:n]).detach()
+        XFER[1] += t.numel() * t.element_size()
+        return t.cpu().numpy().copy()
+
+    def _xfer_bytes(self):
+        """(host->device, device->host) bytes of the last run() of this model."""
+        return getattr(self, '_last_xfer', (0, 0))
+
+    def _xfer_mark(self, start=None):
+        if start is None:
+            return (XFER[0], XFER[1])
+        self._last_xfer = (XFER[0] - start[0], XFER[1] - start[1])
 
     # Factor state crosses PCIe through persistent page-locked buffers.  After run() the state attributes (U, expU, ...)
     # ARE numpy views of those buffers, rewritten in place by the next run() -- the same aliasing the reference has,
@@ -139,12 +172,14 @@ class _TwoFactorBase(object):
         if ent is None or tuple(ent[0].shape) != tuple(t.shape):
             buf = torch.empty(tuple(t.shape), dtype=torch.float64, pin_memory=True)
             ent = pins[key] = (buf, buf.numpy())
+        XFER[1] += t.numel() * t.element_size()
         ent[0].copy_(t, non_blocking=True)       # caller synchronises before handing the view out
         return ent[1]
 
     def _up_s(self, key, dst, src):
         ent = self.__dict__.get('_pins', {}).get(key)
         if ent is not None and src is ent[1]:
+            XFER[0] += src.nbytes
             dst[:src.shape[0]].copy_(ent[0], non_blocking=True)
         else:
             self._up(dst, src)
@@ -215,6 +250,7 @@ class _TwoFactorBase(object):
             marks.append(ev)
         torch.cuda.synchronize()
         self.all_times = [start.elapsed_time(ev) / 1e3 for ev in marks]
+        XFER[1] += eng.trace.numel() * 8
         tr = eng.trace.cpu().numpy()[:iterations]
         for i, metric in enumerate(METRICS):
             self.all_performances[metric] = [float(v) for v in tr[:, 1 + i]]
@@ -248,6 +284,7 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
         return eng
 
     def run(self, iterations):
+        x0 = self._xfer_mark()
         eng = self._push()
         dev = eng.ds.device
         all_U = torch.zeros((iterations, self.I, self.K), dtype=torch.float64, device=dev)
@@ -265,6 +302,7 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
         if self.verbose:
             for it in range(iterations):
                 print("Iteration %s. MSE: %s. R^2: %s. Rp: %s." % (it + 1, tr[it, 1], tr[it, 2], tr[it, 3]))
+        self._xfer_mark(x0)
         return (self.all_U, self.all_V, self.all_tau)
 
     # ---- conditional parameters (reference :161-177) -----------------------------------------------------
@@ -355,6 +393,7 @@ class nmf_icm(_TwoFactorBase):
                             bnmf_gibbs_optimised.tauV, bnmf_gibbs_optimised.muV)
 
     def run(self, iterations, minimum_TN=0.):
+        x0 = self._xfer_mark()
         eng = self._push()
         self._init_trace_lists()
         tr = self._run_loop(eng, iterations, minimum_TN=minimum_TN)
@@ -363,6 +402,7 @@ class nmf_icm(_TwoFactorBase):
         torch.cuda.current_stream().synchronize()
         if iterations > 0:
             self.tau = float(tr[-1, 0])
+        self._xfer_mark(x0)
         return
 
     def predict(self, M_pred):
@@ -430,6 +470,7 @@ class bnmf_vb_optimised(_TwoFactorBase):
         torch.cuda.current_stream().synchronize()
 
     def run(self, iterations):
+        x0 = self._xfer_mark()
         eng = self._push()
         self._init_trace_lists()
         tr = self._run_loop(eng, iterations)
@@ -444,6 +485,7 @@ class bnmf_vb_optimised(_TwoFactorBase):
         if self.verbose:
             for it in range(iterations):
                 print("Iteration %s. ELBO: %s. MSE: %s. R^2: %s. Rp: %s." % (it + 1, tr[it, 4], tr[it, 1], tr[it, 2], tr[it, 3]))
+        self._xfer_mark(x0)
         return
 
     # ---- white-box pieces (reference :163-215) ---------------------------------------------------------------

@@ -92,12 +92,15 @@ __global__ void k_nmtf_transform(TransformArgs a) {
 // S phase, reduction over rows.  Per CTA partial of  H (D x D), prec (D), rhs (D),  D = K*L, d = k*L + l.
 // ---------------------------------------------------------------------------------------------------
 
+// GMEM_ACC: the accumulators do not fit shared memory (K*L > ~150): each CTA accumulates straight into its own slice of
+// `partial` (every entry is only ever touched by the same thread, so no atomics and no extra synchronisation).
+template <bool GMEM_ACC>
 __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
   extern __shared__ double sm[];
   const int K = a.K, L = a.L, D = K * L;
   const int ntl = tiles_for(L), KPl = 8 * ntl, gll = ntl * (ntl + 1) / 2 * 64;
-  double* H = sm;                 // D*D + 2D accumulators
-  double* GG = H + D * D + 2 * D; // L*L
+  double* H = GMEM_ACC ? a.partial + (size_t)blockIdx.x * ((size_t)D * D + 2 * D) : sm;   // D*D + 2D accumulators
+  double* GG = GMEM_ACC ? sm : H + D * D + 2 * D; // L*L
   double* sv = GG + L * L;        // L
   double* rg = sv + L;            // L
   double* f = rg + L;             // K
@@ -135,7 +138,8 @@ __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < tot; i += 256) a.partial[(size_t)blockIdx.x * tot + i] = H[i];
+  if (!GMEM_ACC)
+    for (int i = threadIdx.x; i < tot; i += 256) a.partial[(size_t)blockIdx.x * tot + i] = H[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -268,10 +272,15 @@ __global__ void k_sum_partials2(const double* __restrict__ partial, int nparts, 
 }
 int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
   const int D = a.K * a.L;
-  const size_t smem = ((size_t)D * D + 2 * D + (size_t)a.L * a.L + 2 * a.L + 2 * a.K) * sizeof(double);
-  if (smem > 200 * 1024) { set_error("nmtf_sq: K*L = %d too large for the shared-memory accumulator", D); return -2; }
-  cudaFuncSetAttribute(k_nmtf_sq_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_nmtf_sq_partial<<<nparts, 256, smem, st>>>(a);
+  const size_t small = ((size_t)a.L * a.L + 2 * a.L + 2 * a.K) * sizeof(double);
+  const size_t smem = ((size_t)D * D + 2 * D) * sizeof(double) + small;
+  if (smem <= 200 * 1024) {
+    cudaFuncSetAttribute(k_nmtf_sq_partial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_nmtf_sq_partial<false><<<nparts, 256, smem, st>>>(a);
+  } else {
+    // the reference has no size limit (its grid searches go to K, L = 20..30): accumulate in global memory instead
+    k_nmtf_sq_partial<true><<<nparts, 256, small, st>>>(a);
+  }
   const int len = D * D + 2 * D;
   k_sum_partials2<<<(len + 127) / 128, 128, 0, st>>>(a.partial, nparts, len, out);
   return check_launch("nmtf_sq");

@@ -12,9 +12,10 @@ namespace bnmtf {
 // P[i][j] = sum_k A[i][k] * B[j][k]   (A: rows x K, B: cols x K, plain row-major), padding columns get 1
 __global__ void __launch_bounds__(256) k_np_build_pred(const double* __restrict__ A, const double* __restrict__ B, int rows,
                                                       int cols, int ld, int K, double* __restrict__ P) {
-  const int i = blockIdx.y;
+  // rows on grid.x (2^31 - 1 blocks), column blocks on grid.y: gridDim.y stops at 65535, and row counts do not
+  const int i = blockIdx.x;
   const double* a = A + (size_t)i * K;
-  for (int j = blockIdx.x * 256 + threadIdx.x; j < ld; j += gridDim.x * 256) {
+  for (int j = blockIdx.y * 256 + threadIdx.x; j < ld; j += gridDim.y * 256) {
     double s = 1.0;
     if (j < cols) {
       s = 0.0;
@@ -156,8 +157,8 @@ __global__ void k_small_matmul(const double* __restrict__ A, const double* __res
 
 // ---- launchers -------------------------------------------------------------------------------------------
 int launch_np_build_pred(const double* A, const double* B, int rows, int cols, int ld, int K, double* P, cudaStream_t st) {
-  dim3 grid((ld + 255) / 256, rows);
-  if (grid.x > 64) grid.x = 64;
+  dim3 grid(rows, (ld + 255) / 256);
+  if (grid.y > 64) grid.y = 64;
   k_np_build_pred<<<grid, 256, 0, st>>>(A, B, rows, cols, ld, K, P);
   return check_launch("np_build_pred");
 }

@@ -412,9 +412,11 @@ class BNMFEngine:
             return self.U, self.V, ds.R, ds.bits, cnt, ds.ldJ, lo
         return self.V, self.U, ds.RT, ds.bitsT, cnt, ds.ldI, lo
 
-    def stats(self, side, need_rx=True, sums=False):
+    def stats(self, side, need_rx=True, sums=False, timers=None):
         """Layer-1 passes for one phase: statistics of this rank's rows of R (side 0) / R^T (side 1) w.r.t. the
-        other factor.  sums: also the masked column sums of the other factor (for the statistics-based metrics)."""
+        other factor.  sums: also the masked column sums of the other factor (for the statistics-based metrics).
+        timers: a list that receives (name, start event, end event) for the two kernels as they run HERE, i.e.
+        concurrently on their two streams (profile_sweep)."""
         me, other, R, bits, rows, ld, lo = self._sides(side)
         nrx, ng, _ = self.nseg[side]
         other.pad()
@@ -433,10 +435,21 @@ class BNMFEngine:
             main = torch.cuda.current_stream()
             self._ev[0].record(main)
             self._side.wait_event(self._ev[0])
+            tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers is not None else None
             with torch.cuda.stream(self._side):
+                if tev:
+                    tev[0].record(self._side)
                 self._rx(side, max_ctas=self.split)
+                if tev:
+                    tev[1].record(self._side)
                 self._ev[1].record(self._side)
+            if tev:
+                tev[2].record(main)
             self._gram(side, sums)
+            if tev:
+                tev[3].record(main)
+                timers.append(("stats_rx_in_sweep", tev[0], tev[1]))
+                timers.append(("stats_gram_in_sweep", tev[2], tev[3]))
             main.wait_event(self._ev[1])
         elif need_rx and self.overlap:
             # the Gram kernel goes to a high-priority stream: its one-per-SM, long-lived CTAs are placed as soon as
@@ -690,7 +703,24 @@ class BNMFEngine:
                 _lib.call("bnmtf_metrics_from_sums_f64", _ptr(self.sums4), _ptr(self.statics_global), self.guard,
                           _ptr(self.m8), _ptr(self.flag), _stream())
             self.finish(update_tau=True, record=False)
-        return {n: acc[n] / max(1, count[n]) for n in names}
+        out = {n: acc[n] / max(1, count[n]) for n in names}
+        # the same two statistics kernels as they run inside a real sweep: side by side on their two streams (SM split)
+        if self.split > 0 and self.rx == "umma" and self.gram == "umma":
+            timers, spans = [], []
+            for _ in range(reps):
+                for side in (0, 1):
+                    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    p0.record()
+                    self.stats(side, sums=stat and side == 1, timers=timers)
+                    p1.record()
+                    spans.append((p0, p1))
+            torch.cuda.synchronize()
+            for name in ("stats_rx_in_sweep", "stats_gram_in_sweep"):
+                v = [a.elapsed_time(b) for (n, a, b) in timers if n == name]
+                out[name] = sum(v) / max(1, len(v))
+            out["stats_phase_in_sweep"] = sum(a.elapsed_time(b) for a, b in spans) / max(1, len(spans))
+        out["_meta"] = {"gram": self.gram, "rx": self.rx, "metrics_mode": self.metrics_mode, "split": self.split}
+        return out
 
     def alloc_trace(self, iterations):
         self.trace_cap = int(iterations)

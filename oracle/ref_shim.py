@@ -8,8 +8,11 @@ mechanically rewritten copy under a scratch directory OUTSIDE the repository (de
   * oracle/*.py (our numpy restatement) can be validated against the reference's own code, and
   * tests/golden/*.npz can be generated from the reference itself (tests/golden/make_golden.py).
 
-Nothing here is shipped, nothing is copied into the repository, and nothing on the GPU box uses it
-(/root/reference does not exist there).  Only tests/ and the golden generator may import this file.
+Nothing here is shipped and nothing is copied into the repository's history.  One more copy is made by
+__graft_entry__.build() under baseline/_ref (git-ignored): it travels to the GPU box with the snapshot and is what
+`bench.py --impl reference` and bench.py's cpu_baseline / parity legs time and compare against there
+(/root/reference itself does not exist on the GPU box).  Only tests/, the golden generators, bench.py's CPU legs and
+__graft_entry__.build() may import this file.
 """
 import os
 import re
@@ -41,13 +44,13 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "code", "models"))
 
 
-def build(scratch=DEFAULT_SCRATCH):
+def build(scratch=DEFAULT_SCRATCH, subdirs=("code", "data_toy", "data_drug_sensitivity", "tests")):
     """Create the rewritten scratch copy (library code + data only) and return its parent dir."""
     dst = os.path.join(scratch, "BNMTF")
     if os.path.isdir(dst):
         shutil.rmtree(dst)
     os.makedirs(dst)
-    for sub in ("code", "data_toy", "data_drug_sensitivity", "tests"):
+    for sub in subdirs:
         src = os.path.join(REFERENCE_ROOT, sub)
         if os.path.isdir(src):
             shutil.copytree(src, os.path.join(dst, sub))
@@ -79,9 +82,11 @@ def build(scratch=DEFAULT_SCRATCH):
 
 def load(scratch=DEFAULT_SCRATCH, rebuild=False):
     """Return a namespace with the reference's model classes and distribution functions."""
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-    if rebuild or not os.path.isdir(os.path.join(scratch, "BNMTF", "code")):
+    have = os.path.isdir(os.path.join(scratch, "BNMTF", "code"))
+    if rebuild or not have:
+        # a rewritten copy made earlier (e.g. baseline/_ref, which travels to the GPU box) is used as it is
+        if not available():
+            raise RuntimeError("reference tree not present at %s and no rewritten copy under %s" % (REFERENCE_ROOT, scratch))
         build(scratch)
     if scratch not in sys.path:
         sys.path.insert(0, scratch)
