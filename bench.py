@@ -353,6 +353,9 @@ def gpu_parity_run(K, distributed, shape=PARITY_SHAPE, vb_sweeps=2, icm_sweeps=2
         m.run(1)
         out["vb"].append({"expU": m.expU.copy(), "expV": m.expV.copy(), "varU": m.varU.copy(), "varV": m.varV.copy(),
                           "exptau": float(m.exptau), "elbo": float(m.all_elbo[-1]), "MSE": float(m.all_performances["MSE"][-1])})
+    # the device's TN variance against the reference's formula (truncated_normal_vector.py:62-73) at the device's own mu, tau
+    from oracle import bnmtf_oracle as orc
+    out["var_same_inputs"] = max(rel_err(m.varU, orc.tn_variance(m.muU, m.tauU)), rel_err(m.varV, orc.tn_variance(m.muV, m.tauV)))
     np.random.seed(12)
     g = bnmtf_b200.bnmf_gibbs_optimised(R, M, K, PRIORS, seed=6, **kw)
     g.initialise("random")
@@ -387,14 +390,27 @@ def parity_block(gpu, cpu, K, world):
     worst = 0.0
     vb = {"sweeps": len(cpu["vb"]), "max_rel_factors": 0.0, "max_rel_variances": 0.0, "max_rel_mse": 0.0, "max_rel_elbo": 0.0,
           "max_rel_exptau": 0.0}
+    elbo_finite = 0
     for a, b in zip(gpu["vb"], cpu["vb"]):
         vb["max_rel_factors"] = max(vb["max_rel_factors"], rel_err(a["expU"], b["expU"]), rel_err(a["expV"], b["expV"]))
         vb["max_rel_variances"] = max(vb["max_rel_variances"], rel_err(a["varU"], b["varU"]), rel_err(a["varV"], b["varV"]))
         vb["max_rel_mse"] = max(vb["max_rel_mse"], abs(a["MSE"] / b["MSE"] - 1.0))
-        vb["max_rel_elbo"] = max(vb["max_rel_elbo"], abs(a["elbo"] / b["elbo"] - 1.0))
+        if np.isfinite(a["elbo"]) and np.isfinite(b["elbo"]):
+            vb["max_rel_elbo"] = max(vb["max_rel_elbo"], abs(a["elbo"] / b["elbo"] - 1.0))
+            elbo_finite += 1
+        elif not (a["elbo"] == b["elbo"] or (np.isnan(a["elbo"]) and np.isnan(b["elbo"]))):
+            vb["max_rel_elbo"] = float("inf")          # one side finite, the other not
         vb["max_rel_exptau"] = max(vb["max_rel_exptau"], abs(a["exptau"] / b["exptau"] - 1.0))
+    vb["elbo_finite_sweeps"] = elbo_finite   # log(erfc) underflows to -inf on both sides while entries sit > 38 sigma below 0
+    vb["variance_note"] = ("the reference's TN variance sigma^2 (1 - lambda (lambda - x)) is evaluated from exp(-x*x/2) and "
+                           "erfc(x/sqrt2), whose argument roundings differ: for strongly truncated entries its value depends "
+                           "on the last bits of x with amplitude ~1e-13 x^4 (x = -mu sqrt(tau) up to 30), so two evaluations "
+                           "whose mu differ by 1e-10 differ by that much; max_rel_variances_same_inputs is the device value "
+                           "against the same formula in numpy at the DEVICE's own mu, tau")
+    if "var_same_inputs" in gpu:
+        vb["max_rel_variances_same_inputs"] = gpu["var_same_inputs"]
     blk["vb"] = vb
-    worst = max(worst, *[v for k, v in vb.items() if k.startswith("max_")])
+    worst = max(worst, *[v for k, v in vb.items() if k.startswith("max_") and k != "max_rel_variances"])
     icm = {"sweeps": len(cpu["icm"]), "max_rel_factors": 0.0, "max_rel_mse": 0.0, "max_rel_tau": 0.0}
     for a, b in zip(gpu["icm"], cpu["icm"]):
         icm["max_rel_factors"] = max(icm["max_rel_factors"], rel_err(a["U"], b["U"]), rel_err(a["V"], b["V"]))
@@ -409,6 +425,7 @@ def parity_block(gpu, cpu, K, world):
     blk["gibbs_conditionals"] = gc
     blk["worst"] = worst
     blk["pass"] = bool(worst <= PARITY_TOL)
+    blk["pass_covers"] = "factors, MSE, ELBO, tau, conditionals, variances at the same inputs (trajectory variances: see variance_note)"
     return blk
 
 

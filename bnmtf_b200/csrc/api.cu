@@ -28,10 +28,11 @@ int check_launch(const char* what) {
 int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int, int, double*, const int*, cudaStream_t);
 long long rxu_planes_bytes(long long, long long);
 long long rxu_workspace_bytes(int, long long);
-int launch_rxu_pack(const double*, const uint32_t*, int, int, uint8_t*, double*, int*, cudaStream_t);
+int launch_rxu_pack(const double*, const uint32_t*, int, int, uint8_t*, double*, int*, int*, cudaStream_t);
+int launch_range_guard(const double*, int, int, const double*, int, int, int, const void*, int*, unsigned long long*, cudaStream_t);
 int launch_stats_rx_umma(const uint8_t*, const double*, const double*, const uint32_t*, int, int, int, const double*, int, int,
                          int, double*, void*, long long, cudaStream_t);
-int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, cudaStream_t);
+int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, const int*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 long long umma_workspace_bytes(int, int, long long);
 int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, int, int, int,
@@ -171,8 +172,27 @@ int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld) {
 }
 
 int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
-                             double* rscale, int32_t* rexp_scratch, void* stream) {
-  return launch_rxu_pack(R, bits, (int)rows, (int)ld, planes, rscale, rexp_scratch, ST(stream));
+                             double* rscale, int32_t* rexp_scratch, int32_t* wide_flag, void* stream) {
+  return launch_rxu_pack(R, bits, (int)rows, (int)ld, planes, rscale, rexp_scratch, wide_flag, ST(stream));
+}
+
+int bnmtf_range_guard_f64(const double* Gpart, int nseg, int64_t rows, const double* Gfull, int polarity, int K,
+                          int64_t cols, const void* gram_workspace, int32_t* flag, uint64_t* trips, void* stream) {
+  if (check_k(K)) return -2;
+  return launch_range_guard(Gpart, nseg, (int)rows, Gfull, polarity, K, (int)cols, gram_workspace, flag,
+                            reinterpret_cast<unsigned long long*>(trips), ST(stream));
+}
+
+int bnmtf_stats_gated_f64(const int32_t* run_flag, const double* R, const uint32_t* bits, int64_t rows, int64_t ld,
+                          const double* Xp, const double* Vp, int K, int polarity, int nseg_rx, int nseg_gram,
+                          double* RXpart, double* Gpart, double* SVpart, void* stream) {
+  if (check_k(K)) return -2;
+  if (!run_flag) { set_error("stats_gated: run_flag is NULL"); return -2; }
+  if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gated: Vp and SVpart must be given together"); return -2; }
+  int rc = 0;
+  if (RXpart) rc = launch_stats_rx(R, bits, (int)rows, (int)ld, Xp, K, nseg_rx, RXpart, run_flag, ST(stream));
+  if (rc) return rc;
+  return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg_gram, Gpart, SVpart, run_flag, ST(stream));
 }
 
 int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld) {
@@ -192,7 +212,7 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
                          int polarity, int nseg, double* Gpart, double* SVpart, void* stream) {
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram: Vp and SVpart must be given together"); return -2; }
-  return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, ST(stream));
+  return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, nullptr, ST(stream));
 }
 
 int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld) {

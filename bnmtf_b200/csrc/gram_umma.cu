@@ -433,6 +433,50 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
+// dynamic-range guard.  The fixed-point images have ONE scale per product column (the column's largest magnitude)
+// and one per factor column in the R.X kernel: a row whose selected set only meets entries far below that scale
+// gets statistics with few significant bits.  What matters to the row's update is the rms of X_k over the row's
+// observed set, sqrt(G_i[k][k] / n_i), against the column maximum: the quantisation error of both statistics relative to
+// an fp64 evaluation is ~32 * max / rms (rx_umma.cu).  thread <-> (row, k): raises `flag` (and
+// counts the event once per launch) when  G_i[k][k] < 2^-24 * n_i * max_j X_jk^2,  i.e. max / rms > 4096; the gated
+// fp64 kernels (k_stats_rx, k_stats_gram with run_flag) then recompute the phase's statistics.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_range_guard(const double* __restrict__ Gpart, int nseg, int rows, int gl,
+                                                    const double* __restrict__ Gfull, int polarity, int K, int NT, int cols,
+                                                    const unsigned long long* __restrict__ colmax, int* __restrict__ flag,
+                                                    unsigned long long* __restrict__ trips) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)rows * K) return;
+  const int row = (int)(gid / K), k = (int)(gid - (long long)row * K);
+  const int ta = k >> 3, tk = K >> 3;
+  const int di = (ta * NT - ta * (ta - 1) / 2) * 64 + (k & 7) * 9;
+  const int ci = (tk * NT - tk * (tk - 1) / 2) * 64 + (K & 7) * 9;
+  double d = 0.0, cnt = 0.0;
+  for (int sgm = 0; sgm < nseg; ++sgm) {
+    const double* g = Gpart + ((size_t)sgm * rows + row) * gl;
+    d += g[di];
+    cnt += g[ci];
+  }
+  if (!polarity) { d = Gfull[di] - d; cnt = (double)cols - cnt; }
+  const double cmax = __longlong_as_double((long long)colmax[k * K - k * (k - 1) / 2]);       // max_j X_jk^2
+  if (cnt > 0.0 && d < 5.9604644775390625e-8 * cnt * cmax) {
+    if (atomicOr(flag, 1) == 0 && trips) atomicAdd(trips, 1ull);
+  }
+}
+
+// workspace: the one the preceding launch_stats_gram_umma call used (its colmax entries are read)
+int launch_range_guard(const double* Gpart, int nseg, int rows, const double* Gfull, int polarity, int K, int cols,
+                       const void* workspace, int* flag, unsigned long long* trips, cudaStream_t st) {
+  if (rows <= 0 || nseg <= 0) { set_error("range_guard: bad shape"); return -2; }
+  const int nt = tiles_for(K);
+  cudaMemsetAsync(flag, 0, sizeof(int), st);
+  const long long tot = (long long)rows * K;
+  k_range_guard<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Gpart, nseg, rows, nt * (nt + 1) / 2 * 64, Gfull, polarity, K, nt,
+                                                            cols, static_cast<const unsigned long long*>(workspace), flag, trips);
+  return check_launch("range_guard");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 // workspace layout: colmax (nc u64) | cscale (nc f64) | cexp (nc i32, padded) | digits (nch*nb x ldb bytes, 1024-aligned)

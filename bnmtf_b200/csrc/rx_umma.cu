@@ -52,7 +52,8 @@ __host__ __device__ inline size_t rxu_tile_offset(int rb, int kt, int ktiles) {
 // dataset pack (once): row scales, then the digit planes in tiled + swizzled order
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rxu_rowscale(const double* __restrict__ R, const uint32_t* __restrict__ bits,
-                                                     int rows, int ld, int* __restrict__ rexp, double* __restrict__ rscale) {
+                                                     int rows, int ld, int* __restrict__ rexp, double* __restrict__ rscale,
+                                                     int* __restrict__ wide) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const double* rr = R + (size_t)row * ld;
@@ -70,6 +71,26 @@ __global__ void __launch_bounds__(256) k_rxu_rowscale(const double* __restrict__
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   bad = __any_sync(0xffffffffu, bad);
+  // Dynamic range of the row.  One scale per row (the quantum is 2^-47 of the row's LARGEST magnitude) costs every other
+  // entry log2(max / |r|) significant bits, and the updates use the entries after the model's prediction has been
+  // subtracted -- the large ones cancel, the typical ones remain.  If more than half of the row's
+  // non-zero observed entries lie more than 2^12 below the largest (a row with outliers >= 4096 x its typical entry),
+  // the dataset is flagged and the engine keeps the fp64 kernel (engine.Dataset.ensure_planes / BNMFEngine).
+  if (wide) {
+    int small = 0, nz = 0;
+    const double cut = m * 0.000244140625;
+    for (int w = 0; w < (ld >> 5); ++w) {
+      const uint32_t word = mr[w];
+      if ((word >> lane) & 1u) {
+        const double v = fabs(rr[w * 32 + lane]);
+        nz += v > 0.0;
+        small += (v > 0.0 && v < cut);
+      }
+    }
+    small = __reduce_add_sync(0xffffffffu, small);
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if (lane == 0 && 2 * small > nz) atomicOr(wide, 1);
+  }
   if (lane == 0) {
     int e = 0;
     if (m > 0.0) frexp(m, &e);
@@ -401,10 +422,11 @@ long long rxu_planes_bytes(long long rows, long long ld) {
 
 // planes: rxu_planes_bytes(rows, ld) bytes (1024-aligned); rscale: rows doubles; rexp: rows ints of scratch
 int launch_rxu_pack(const double* R, const uint32_t* bits, int rows, int ld, uint8_t* planes, double* rscale, int* rexp,
-                    cudaStream_t st) {
+                    int* wide_flag, cudaStream_t st) {
   if (rows <= 0 || ld <= 0 || ld % 64) { set_error("rx_planes_pack: bad shape"); return -2; }
   const int ktiles = ld / RXU_KT, rows_pad = (rows + 127) / 128 * 128;
-  k_rxu_rowscale<<<(rows + 7) / 8, 256, 0, st>>>(R, bits, rows, ld, rexp, rscale);
+  if (wide_flag) cudaMemsetAsync(wide_flag, 0, sizeof(int), st);
+  k_rxu_rowscale<<<(rows + 7) / 8, 256, 0, st>>>(R, bits, rows, ld, rexp, rscale, wide_flag);
   const long long total = (long long)rows_pad * ktiles * 4;
   k_rxu_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(R, bits, rows, rows_pad, ld, ktiles, rexp, planes);
   return check_launch("rx_planes_pack");

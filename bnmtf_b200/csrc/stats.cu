@@ -132,10 +132,11 @@ template <int NT, bool VB>
 __global__ void __launch_bounds__(256) k_stats_gram(const uint32_t* __restrict__ bits, int rows, int ld, int seg_words,
                                                    const double* __restrict__ Xp, const double* __restrict__ Vp,
                                                    int polarity, int K, double* __restrict__ Gout,
-                                                   double* __restrict__ SVout) {
+                                                   double* __restrict__ SVout, const int* __restrict__ run_flag) {
   constexpr int KP = 8 * NT;
   constexpr int NTP = NT * (NT + 1) / 2;
   __shared__ uint16_t queue[8][1024 + 8];
+  if (run_flag && *run_flag == 0) return;      // gated fallback of the tcgen05 kernel (dynamic-range guard, gram_umma.cu)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, e = lane & 3;
   const int row = blockIdx.x * 8 + warp;
@@ -315,16 +316,16 @@ int launch_stats_rx(const double* R, const uint32_t* bits, int rows, int ld, con
 }
 
 int launch_stats_gram(const uint32_t* bits, int rows, int ld, const double* Xp, const double* Vp, int K, int polarity,
-                      int nseg, double* Gout, double* SVout, cudaStream_t st) {
+                      int nseg, double* Gout, double* SVout, const int* run_flag, cudaStream_t st) {
   if (rows <= 0 || ld <= 0 || ld % 64 || nseg <= 0) { set_error("stats_gram: bad shape"); return -2; }
   const int nt = tiles_for(K);
   const int wpr = ld / 32;
   const int seg_words = round_up((wpr + nseg - 1) / nseg, 32);
   dim3 grid((rows + 7) / 8, nseg);
   if (Vp) {
-    BNMTF_DISPATCH_NT(nt, (k_stats_gram<NT, true><<<grid, 256, 0, st>>>(bits, rows, ld, seg_words, Xp, Vp, polarity, K, Gout, SVout)));
+    BNMTF_DISPATCH_NT(nt, (k_stats_gram<NT, true><<<grid, 256, 0, st>>>(bits, rows, ld, seg_words, Xp, Vp, polarity, K, Gout, SVout, run_flag)));
   } else {
-    BNMTF_DISPATCH_NT(nt, (k_stats_gram<NT, false><<<grid, 256, 0, st>>>(bits, rows, ld, seg_words, Xp, nullptr, polarity, K, Gout, nullptr)));
+    BNMTF_DISPATCH_NT(nt, (k_stats_gram<NT, false><<<grid, 256, 0, st>>>(bits, rows, ld, seg_words, Xp, nullptr, polarity, K, Gout, nullptr, run_flag)));
   }
   return check_launch("stats_gram");
 }

@@ -155,6 +155,7 @@ class Dataset:
         self.R = self.bits = self.RT = self.bitsT = None
         self.n_obs = None          # global |Omega|
         self.planes = {}           # side -> (digit planes (uint8), row scales) for the tcgen05 R.X kernel, built on demand
+        self.wide = {}             # side -> True when some row of that orientation has an outlier (dynamic-range flag)
 
     def _pack(self, R, M, rows, cols, ld):
         out = torch.zeros((max(rows, 1), ld), dtype=torch.float64, device=self.device)
@@ -213,6 +214,7 @@ class Dataset:
             ld = self.ldJ if side == 0 else self.ldI
             if rows == 0:
                 self.planes[side] = (None, None)
+                self.wide[side] = False
                 return self.planes[side]
             nbytes = _lib.call("bnmtf_rx_planes_bytes", rows, ld)
             buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
@@ -220,9 +222,12 @@ class Dataset:
             planes = buf[off:off + nbytes]
             rscale = torch.empty(rows, dtype=torch.float64, device=self.device)
             rexp = torch.empty(rows, dtype=torch.int32, device=self.device)
+            wide = torch.zeros(1, dtype=torch.int32, device=self.device)
             _lib.call("bnmtf_rx_planes_pack_f64", _ptr(R), _ptr(bits), rows, ld, planes.data_ptr(), _ptr(rscale),
-                      _ptr(rexp), _stream())
+                      _ptr(rexp), _ptr(wide), _stream())
             self.planes[side] = (planes, rscale, buf)
+            # outlier rows (typical entry > 2^12 below the largest) keep too few bits under one fixed-point scale per row
+            self.wide[side] = bool(int(wide.item()))
         return self.planes[side]
 
     def pack_mask(self, M):
@@ -316,6 +321,23 @@ class BNMFEngine:
         KP, GL = kp_for(K), gram_len(K)
         # local row ranges of the two phases
         self.loc = {0: (dataset.partI.lo(), dataset.partI.cnt()), 1: (dataset.partJ.lo(), dataset.partJ.cnt())}
+        # dynamic-range guards of the fixed-point statistics kernels (include/bnmtf_b200.h, bnmtf_range_guard_f64):
+        # static -- a dataset with an outlier row keeps the fp64 R.X kernel; dynamic -- a device flag per phase that makes
+        # the gated fp64 kernels recompute the statistics (range_trips counts such phases)
+        self.range_guard = self.gram == "umma" and os.environ.get("BNMTF_RANGE_GUARD", "1") != "0"
+        self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.range_trips = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.wide_dataset = False
+        if self.rx == "umma":
+            for side in (0, 1):
+                dataset.ensure_planes(side)
+            wide = torch.tensor([int(any(dataset.wide.values()))], dtype=torch.int32, device=dev)
+            self.comm.allreduce(wide)
+            if int(wide.item()) and os.environ.get("BNMTF_RANGE_GUARD", "1") != "0":
+                import warnings
+                warnings.warn("bnmtf_b200: some row or column of R has outliers more than 4096 x its typical entry; the 48-bit "
+                              "fixed-point R.X kernel would lose precision there, using the fp64 kernel for this dataset")
+                self.rx, self.wide_dataset = "dmma", True
         # CTAs per launch: aim for >= 6 waves of resident CTAs (148 SMs x 3 resp. 2 CTAs) so that the tail wave
         # costs little; segments are column ranges whose partial results the solver adds up in order
         self.nseg = {}
@@ -359,8 +381,6 @@ class BNMFEngine:
             self.wsrx_bytes = max(_lib.call("bnmtf_rx_umma_workspace_bytes", self.K, ld) for ld in (dataset.ldJ, dataset.ldI))
             self.wsrx = torch.zeros(self.wsrx_bytes + 1024, dtype=torch.uint8, device=dev)
             self.wsrx_ptr = (self.wsrx.data_ptr() + 1023) // 1024 * 1024
-            for side in (0, 1):
-                dataset.ensure_planes(side)
         if self.gram == "umma":
             self.ws_bytes = max(_lib.call("bnmtf_gram_umma_workspace_bytes", self.K, int(self.vb), ld)
                                 for ld in (dataset.ldJ, dataset.ldI))
@@ -413,6 +433,20 @@ class BNMFEngine:
         return self.V, self.U, ds.RT, ds.bitsT, cnt, ds.ldI, lo
 
     def stats(self, side, need_rx=True, sums=False, timers=None):
+        """The statistics kernels of one phase (_stats_kernels) followed by the dynamic-range guard of the fixed-point
+        kernels and its gated fp64 recomputation (a few microseconds unless the guard trips)."""
+        self._stats_kernels(side, need_rx, sums, timers)
+        me, other, R, bits, rows, ld, lo = self._sides(side)
+        if not self.range_guard or rows == 0:
+            return
+        nrx, ng, _ = self.nseg[side]
+        _lib.call("bnmtf_range_guard_f64", _ptr(self.Gpart), ng, rows, _ptr(self.Gfull), self.polarity, self.K, other.n,
+                  self.ws_ptr, _ptr(self.range_flag), _ptr(self.range_trips), _stream())
+        _lib.call("bnmtf_stats_gated_f64", _ptr(self.range_flag), _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), _ptr(other.Vp),
+                  self.K, self.polarity, nrx, ng, _ptr(self.RXpart) if need_rx else 0, _ptr(self.Gpart), _ptr(self.SVpart),
+                  _stream())
+
+    def _stats_kernels(self, side, need_rx=True, sums=False, timers=None):
         """Layer-1 passes for one phase: statistics of this rank's rows of R (side 0) / R^T (side 1) w.r.t. the
         other factor.  sums: also the masked column sums of the other factor (for the statistics-based metrics).
         timers: a list that receives (name, start event, end event) for the two kernels as they run HERE, i.e.

@@ -10,7 +10,13 @@
  *     and keeps no state besides a thread-local error string);
  *   - every function enqueues its work on `stream` (a cudaStream_t passed as void*) and returns 0, or a negative
  *     code with the message available from bnmtf_last_error(); no hidden synchronisation;
- *   - all arithmetic is IEEE double.
+ *   - inputs, outputs and the per-row solver (TN moments / draws, Gamma, ELBO terms) are IEEE double.  The two O(I*J)
+ *     statistics passes (bnmtf_stats_rx_umma_f64, bnmtf_stats_gram_umma_f64) are NOT fp64 arithmetic: they cut their
+ *     operands into bnmtf_fixed_point_digits() 8-bit digits of a fixed-point image (6 digits = 48 bits by default, one
+ *     power-of-two scale per row of R / per factor column / per product column), multiply the digits on the int8
+ *     tensor cores and accumulate EXACTLY in int32; the exact total is rounded once to double.  Per term that is
+ *     narrower than a 53-bit mantissa, in accumulation it is wider; the error model and its guards are in DESIGN.md
+ *     section 2 and below (bnmtf_range_guard_f64).  The bnmtf_stats_*_f64 entry points without "umma" are plain fp64.
  *
  * Data layout
  *   dataset   R    : rows x ld doubles, row-major, ld = bnmtf_ld_for(cols) (multiple of 64), padding = 0
@@ -75,9 +81,13 @@ int bnmtf_pad_factor_f64(const double* X, const double* Var /*or NULL*/, int64_t
 int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, int K,
                        int nseg, double* RXpart, void* stream);
 /* The same product on the 5th-generation tensor cores (tcgen05.mma kind::i8, csrc/rx_umma.cu).  The dataset is
- * packed ONCE into seven 8-bit digit planes of a per-row 56-bit fixed-point image of the observed entries
+ * packed ONCE into D = bnmtf_fixed_point_digits() 8-bit digit planes of a per-row 8D-bit fixed-point image of the
+ * observed entries (D = 6, 48 bits, by default; 7 with -DBNMTF_DIGITS=7)
  * (bnmtf_rx_planes_pack_f64: planes = bnmtf_rx_planes_bytes(rows, ld) bytes, 1024-byte aligned; rscale = rows doubles;
- * rexp_scratch = rows int32), 7 instead of 8.125 bytes per entry streamed per phase.  Per call the factor is cut into
+ * rexp_scratch = rows int32; wide_flag (or NULL): one int32 set to 1 when in some row more than half of the non-zero
+ * observed entries lie more than 2^12 below the row's largest magnitude -- a row with outliers keeps too few
+ * significant bits for its typical entries under one scale per row, and the caller should use bnmtf_stats_rx_f64 for
+ * this orientation), D instead of 8.125 bytes per entry streamed per phase.  Per call the factor is cut into
  * digits too (K <= 32, entries >= 0) and the digit products are accumulated exactly in int32 tensor memory.  If the
  * factor has a negative or non-finite entry, a device-side flag routes the call to the fp64 kernel above (R, bits are
  * only read in that case); RXpart always receives nseg valid partial results.  The kernel is persistent (one CTA per
@@ -89,7 +99,7 @@ int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int6
 int bnmtf_fixed_point_digits(void);
 int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld);
 int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
-                             double* rscale, int32_t* rexp_scratch, void* stream);
+                             double* rscale, int32_t* rexp_scratch, int32_t* wide_flag /*or NULL*/, void* stream);
 int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld);
 int bnmtf_stats_rx_umma_f64(const uint8_t* planes, const double* rscale, const double* R, const uint32_t* bits,
                             int64_t rows, int64_t ld, int64_t cols, const double* Xp, int K, int nseg, int max_ctas,
@@ -99,9 +109,9 @@ int bnmtf_stats_rx_umma_f64(const uint8_t* planes, const double* rscale, const d
 int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const double* Xp, const double* Vp /*or NULL*/,
                          int K, int polarity, int nseg, double* Gpart, double* SVpart /*or NULL*/, void* stream);
 /* The same statistics on the 5th-generation tensor cores (tcgen05.mma kind::i8 with tensor-memory accumulators):
- * the products X_ja X_jb (and Var_jk) are cut into seven exact 8-bit digits of a 56-bit fixed-point value per
- * column and multiplied with the 0/1 selection matrix of the rows, so the result is the exactly summed,
- * once-rounded value.  cols = number of valid columns (<= ld); tile = 64 or 128 (bytes of the column range staged
+ * the products X_ja X_jb (and Var_jk) are cut into bnmtf_fixed_point_digits() exact 8-bit digits (6: a 48-bit
+ * fixed-point value per column, by default) and multiplied with the 0/1 selection matrix of the rows, so the result is
+ * the exactly summed, once-rounded value of the quantised products.  cols = number of valid columns (<= ld); tile = 64 or 128 (bytes of the column range staged
  * per pipeline stage); pair != 0 runs CTA pairs (cta_group::2: adjacent 128-row blocks share every MMA and each
  * CTA stages only half of the digit rows); sums != 0 also accumulates the masked column sums of X (slot (k, K) of the packed tiles,
  * as the ones-column of Xp does in bnmtf_stats_gram_f64; the selected-entry count always goes to slot (K, K));
@@ -113,6 +123,18 @@ int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, in
                               const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, int pair, int sums,
                               int max_stages, double* Gpart, double* SVpart /*or NULL*/, void* workspace,
                               int64_t workspace_bytes, void* stream);
+/* Dynamic-range guard of the two tcgen05 statistics kernels, run after them on the same stream.  Both use one scale
+ * per factor column, so a row whose observed set only meets entries far below a column's maximum gets statistics with
+ * few significant bits.  flag <- 1 (and *trips += 1, if given) when for some row i and column k
+ * G_i[k][k] < 2^-24 n_i max_j X_jk^2, i.e. max / rms over the row's observed set > 4096; flag <- 0 otherwise.
+ * Gpart / Gfull / polarity / nseg as passed to bnmtf_stats_gram_umma_f64, gram_workspace the workspace of that call.
+ * bnmtf_stats_gated_f64 then recomputes RXpart (skipped if NULL), Gpart and SVpart with the fp64 kernels -- only when
+ * *run_flag != 0; otherwise its kernels return at once.  Reference formulas: bnmf_vb_optimised.py:189-195. */
+int bnmtf_range_guard_f64(const double* Gpart, int nseg, int64_t rows, const double* Gfull, int polarity, int K,
+                          int64_t cols, const void* gram_workspace, int32_t* flag, uint64_t* trips /*or NULL*/, void* stream);
+int bnmtf_stats_gated_f64(const int32_t* run_flag, const double* R, const uint32_t* bits, int64_t rows, int64_t ld,
+                          const double* Xp, const double* Vp /*or NULL*/, int K, int polarity, int nseg_rx, int nseg_gram,
+                          double* RXpart /*or NULL*/, double* Gpart, double* SVpart /*or NULL*/, void* stream);
 /* scratch: >= 64 * (bnmtf_gram_len(K) + KP) doubles */
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t n, int K, int64_t dummy_row,
                         double* Gfull, double* scratch, void* stream);

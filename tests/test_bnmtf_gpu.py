@@ -67,53 +67,100 @@ def _set_vb_state(m, o):
     m.exptau, m.explogtau, m.alpha_s, m.beta_s = o.exptau, o.explogtau, o.alpha_s_, o.beta_s_
 
 
-@pytest.mark.parametrize("name", ["toy_bnmtf_vb", "gdsc_bnmtf_vb"])
-def test_vb_every_sweep_matches_oracle_from_the_same_state(golden, name):
-    """Per-sweep parity without error accumulation: before every sweep the device state is set to the oracle's
-    state (which itself follows the reference's golden trajectory to ~1e-9), then both do one sweep with the
-    reference's shuffled orders and all variational parameters are compared.
+def _tn_close(m, o, k, what):
+    """mu, tau at 1e-9; exp / var entry by entry with the truncation-dependent tolerance of the REFERENCE's own formula:
+    lambda = pdf(x) / (0.5 erfc(x / sqrt 2)) is built from exp(-x*x/2) and exp(-(x/sqrt2)^2), whose argument roundings
+    differ, so sigma (lambda - x) and sigma^2 (1 - lambda (lambda - x)) depend on the last bits of x = -mu sqrt(tau) with
+    amplitudes 2.5e-13 x^2 and 2.5e-13 x^4 (tests/test_oracle_golden.py::test_tn_moment_formulas_amplify_the_last_bits_of_x
+    measures exactly that on the CPU).  Returns the number of entries that needed more than 1e-9."""
+    mu_o, tau_o = getattr(o, "mu" + k), getattr(o, "tau" + k)
+    close(getattr(m, "mu" + k), mu_o, rtol=1e-9, what="mu%s %s" % (k, what))
+    close(getattr(m, "tau" + k), tau_o, rtol=1e-9, what="tau%s %s" % (k, what))
+    with np.errstate(all="ignore"):
+        x = np.where(mu_o < -30.0 / np.sqrt(tau_o), 0.0, np.maximum(-mu_o * np.sqrt(tau_o), 0.0))   # limit branch: no cancellation
+    loose = 0
+    for q, power, ref in (("exp", 2, getattr(o, k)), ("var", 4, getattr(o, "var" + k))):
+        a = getattr(m, q + k)
+        scale = float(np.abs(ref).max())
+        tol = 1e-9 + 3e-13 * x ** power
+        err = np.abs(a - ref) / (np.abs(ref) + 1e-2 * scale)
+        bad = err > tol
+        assert not bad.any(), "%s%s %s: %d entries beyond 1e-9 + 3e-13 x^%d, worst %.2e at x = %.1f" % (
+            q, k, what, int(bad.sum()), power, float(err.max()), float(x.flat[int(np.argmax(err))]))
+        loose += int((err > 1e-9).sum())
+        assert not (err > 1e-9)[x <= 10.0].any(), "%s%s %s: an entry with x <= 10 is off by more than 1e-9" % (q, k, what)
+    return loose
 
-    Tolerance 1e-7, not 1e-9: the reference's TN variance sigma^2 (1 - lambda (lambda - x)) cancels catastrophically
-    for strongly truncated entries (x = -mu sqrt(tau) between ~10 and the 30-sigma switch; most of S in these runs):
-    a 1-ulp difference between CUDA's and SciPy's erfc/exp becomes up to ~x^4 * 2e-13 relative in varS, and varS
-    enters tauF/tauG directly (measured: 7e-9 in tauF after the first S phase on GDSC, tools/gpu_debug2.py).  The
-    same spread exists between two SciPy builds, so it is the formula's conditioning, not the kernels'.  The
-    single-update tests above (fixed inputs, no variance recomputation in between) hold 1e-10."""
-    tol = 2e-7
+
+@pytest.mark.parametrize("name", ["toy_bnmtf_vb", "gdsc_bnmtf_vb"])
+def test_vb_every_phase_matches_oracle_from_the_same_state(golden, name):
+    """Phase-by-phase parity without error accumulation: before every phase (all S entries / all F columns / all G
+    columns, in the reference's shuffled orders) the device state is set to the oracle's, then both run the phase and
+    every variational parameter of the updated factor is compared at 1e-9 -- except that exp / var of strongly
+    truncated entries get the x-dependent tolerance of _tn_close, because there the REFERENCE's value is itself a
+    function of the last bits of its input.  (Within a phase the updated factor's variances are not read, so that
+    noise cannot leak into the mu / tau compared here; across phases it does -- varS enters tauF directly -- which is
+    why the free-running trajectory test below cannot be a 1e-9 test on every quantity.)"""
     from oracle import bnmtf_oracle as orc
     g = golden(name)
     K, L = int(g["K"]), int(g["L"])
     m = vb_from_golden(g)
     o = orc.OracleBNMTF(g["R"], g["M"], K, L, priors3(g), mode="vb")
     o.init_vb(g["init_muF"], g["init_muS"], g["init_muG"], {"F": g["init_tauF"], "S": g["init_tauS"], "G": g["init_tauG"]})
-    for it in range(min(12, int(g["its"]))):
-        _set_vb_state(m, o)
-        eng = m._push()
-        eng.alloc_trace(1)
+    loose = 0
+    for it in range(min(8, int(g["its"]))):
         oS = [tuple(int(v) for v in x) for x in g["order_S"][it]]
-        order = {"S": oS, "F": [int(x) for x in g["order_F"][it]], "G": [int(x) for x in g["order_G"][it]]}
-        perf = o.sweep(order=order)
-        eng.sweep(order={"S": [k * L + l for k, l in oS], "F": order["F"], "G": order["G"]})
-        tr = eng.trace.cpu().numpy()[0]
-        m._pull(eng)
-        for k in "FSG":
-            close(getattr(m, "exp" + k), getattr(o, k), rtol=tol, what="exp%s it %d" % (k, it))
-            # the variance itself: up to ~1.5e-7 for the entries just inside the 30-sigma switch (measured), so 1e-6
-            close(getattr(m, "var" + k), getattr(o, "var" + k), rtol=1e-6, what="var%s it %d" % (k, it))
-            close(getattr(m, "tau" + k), getattr(o, "tau" + k), rtol=tol, what="tau%s it %d" % (k, it))
-            close(getattr(m, "mu" + k), getattr(o, "mu" + k), rtol=tol, what="mu%s it %d" % (k, it))
-        close(tr[1], perf["MSE"], rtol=tol), close(tr[0], o.exptau, rtol=tol), close(tr[6], o.exp_square_diff(), rtol=tol)
+        oF, oG = [int(x) for x in g["order_F"][it]], [int(x) for x in g["order_G"][it]]
+        for phase in "SFG":
+            _set_vb_state(m, o)
+            eng = m._push()
+            if phase == "S":
+                for k, l in oS:
+                    o.vb_update_S(k, l)
+                    o.S[k, l], o.varS[k, l] = orc.tn_expectation(o.muS[k, l], o.tauS[k, l]), orc.tn_variance(o.muS[k, l], o.tauS[k, l])
+                eng.stats_rows()
+                eng.phase_S([k * L + l for k, l in oS])
+            elif phase == "F":
+                for k in oF:
+                    o.vb_update_F(k)
+                    o.F[:, k], o.varF[:, k] = orc.tn_expectation(o.muF[:, k], o.tauF[:, k]), orc.tn_variance(o.muF[:, k], o.tauF[:, k])
+                eng.stats_rows()
+                eng.phase_F(oF)
+            else:
+                for l in oG:
+                    o.vb_update_G(l)
+                    o.G[:, l], o.varG[:, l] = orc.tn_expectation(o.muG[:, l], o.tauG[:, l]), orc.tn_variance(o.muG[:, l], o.tauG[:, l])
+                eng.stats_cols()
+                eng.phase_G(oG)
+            m._pull(eng)
+            loose += _tn_close(m, o, phase, "it %d" % it)
+        o.update_tau_vb()
+        # the sweep's scalars from the oracle's end-of-sweep state: exp_square_diff, tau, MSE, ELBO
+        _set_vb_state(m, o)
+        close(m.exp_square_diff(), o.exp_square_diff(), rtol=1e-10, what="exp_square_diff it %d" % it)
         if np.isfinite(o.elbo()):
-            close(tr[4], o.elbo(), rtol=tol, what="elbo it %d" % it)
+            close(m.elbo(), o.elbo(), rtol=1e-10, what="elbo it %d" % it)
+    print("%s: %d exp/var entries needed the truncation-dependent tolerance" % (name, loose))
 
 
-@pytest.mark.parametrize("name,rtol", [("toy_bnmtf_vb", 1e-6), ("gdsc_bnmtf_vb", 1e-9)])
-def test_vb_trajectory_matches_reference(golden, name, rtol):
-    """Free-running trajectory against the reference's golden run, replaying its python-random shuffles.
-    VB-NMTF on the toy data amplifies rounding differences (two fp64 CPU evaluations -- reference vs oracle -- drift
-    from 2e-12 after one sweep to 1e-9 in the traces / 2e-8 in the factors after 30 sweeps, tests/test_oracle_golden.py);
-    the device path sums in yet another order, hence 1e-6 there.  GDSC stays within 1e-9."""
+def _trajectory_tolerances(golden):
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "vb_nmtf_sensitivity.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ["toy_bnmtf_vb", "gdsc_bnmtf_vb"])
+def test_vb_trajectory_matches_reference(golden, name):
+    """Free-running trajectory against the reference's golden run, replaying its python-random shuffles.  Tolerance:
+    1e-9, widened to 3x the reference's OWN reproducibility where that is worse -- tests/golden/vb_nmtf_sensitivity.json
+    holds, per quantity, how far the CPU trajectory moves when its start is perturbed in the last bit (made by
+    tests/golden/make_sensitivity.py, re-derived on the CPU by tests/test_oracle_golden.py): on the toy data the traces
+    move by ~1e-9 and the factors by ~1e-8 (the TN-moment noise of _tn_close, fed back 30 times); GDSC stays below 1e-9."""
     g = golden(name)
+    sens = _trajectory_tolerances(golden)[name]
+    tol = lambda key: max(1e-9, 3.0 * sens[key])
     m = vb_from_golden(g)
     its = int(g["its"])
     eng = m._push()
@@ -124,20 +171,20 @@ def test_vb_trajectory_matches_reference(golden, name, rtol):
                  "G": [int(x) for x in g["order_G"][it]]}
         eng.sweep(order=order)
     tr = eng.trace.cpu().numpy()[:its]
-    close(tr[:, 1], g["trace_MSE"], rtol=rtol, what="MSE trace")
-    close(tr[:, 0], g["trace_exptau"], rtol=rtol, what="exptau trace")
+    close(tr[:, 1], g["trace_MSE"], rtol=tol("MSE"), what="MSE trace")
+    close(tr[:, 0], g["trace_exptau"], rtol=tol("exptau"), what="exptau trace")
     ok = np.isfinite(g["trace_elbo"])
-    close(tr[ok, 4], g["trace_elbo"][ok], rtol=rtol, what="ELBO trace")
+    close(tr[ok, 4], g["trace_elbo"][ok], rtol=tol("elbo"), what="ELBO trace")
     m._pull(eng)
     for k in "FSG":
-        close(getattr(m, "exp" + k), g["final_exp" + k], rtol=max(rtol, 1e-8) * 100, what="exp" + k)
+        close(getattr(m, "exp" + k), g["final_exp" + k], rtol=tol("exp" + k), what="exp" + k)
 
 
 @pytest.mark.parametrize("K,L,init_FG", [(5, 4, "kmeans"), (4, 6, "kmeans"), (3, 7, "random"), (6, 2, "random")])
 def test_vb_rectangular_core_matches_oracle(golden, K, L, init_FG):
     """K != L (the golden trajectories are all K = L = 5): host initialisation with the reference's draw order (numpy
     exponentials for S, python-random K-means for F and G), then 8 free-running sweeps with the reference's shuffles,
-    against the oracle from the same start.  Measured 4e-10 on the MSE trace, 2e-8 on the factors (tools/gpu_debug3.py)."""
+    against the oracle from the same start.  Measured 4e-10 on the MSE trace, 2e-8 on the factors."""
     from oracle import bnmtf_oracle as orc
     import bnmtf_b200
     g = golden("toy_bnmtf_vb")
@@ -157,6 +204,37 @@ def test_vb_rectangular_core_matches_oracle(golden, K, L, init_FG):
     for k in "FSG":
         close(getattr(m, "exp" + k), getattr(o, k), rtol=1e-6, what="exp" + k)
     close(m.quality("ELBO"), o.elbo(), rtol=1e-7) if np.isfinite(o.elbo()) else None
+
+
+def test_large_core_uses_the_global_memory_accumulator(golden):
+    """K * L = 13 * 14 = 182: the (KL x KL) normal matrix of the S phase no longer fits shared memory (limit ~158), so
+    the reduction accumulates in global memory (csrc/nmtf.cu, k_nmtf_sq_partial<true>) -- the reference has no size
+    limit and its grid searches go to K, L of 20-30.  Two VB sweeps and two ICM sweeps against the oracle."""
+    from oracle import bnmtf_oracle as orc
+    import bnmtf_b200
+    g = golden("toy_bnmtf_vb")
+    K, L = 13, 14
+    np.random.seed(4), random.seed(4)
+    m = bnmtf_b200.bnmtf_vb_optimised(g["R"], g["M"], K, L, priors3(g))
+    m.initialise("random", "random")
+    o = orc.OracleBNMTF(g["R"], g["M"], K, L, priors3(g), mode="vb")
+    o.init_vb(m.muF.copy(), m.muS.copy(), m.muG.copy())
+    random.seed(5)
+    orders = [orc.OracleBNMTF.shuffled_order(K, L) for _ in range(2)]
+    mse = [o.sweep(order=od)["MSE"] for od in orders]
+    random.seed(5)
+    m.run(2)
+    close(m.all_performances["MSE"], mse, rtol=1e-9, what="MSE trace")
+    close(m.muS, o.muS, rtol=1e-8), close(m.tauS, o.tauS, rtol=1e-8), close(m.expF, o.F, rtol=1e-8)
+    np.random.seed(6)
+    c = bnmtf_b200.nmtf_icm(g["R"], g["M"], K, L, priors3(g))
+    c.initialise("random", "random")
+    oc = orc.OracleBNMTF(g["R"], g["M"], K, L, priors3(g), mode="icm")
+    oc.set_state(c.F.copy(), c.S.copy(), c.G.copy(), tau=c.tau)
+    c.run(2, minimum_TN=0.1)
+    for _ in range(2):
+        oc.sweep(minimum_TN=0.1)
+    close(c.S, oc.S, rtol=1e-9), close(c.F, oc.F, rtol=1e-9), close(c.tau, oc.tau, rtol=1e-10)
 
 
 def test_vb_run_uses_python_random_like_reference(golden):

@@ -3,10 +3,15 @@
 This pins the oracle: every deterministic path (VB, ICM, NP, Gibbs conditional parameters, TN moments,
 model-selection metrics) must reproduce the reference's numbers to 1e-9 relative.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 
 from oracle import bnmtf_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 RTOL = 1e-9
 
@@ -179,3 +184,42 @@ def test_bnmtf_gibbs_conditionals(golden):
     for l in range(L):
         t, m = o.params_G(l)
         close(t, g["tauG"][:, l]), close(m, g["muG"][:, l])
+
+
+# ---- conditioning of the reference's own formulas (what a 1e-9 comparison can and cannot mean) ----------------
+def test_tn_moment_formulas_amplify_the_last_bits_of_x():
+    """truncated_normal_vector.py:53-73 evaluates lambda = pdf(x) / (0.5 erfc(x / sqrt 2)) from exp(-x*x/2) and
+    exp(-(x/sqrt2)^2): two roundings of the same exponent (~450 at x = 30, ulp 6e-14).  sigma (lambda - x) and
+    sigma^2 (1 - lambda (lambda - x)) then cancel, so the reference's mean / variance of a strongly truncated entry move by
+    up to ~2.5e-13 x^2 / x^4 when mu changes in its LAST BIT.  The GPU tests compare such entries with the tolerance
+    1e-9 + 3e-13 x^power (tests/test_bnmtf_gpu.py::_tn_close, bench.py's variance note); this test pins both facts: the
+    noise is real (> 1e-8 on the variance beyond x = 20) and the bound holds."""
+    rng = np.random.RandomState(0)
+    x = rng.uniform(0.0, 29.99, 400000)
+    tau = rng.uniform(0.1, 10.0, x.size)
+    mu = -x / np.sqrt(tau)
+    mu1 = mu * (1.0 + 1.1e-16 * rng.choice([-1.0, 1.0], x.size))          # rounds to mu itself or to a neighbour
+    with np.errstate(all="ignore"):
+        v0, v1 = orc.tn_variance(mu, tau), orc.tn_variance(mu1, tau)
+        e0, e1 = orc.tn_expectation(mu, tau), orc.tn_expectation(mu1, tau)
+    xs = -mu * np.sqrt(tau)
+    rv, re = np.abs(v1 / v0 - 1.0), np.abs(e1 / e0 - 1.0)
+    assert rv[xs > 20].max() > 1e-8 and re[xs > 20].max() > 3e-11
+    assert (rv <= 1e-11 + 3e-13 * xs ** 4).all() and (re <= 1e-12 + 3e-13 * xs ** 2).all()
+    assert rv[xs < 10].max() < 1e-9
+
+
+def test_vb_nmtf_trajectory_sensitivity_fixture():
+    """tests/golden/vb_nmtf_sensitivity.json (made by make_sensitivity.py) says how far the CPU trajectory of the VB
+    tri-factorisation moves when its start changes in the last bit.  Re-derive it for one other perturbation on the toy
+    data: same order of magnitude, and -- the point -- the factors are NOT reproducible to 1e-9 even on the CPU."""
+    import json
+    sys.path.insert(0, GOLDEN)
+    import make_sensitivity as ms
+    with open(os.path.join(GOLDEN, "vb_nmtf_sensitivity.json")) as fh:
+        stored = json.load(fh)
+    g = dict(np.load(os.path.join(GOLDEN, "toy_bnmtf_vb.npz")))
+    cur = ms.spread(g, seeds=(11,))
+    for k in ms.KEYS:
+        assert cur[k] <= 10.0 * stored["toy_bnmtf_vb"][k] + 1e-12, (k, cur[k], stored["toy_bnmtf_vb"][k])
+    assert stored["toy_bnmtf_vb"]["expF"] > 1e-9 and cur["expF"] > 1e-10
