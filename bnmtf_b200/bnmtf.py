@@ -112,7 +112,7 @@ class BNMTFEngine:
                   _ptr(self.eff["SV"]) if self.vb else 0, 0, _ptr(me.fac), _ptr(me.var), _ptr(me.mu), _ptr(me.tauf),
                   _ptr(me.lam), _ptr(self.scalars), optr, n_order, 1 if apply else 0, float(minimum_TN), self.seed,
                   _ptr(self.iter if use_iter else self.iter_scratch), salt, 0,
-                  _ptr(self.sterm) if want_sterm else 0, 0, 0, 0, 0, 0, 0, _stream())
+                  _ptr(self.sterm) if want_sterm else 0, 0, 0, 0, 0, 0, 0, 0, _stream())
         del keep
 
     def phase_F(self, order=None, n_order=None, apply=True, minimum_TN=0.0, want_sterm=False, use_iter=True):

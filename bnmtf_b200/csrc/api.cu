@@ -192,7 +192,10 @@ int bnmtf_stats_gated_f64(const int32_t* run_flag, const double* R, const uint32
   int rc = 0;
   if (RXpart) rc = launch_stats_rx(R, bits, (int)rows, (int)ld, Xp, K, nseg_rx, RXpart, run_flag, ST(stream));
   if (rc) return rc;
-  return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg_gram, Gpart, SVpart, run_flag, ST(stream));
+  // always over the OBSERVED set: rows that trip the guard are the ones where Gfull - (sum over the missing set) would
+  // cancel; the solver is told through the same flag (bnmf_row_solve_f64: observed_flag)
+  (void)polarity;
+  return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, 1, nseg_gram, Gpart, SVpart, run_flag, ST(stream));
 }
 
 int64_t bnmtf_rx_umma_workspace_bytes(int K, int64_t ld) {
@@ -241,7 +244,7 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
                        double* mu, double* tauf, const double* lambda, const double* scalars, const int* order,
                        int n_order, int apply, double min_tn, uint64_t seed, const uint64_t* iter, uint64_t salt,
                        int64_t row_offset, double* sterm, double* extra, double* mstat, const uint64_t* peer_fac,
-                       const uint64_t* peer_var, int n_peers, int my_rank, void* stream) {
+                       const uint64_t* peer_var, int n_peers, int my_rank, const int32_t* observed_flag, void* stream) {
   if (check_k(K)) return -2;
   if (peer_fac && (n_peers < 2 || my_rank < 0 || my_rank >= n_peers || !apply)) { set_error("row_solve: bad peer arguments"); return -2; }
   if (mode < 0 || mode > 2) { set_error("row_solve: bad mode %d", mode); return -2; }
@@ -256,6 +259,7 @@ int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, i
   a.peer_fac = reinterpret_cast<double* const*>(peer_fac);
   a.peer_var = (mode == BNMTF_MODE_VB) ? reinterpret_cast<double* const*>(peer_var) : nullptr;
   a.n_peers = peer_fac ? n_peers : 0; a.my_rank = my_rank;
+  a.observed_flag = observed_flag;
   if (a.peer_fac && mode == BNMTF_MODE_VB && !a.peer_var) { set_error("row_solve: VB peer exchange needs peer_var"); return -2; }
   return launch_row_solve(a, ST(stream));
 }

@@ -72,6 +72,7 @@ struct RowSolveArgs {
   // fused exchange of a row-sharded run: base pointers of every rank's replicated n x K factor (and variance) array,
   // peer-mapped (NVLink P2P); a finished row is stored straight into each peer's copy at global row row_offset + row
   double* const* peer_fac; double* const* peer_var; int n_peers, my_rank;
+  const int* observed_flag;   // optional device flag: != 0 -> the statistics are sums over the observed set (as polarity 1)
 };
 
 struct FinishArgs {

@@ -72,13 +72,14 @@ __global__ void __launch_bounds__(256) k_rxu_rowscale(const double* __restrict__
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   bad = __any_sync(0xffffffffu, bad);
   // Dynamic range of the row.  One scale per row (the quantum is 2^-47 of the row's LARGEST magnitude) costs every other
-  // entry log2(max / |r|) significant bits, and the updates use the entries after the model's prediction has been
-  // subtracted -- the large ones cancel, the typical ones remain.  If more than half of the row's
-  // non-zero observed entries lie more than 2^12 below the largest (a row with outliers >= 4096 x its typical entry),
-  // the dataset is flagged and the engine keeps the fp64 kernel (engine.Dataset.ensure_planes / BNMFEngine).
+  // entry log2(max / |r|) significant bits.  The statistics are scale-covariant -- an entry that sets the scale also
+  // dominates the sums by the same factor -- and no failing case was found with outliers up to 1e9 x the typical entry
+  // (tests/test_range_gpu.py), so this is a conservative backstop: if more than half of the row's non-zero observed
+  // entries lie more than 2^20 below the largest (fewer than 28 significant bits left for the typical entry), the
+  // dataset is flagged and the engine keeps the fp64 kernels (engine.Dataset.ensure_planes / BNMFEngine).
   if (wide) {
     int small = 0, nz = 0;
-    const double cut = m * 0.000244140625;
+    const double cut = m * 9.5367431640625e-7;
     for (int w = 0; w < (ld >> 5); ++w) {
       const uint32_t word = mr[w];
       if ((word >> lane) & 1u) {

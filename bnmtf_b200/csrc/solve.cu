@@ -35,6 +35,8 @@ __global__ void k_pad_factor(const double* __restrict__ X, const double* __restr
 // ---------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
+  // observed_flag: the dynamic-range guard made the gated fp64 kernels recompute the statistics over the OBSERVED set
+  const int pol = a.polarity | (a.observed_flag ? *a.observed_flag : 0);
   constexpr int KP = 8 * NT;
   constexpr int GS = KP + 1;
   constexpr int NTP = NT * (NT + 1) / 2;
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
     const int tb = ta + rem;
     double s = 0.0;
     for (int sgm = 0; sgm < a.nseg_g; ++sgm) s += a.Gpart[((size_t)sgm * a.rows + row) * (NTP * 64) + i];
-    const double v = a.polarity ? s : a.Gfull[i] - s;
+    const double v = pol ? s : a.Gfull[i] - s;
     const int kr = 8 * ta + r, kc = 8 * tb + c;
     G[kr * GS + kc] = v;
     if (ta != tb) G[kc * GS + kr] = v;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
       if (a.mode == MODE_VB) {
         double s = 0.0;
         for (int sgm = 0; sgm < a.nseg_g; ++sgm) s += a.SVpart[((size_t)sgm * a.rows + row) * KP + c];
-        sv[q] = a.polarity ? s : a.Gfull[NTP * 64 + c] - s;
+        sv[q] = pol ? s : a.Gfull[NTP * 64 + c] - s;
       }
     }
     if (c < K) {
@@ -201,6 +203,8 @@ __global__ void __launch_bounds__(128) k_bnmf_row_solve(RowSolveArgs a) {
 // ---------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) {
+  // observed_flag: the dynamic-range guard made the gated fp64 kernels recompute the statistics over the OBSERVED set
+  const int pol = a.polarity | (a.observed_flag ? *a.observed_flag : 0);
   constexpr int KP = 8 * NT;
   constexpr int NTP = NT * (NT + 1) / 2;
   __shared__ double u_s[KP][32];
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) 
           lo.x += x.x; lo.y += x.y; lo.z += x.z; lo.w += x.w;
           hi.x += y.x; hi.y += y.y; hi.z += y.z; hi.w += y.w;
         }
-        if (!a.polarity) {
+        if (!pol) {
           const double4 x = *reinterpret_cast<const double4*>(a.Gfull + off);
           const double4 y = *reinterpret_cast<const double4*>(a.Gfull + off + 4);
           lo.x = x.x - lo.x; lo.y = x.y - lo.y; lo.z = x.z - lo.z; lo.w = x.w - lo.w;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_lane(RowSolveArgs a) 
     if (vb) {
       double t = 0.0;
       for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += a.SVpart[((size_t)sgm * a.rows + row) * KP + k];
-      svk = a.polarity ? t : a.Gfull[NTP * 64 + k] - t;
+      svk = pol ? t : a.Gfull[NTP * 64 + k] - t;
     }
     const double acck = acc_s[k][lane];
     double part = 0.0, gkk = 0.0, colsum = 0.0;
@@ -368,6 +372,8 @@ __device__ __noinline__ void row_update_value(int mode, double mu_k, double tau_
 
 template <int NT, int W>
 __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_sub(RowSolveArgs a) {
+  // observed_flag: the dynamic-range guard made the gated fp64 kernels recompute the statistics over the OBSERVED set
+  const int pol = a.polarity | (a.observed_flag ? *a.observed_flag : 0);
   constexpr int KP = 8 * NT;
   constexpr int NTP = NT * (NT + 1) / 2;
   constexpr int CPL = (KP + W - 1) / W;       // columns per lane
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_sub(RowSolveArgs a) {
               lo.x += x.x; lo.y += x.y; lo.z += x.z; lo.w += x.w;
               hi.x += y.x; hi.y += y.y; hi.z += y.z; hi.w += y.w;
             }
-            if (!a.polarity) {
+            if (!pol) {
               const double4 x = *reinterpret_cast<const double4*>(a.Gfull + off);
               const double4 y = *reinterpret_cast<const double4*>(a.Gfull + off + 4);
               lo.x = x.x - lo.x; lo.y = x.y - lo.y; lo.z = x.z - lo.z; lo.w = x.w - lo.w;
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_sub(RowSolveArgs a) {
             const int off = tile_pair(ta, c >> 3, NT) * 64 + r * 8 + (c & 7);
             double t = 0.0;
             for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += grow[sgm * gstride + off];
-            gv[i] = a.polarity ? t : a.Gfull[off] - t;
+            gv[i] = pol ? t : a.Gfull[off] - t;
           }
         }
       }
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_sub(RowSolveArgs a) {
       if (vb) {
         double t = 0.0;
         for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += a.SVpart[((size_t)sgm * a.rows + row) * KP + k];
-        svk = a.polarity ? t : a.Gfull[NTP * 64 + k] - t;
+        svk = pol ? t : a.Gfull[NTP * 64 + k] - t;
       }
       const size_t idx = (size_t)row * K + k;
       const double lam = a.lambda[idx];
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(32, 14) k_bnmf_row_solve_sub(RowSolveArgs a) {
         const int off = tile_pair(ta, K >> 3, NT) * 64 + r * 8 + (K & 7);
         double t = 0.0;
         for (int sgm = 0; sgm < a.nseg_g; ++sgm) t += grow[sgm * gstride + off];
-        colsum = a.polarity ? t : a.Gfull[off] - t;
+        colsum = pol ? t : a.Gfull[off] - t;
       }
       const double s = rxk - (acck + part);
       const double b = vb ? gkk + svk : gkk;

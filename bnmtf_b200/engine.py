@@ -226,7 +226,7 @@ class Dataset:
             _lib.call("bnmtf_rx_planes_pack_f64", _ptr(R), _ptr(bits), rows, ld, planes.data_ptr(), _ptr(rscale),
                       _ptr(rexp), _ptr(wide), _stream())
             self.planes[side] = (planes, rscale, buf)
-            # outlier rows (typical entry > 2^12 below the largest) keep too few bits under one fixed-point scale per row
+            # outlier rows (typical entry > 2^20 below the largest) keep few bits under one fixed-point scale per row
             self.wide[side] = bool(int(wide.item()))
         return self.planes[side]
 
@@ -335,9 +335,12 @@ class BNMFEngine:
             self.comm.allreduce(wide)
             if int(wide.item()) and os.environ.get("BNMTF_RANGE_GUARD", "1") != "0":
                 import warnings
-                warnings.warn("bnmtf_b200: some row or column of R has outliers more than 4096 x its typical entry; the 48-bit "
-                              "fixed-point R.X kernel would lose precision there, using the fp64 kernel for this dataset")
-                self.rx, self.wide_dataset = "dmma", True
+                warnings.warn("bnmtf_b200: some row or column of R has outliers more than 2^20 x its typical entry; the 48-bit "
+                              "fixed-point statistics kernels would leave those entries fewer than 28 significant bits, "
+                              "using the fp64 kernels for this dataset")
+                self.rx = self.gram = "dmma"
+                self.wide_dataset, self.range_guard = True, False
+                self.metrics_mode = os.environ.get("BNMTF_METRICS", "direct")
         # CTAs per launch: aim for >= 6 waves of resident CTAs (148 SMs x 3 resp. 2 CTAs) so that the tail wave
         # costs little; segments are column ranges whose partial results the solver adds up in order
         self.nseg = {}
@@ -553,7 +556,8 @@ class BNMFEngine:
                       _ptr(self.sterm, lo) if want_sterm else 0, _ptr(self.extra) if want_extra else 0,
                       _ptr(self.mstat) if want_mstat else 0,
                       _ptr(me.peer[1]) if fused else 0, _ptr(me.peer[2]) if (fused and self.vb) else 0,
-                      self.comm.world if fused else 0, self.comm.rank, _stream())
+                      self.comm.world if fused else 0, self.comm.rank,
+                      _ptr(self.range_flag) if self.range_guard else 0, _stream())
         if fused:
             me.peer[0].barrier(channel=side)          # every rank's rows have landed in every copy before anyone reads
         elif gather and self.comm.world > 1:

@@ -85,9 +85,9 @@ int bnmtf_stats_rx_f64(const double* R, const uint32_t* bits, int64_t rows, int6
  * observed entries (D = 6, 48 bits, by default; 7 with -DBNMTF_DIGITS=7)
  * (bnmtf_rx_planes_pack_f64: planes = bnmtf_rx_planes_bytes(rows, ld) bytes, 1024-byte aligned; rscale = rows doubles;
  * rexp_scratch = rows int32; wide_flag (or NULL): one int32 set to 1 when in some row more than half of the non-zero
- * observed entries lie more than 2^12 below the row's largest magnitude -- a row with outliers keeps too few
- * significant bits for its typical entries under one scale per row, and the caller should use bnmtf_stats_rx_f64 for
- * this orientation), D instead of 8.125 bytes per entry streamed per phase.  Per call the factor is cut into
+ * observed entries lie more than 2^20 below the row's largest magnitude -- the typical entry of such a row keeps
+ * fewer than 28 significant bits under one scale per row; a conservative backstop, the caller should then use the
+ * fp64 kernels bnmtf_stats_rx_f64 / bnmtf_stats_gram_f64 for this dataset), D instead of 8.125 bytes per entry streamed per phase.  Per call the factor is cut into
  * digits too (K <= 32, entries >= 0) and the digit products are accumulated exactly in int32 tensor memory.  If the
  * factor has a negative or non-finite entry, a device-side flag routes the call to the fp64 kernel above (R, bits are
  * only read in that case); RXpart always receives nseg valid partial results.  The kernel is persistent (one CTA per
@@ -129,7 +129,9 @@ int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, in
  * G_i[k][k] < 2^-24 n_i max_j X_jk^2, i.e. max / rms over the row's observed set > 4096; flag <- 0 otherwise.
  * Gpart / Gfull / polarity / nseg as passed to bnmtf_stats_gram_umma_f64, gram_workspace the workspace of that call.
  * bnmtf_stats_gated_f64 then recomputes RXpart (skipped if NULL), Gpart and SVpart with the fp64 kernels -- only when
- * *run_flag != 0; otherwise its kernels return at once.  Reference formulas: bnmf_vb_optimised.py:189-195. */
+ * *run_flag != 0; otherwise its kernels return at once.  The recomputed Gram / variance sums are over the OBSERVED set
+ * (for a row that trips the guard, "total minus missing-set sum" cancels), so the same flag must be passed to
+ * bnmf_row_solve_f64 as observed_flag; `polarity` is accepted for symmetry and ignored.  Reference formulas: bnmf_vb_optimised.py:189-195. */
 int bnmtf_range_guard_f64(const double* Gpart, int nseg, int64_t rows, const double* Gfull, int polarity, int K,
                           int64_t cols, const void* gram_workspace, int32_t* flag, uint64_t* trips /*or NULL*/, void* stream);
 int bnmtf_stats_gated_f64(const int32_t* run_flag, const double* R, const uint32_t* bits, int64_t rows, int64_t ld,
@@ -158,14 +160,16 @@ int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t 
  *                   into this process (CUDA IPC / symmetric memory; NVLink P2P stores).  Each finished row is stored
  *                   into every other rank's copy at global row row_offset + row; fac / var passed above are this rank's
  *                   own copy offset to its first row.  The caller runs a cross-GPU barrier before any rank reads the
- *                   factor.  NULL: no exchange.  Requires apply != 0. */
+ *                   factor.  NULL: no exchange.  Requires apply != 0.
+ *   observed_flag : optional device int32 (the flag of bnmtf_range_guard_f64): when != 0 the statistics passed in are
+ *                   sums over the OBSERVED set whatever `polarity` says (what bnmtf_stats_gated_f64 writes). */
 int bnmf_row_solve_f64(int mode, int64_t rows, int K, int nseg_rx, int nseg_g, int polarity,
                        const double* RXpart, const double* Gpart, const double* SVpart, const double* Gfull,
                        double* fac, double* var, double* mu, double* tauf, const double* lambda,
                        const double* scalars, const int* order, int n_order, int apply, double min_tn,
                        uint64_t seed, const uint64_t* iter, uint64_t salt, int64_t row_offset, double* sterm,
                        double* extra, double* mstat, const uint64_t* peer_fac, const uint64_t* peer_var, int n_peers,
-                       int my_rank, void* stream);
+                       int my_rank, const int32_t* observed_flag, void* stream);
 /* Sums over the set bits of `bits` of {e^2, p, p^2, r p, r, r^2, 1}, p = A_i.B_j  ->  out8 (predict(),
  * predict_while_running(), beta_s(): bnmf_gibbs_optimised.py:164-165,191-223).  partials: >= ceil(rows/128)*nseg*8.
  * statics3 = {sum r, sum r^2, count} of this mask if already known (training mask; selects the lean kernel that

@@ -76,6 +76,18 @@ def rel(a, b):
     return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-2 * float(np.abs(b).max()))))
 
 
+def rel_tn(a, b, mu, tauf, power):
+    """Largest error of a TN mean (power 2) / variance (power 4) in units of its tolerance 1e-9 + 3e-13 x^power, x = -mu
+    sqrt(tau) clipped to [0, 30): the reference's own formulas move by up to 2.5e-13 x^power when mu changes in its last
+    bit (tests/test_oracle_golden.py::test_tn_moment_formulas_amplify_the_last_bits_of_x), and the device's mu is not
+    bit-identical to the longdouble replay's."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    with np.errstate(all="ignore"):
+        x = np.where(mu < -30.0 / np.sqrt(tauf), 0.0, np.maximum(-mu * np.sqrt(tauf), 0.0))
+    err = np.abs(a - b) / (np.abs(b) + 1e-2 * float(np.abs(b).max()))
+    return float(np.max(err / (1e-9 + 3e-13 * x ** power)))
+
+
 def torch_sums(ds, U, V, U2=None, V2=None):
     """Plain torch fp64: sum over observed entries of (R - U V^T)^2 and of the VB variance term, in row tiles."""
     import torch
@@ -125,12 +137,14 @@ def test_vb_sweeps_at_the_headline_configuration(dataset):
         m._pull(eng)
         torch.cuda.synchronize()
         mu, tf, e, v = replay_rows("vb", Rr, Mr, old["expU"][ri], m.lambdaU[ri], old["expV"], old["varV"], tau_old)
-        errs = {"muU": rel(m.muU[ri], mu), "tauU": rel(m.tauU[ri], tf), "expU": rel(m.expU[ri], e), "varU": rel(m.varU[ri], v)}
+        errs = {"muU": rel(m.muU[ri], mu), "tauU": rel(m.tauU[ri], tf),
+                "expU": 1e-9 * rel_tn(m.expU[ri], e, mu, tf, 2), "varU": 1e-9 * rel_tn(m.varU[ri], v, mu, tf, 4)}
         mu, tf, e, v = replay_rows("vb", Rc, Mc, old["expV"][cj], m.lambdaV[cj], m.expU, m.varU, tau_old)
-        errs.update({"muV": rel(m.muV[cj], mu), "tauV": rel(m.tauV[cj], tf), "expV": rel(m.expV[cj], e), "varV": rel(m.varV[cj], v)})
-        for k, x in errs.items():
+        errs.update({"muV": rel(m.muV[cj], mu), "tauV": rel(m.tauV[cj], tf),
+                     "expV": 1e-9 * rel_tn(m.expV[cj], e, mu, tf, 2), "varV": 1e-9 * rel_tn(m.varV[cj], v, mu, tf, 4)})
+        for k, x in errs.items():                # exp / var: in units of their truncation-dependent tolerance, x 1e-9
             worst[k] = max(worst.get(k, 0.0), x)
-            assert x < (5e-9 if k.startswith("var") else 1e-9), "sweep %d: %s off by %.2e" % (it, k, x)
+            assert x < 1e-9, "sweep %d: %s off by %.2e" % (it, k, x)
         # the sweep's scalars (statistics-based metrics, exp_square_diff, tau) against plain torch fp64 on the new state
         tr = eng.trace.cpu().numpy()[it]
         e2, ex = torch_sums(dataset, m.expU, m.expV, m.varU + m.expU ** 2, m.varV + m.expV ** 2)
@@ -185,4 +199,4 @@ def test_gibbs_conditionals_and_chain_at_the_headline_configuration(dataset):
     assert rel(tU[ri], t.astype(float)) < 1e-10 and rel(mU[ri], mu.astype(float)) < 1e-9
     m.run(12)
     mse = m.all_performances["MSE"]
-    assert mse[-1] < 0.5 * mse[0] and mse[-1] < 4.0, mse
+    assert mse[-1] < 0.05 * mse[0] and all(b < a for a, b in zip(mse, mse[1:])), mse

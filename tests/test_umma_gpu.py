@@ -134,7 +134,7 @@ def _rx_both(d, rows, cols, K, nseg):
     pptr = (pbuf.data_ptr() + 1023) // 1024 * 1024
     rscale = torch.empty(rows, dtype=torch.float64, device=dev)
     rexp = torch.empty(rows, dtype=torch.int32, device=dev)
-    _lib.call("bnmtf_rx_planes_pack_f64", _ptr(d["Rp"]), _ptr(d["bits"]), rows, ld, pptr, _ptr(rscale), _ptr(rexp), _stream())
+    _lib.call("bnmtf_rx_planes_pack_f64", _ptr(d["Rp"]), _ptr(d["bits"]), rows, ld, pptr, _ptr(rscale), _ptr(rexp), 0, _stream())
     wsb = _lib.call("bnmtf_rx_umma_workspace_bytes", K, ld)
     ws = torch.zeros(wsb + 1024, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 1023) // 1024 * 1024

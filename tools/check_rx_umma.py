@@ -73,7 +73,7 @@ def run_case(idx):
     rscale = torch.empty(rows, dtype=torch.float64, device=dev)
     rexp = torch.empty(rows, dtype=torch.int32, device=dev)
     t0 = time.time()
-    _lib.call("bnmtf_rx_planes_pack_f64", _ptr(R), _ptr(bits), rows, ld, pptr, _ptr(rscale), _ptr(rexp), _stream())
+    _lib.call("bnmtf_rx_planes_pack_f64", _ptr(R), _ptr(bits), rows, ld, pptr, _ptr(rscale), _ptr(rexp), 0, _stream())
     torch.cuda.synchronize()
     out = {"case": idx, "shape": [rows, cols, K], "nseg": nseg, "kind": kind, "pack_s": round(time.time() - t0, 3)}
     wsb = _lib.call("bnmtf_rx_umma_workspace_bytes", K, ld)
