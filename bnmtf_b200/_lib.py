@@ -24,6 +24,11 @@ SIGNATURES = {
     "bnmtf_fixed_point_digits": [],
     "bnmtf_rx_planes_bytes": [c_i64, c_i64],
     "bnmtf_rx_planes_pack_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p],
+    "bnmtf_peer_sync_bytes": [],
+    "bnmtf_peer_sync_f64": [c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_p],
+    "bnmtf_peer_put_f64": [c_p, c_p, c_i64, c_i64, c_i, c_i, c_p],
+    "bnmtf_accumulate_f64": [c_p, c_p, c_i64, c_p],
+    "bnmtf_sample_mean_f64": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p],
     "bnmtf_range_guard_f64": [c_p, c_i, c_i64, c_p, c_i, c_i, c_i64, c_p, c_p, c_p, c_p],
     "bnmtf_stats_gated_f64": [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
     "bnmtf_rx_umma_workspace_bytes": [c_i, c_i64],
@@ -60,9 +65,9 @@ SIGNATURES = {
 }
 _RESTYPES = {"bnmtf_last_error": ctypes.c_char_p, "bnmtf_ld_for": c_i64, "bnmtf_gram_len": c_i64,
              "bnmtf_gram_umma_workspace_bytes": c_i64, "bnmtf_rx_planes_bytes": c_i64,
-             "bnmtf_rx_umma_workspace_bytes": c_i64}
+             "bnmtf_rx_umma_workspace_bytes": c_i64, "bnmtf_peer_sync_bytes": c_i64}
 _PLAIN = {"bnmtf_fixed_point_digits", "bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "bnmtf_gram_len",
-          "bnmtf_gram_umma_workspace_bytes", "bnmtf_rx_planes_bytes", "bnmtf_rx_umma_workspace_bytes"}
+          "bnmtf_gram_umma_workspace_bytes", "bnmtf_rx_planes_bytes", "bnmtf_rx_umma_workspace_bytes", "bnmtf_peer_sync_bytes"}
 
 _lib = None
 

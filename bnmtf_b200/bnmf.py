@@ -37,6 +37,66 @@ XFER = [0, 0]
 
 
 
+class _NoSharedHost(Exception):
+    pass
+
+
+class _LazySamples(object):
+    """What bnmf_gibbs_optimised.run() returns: behaves like the reference's tuple (all_U, all_V, all_tau), but the two
+    sample arrays are only downloaded from the device when somebody looks at them."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def __len__(self):
+        return 3
+
+    def __getitem__(self, i):
+        return (self._m.all_U, self._m.all_V, self._m.all_tau)[i] if isinstance(i, slice) else \
+            (self._m.all_U if i in (0, -3) else self._m.all_V if i in (1, -2) else self._m.all_tau if i in (2, -1) else
+             (_ for _ in ()).throw(IndexError(i)))
+
+    def __iter__(self):
+        yield self._m.all_U
+        yield self._m.all_V
+        yield self._m.all_tau
+
+
+def _shared_pinned(shape, register=True):
+    """A float64 host array in POSIX shared memory, mapped and page-locked (cudaHostRegister) by every rank of the default
+    process group: (torch view, numpy view, keep-alive).  Rank 0 creates the segment and unlinks it as soon as everybody
+    has attached, so nothing is left behind in /dev/shm whatever happens to the processes."""
+    import torch.distributed as dist
+    from multiprocessing import resource_tracker, shared_memory
+    nbytes = max(8, int(np.prod(shape)) * 8)
+    rank = dist.get_rank()
+    box = [None]
+    shm = None
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        box[0] = shm.name
+    dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=box[0])
+        try:                                             # attaching registered the segment with this process's tracker too
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
+    dist.barrier()
+    if rank == 0:
+        shm.unlink()
+    arr = np.ndarray(tuple(shape), dtype=np.float64, buffer=shm.buf)
+    t = torch.from_numpy(arr)
+    if register:
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError("cudaHostRegister failed (%s)" % rc)
+    if rank == 0:
+        arr[...] = 0.0
+    dist.barrier()
+    return t, arr, shm
+
+
 def _shared_seed(seed, distributed):
     """Philox seed of a model: the caller's, else one derived from numpy's global state (_lib.derive_seed: distinct for
     successive models, reproducible after numpy.random.seed).  Sharded runs: rank 0's value is broadcast, so that the
@@ -165,30 +225,107 @@ class _TwoFactorBase(object):
     # ARE numpy views of those buffers, rewritten in place by the next run() -- the same aliasing the reference has,
     # whose updates write into self.U in place -- and _push() DMAs straight from them (no staging copy) as long as
     # the attribute still is that view; anything the caller assigned instead takes the pageable path.
-    def _down_s(self, key, src, n):
+    #
+    # Row-sharded runs (one process per GPU of one node): the buffers live in POSIX shared memory mapped -- and
+    # page-locked -- by every rank, so that each rank moves only ITS OWN rows of the factor state over its PCIe link
+    # (upload: own rows, then peer stores replicate them to the other GPUs over NVLink; download: own rows into the
+    # shared array) and every rank still ends up with the complete host arrays, as the reference's attributes are.
+    def _own_rows(self, f):
+        """(sharded-with-shared-host-buffers?, lo, cnt) for the rows of Factor f this rank moves."""
+        eng = self._eng
+        if eng is not None and eng.comm.world > 1 and eng.comm.sync is not None and f.peer is not None \
+                and not self.__dict__.get('_no_shared_host', False):
+            return True, f.part.lo(), f.part.cnt()
+        return False, 0, f.n
+
+    def _host_buffer(self, key, shape, shared):
         pins = self.__dict__.setdefault('_pins', {})
-        t = src[:n]
         ent = pins.get(key)
-        if ent is None or tuple(ent[0].shape) != tuple(t.shape):
-            buf = torch.empty(tuple(t.shape), dtype=torch.float64, pin_memory=True)
-            ent = pins[key] = (buf, buf.numpy())
-        XFER[1] += t.numel() * t.element_size()
-        ent[0].copy_(t, non_blocking=True)       # caller synchronises before handing the view out
+        if ent is not None and tuple(ent[0].shape) == tuple(shape) and ent[2] == shared:
+            return ent
+        if shared:
+            try:
+                t, arr, shm = _shared_pinned(shape)
+                ent = pins[key] = (t, arr, True, shm)
+                return ent
+            except Exception as exc:                      # no /dev/shm, registration refused, ...: private buffers, full copies
+                import warnings
+                warnings.warn("bnmtf_b200: shared page-locked host buffers unavailable (%s: %s); every rank moves the "
+                              "whole factor state" % (type(exc).__name__, exc))
+                self._no_shared_host = True
+                raise _NoSharedHost()
+        buf = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+        ent = pins[key] = (buf, buf.numpy(), False, None)
+        return ent
+
+    def _down_s(self, key, src, f):
+        shared, lo, cnt = self._own_rows(f)
+        try:
+            ent = self._host_buffer(key, (f.n,) + tuple(src.shape[1:]), shared)
+        except _NoSharedHost:
+            shared, lo, cnt = False, 0, f.n
+            ent = self._host_buffer(key, (f.n,) + tuple(src.shape[1:]), False)
+        if cnt > 0:
+            t = src[lo:lo + cnt]
+            XFER[1] += t.numel() * t.element_size()
+            ent[0][lo:lo + cnt].copy_(t, non_blocking=True)       # _pull_done() synchronises before the views are read
         return ent[1]
 
-    def _up_s(self, key, dst, src):
+    def _pull_done(self, eng):
+        """All device->host copies of this run have landed -- on every rank, when the host buffers are shared."""
+        if eng.comm.world > 1 and eng.comm.sync is not None and not self.__dict__.get('_no_shared_host', False):
+            eng.comm.barrier(3)      # a rank's barrier kernel runs after its copies on the stream: when ours has finished, all have
+        torch.cuda.current_stream().synchronize()
+
+    def _up_s(self, key, dst, src, f=None, replicate=True):
+        """Host state -> device.  f given and the run is sharded: only this rank's rows cross PCIe; replicate: the other
+        ranks' copies are completed over NVLink (needed for the factors themselves, not for mu / tau / lambda, of which a
+        rank only reads its own rows).  Returns True if a cross-GPU barrier has to follow (_push_done)."""
         ent = self.__dict__.get('_pins', {}).get(key)
+        shared, lo, cnt = self._own_rows(f) if f is not None else (False, 0, src.shape[0])
+        if shared:
+            if cnt > 0:
+                if ent is not None and src is ent[1]:
+                    XFER[0] += cnt * int(np.prod(src.shape[1:])) * 8
+                    dst[lo:lo + cnt].copy_(ent[0][lo:lo + cnt], non_blocking=True)
+                else:
+                    rows = np.ascontiguousarray(src[lo:lo + cnt], dtype=np.float64)
+                    XFER[0] += rows.nbytes
+                    dst[lo:lo + cnt].copy_(torch.from_numpy(rows), non_blocking=False)
+            if replicate:
+                peers = f.peer[1] if dst is f.fac else f.peer[2]
+                self._eng.comm.put_rows(dst, f.part, peers)
+                self._need_barrier = True
+            return
         if ent is not None and src is ent[1]:
             XFER[0] += src.nbytes
             dst[:src.shape[0]].copy_(ent[0], non_blocking=True)
         else:
             self._up(dst, src)
 
+    def _up_lam(self, key, f, value):
+        """The priors do not change between run() calls: uploaded when the attribute is a different object than last time."""
+        sent = self.__dict__.setdefault('_lam_sent', {})
+        if sent.get(key) is value:
+            return
+        shared, lo, cnt = self._own_rows(f)
+        if shared:
+            if cnt > 0:
+                rows = np.ascontiguousarray(value[lo:lo + cnt], dtype=np.float64)
+                XFER[0] += rows.nbytes
+                f.lam[lo:lo + cnt].copy_(torch.from_numpy(rows))
+        else:
+            self._up(f.lam, value)
+        sent[key] = value
+
+    def _push_done(self, eng):
+        if self.__dict__.pop('_need_barrier', False):
+            eng.comm.barrier(3)      # every rank's rows are in every copy before the first kernel reads a factor
+
     def _set_scalars(self, eng, kv):
-        s = eng.scalars.cpu().numpy()
-        for k, v in kv.items():
-            s[k] = v
-        eng.scalars.copy_(torch.from_numpy(s))
+        idx = torch.tensor(list(kv.keys()), dtype=torch.int64)
+        val = torch.tensor([float(v) for v in kv.values()], dtype=torch.float64)
+        eng.scalars.index_copy_(0, idx.to(eng.scalars.device), val.to(eng.scalars.device))
 
     def _sums_for(self, M_pred, U, V):
         """Seven masked sums of the prediction U V^T over M_pred, on the device."""
@@ -278,24 +415,64 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
 
     def _push(self):
         eng = self._engine()
-        self._up_s('U', eng.U.fac, self.U), self._up_s('V', eng.V.fac, self.V)
-        self._up(eng.U.lam, self.lambdaU), self._up(eng.V.lam, self.lambdaV)
+        self._up_s('U', eng.U.fac, self.U, eng.U), self._up_s('V', eng.V.fac, self.V, eng.V)
+        self._up_lam('lambdaU', eng.U, self.lambdaU), self._up_lam('lambdaV', eng.V, self.lambdaV)
         self._set_scalars(eng, {S_TAU: float(getattr(self, 'tau', 1.0))})
+        self._push_done(eng)
         return eng
 
-    def run(self, iterations):
+    def run(self, iterations, summary=None):
+        """The reference's run(iterations).  The draws of every iteration stay ON THE DEVICE (each rank keeps its own rows):
+        all_U / all_V are downloaded the first time somebody reads them (or the returned tuple), approx_expectation /
+        predict / quality average them on the device.
+
+        summary=(burn_in, thinning): keep only the running sums over range(burn_in, iterations, thinning) -- what
+        approx_expectation(burn_in, thinning) needs -- instead of iterations x (I + J) x K samples; all_U / all_V are then
+        not available.  This is how a long chain on a matrix of the benchmark's size is run (1000 iterations at
+        65536 x 32768, K=20 would be 15.7 GB of samples)."""
         x0 = self._xfer_mark()
         eng = self._push()
         dev = eng.ds.device
-        all_U = torch.zeros((iterations, self.I, self.K), dtype=torch.float64, device=dev)
-        all_V = torch.zeros((iterations, self.J, self.K), dtype=torch.float64, device=dev)
-        self._init_trace_lists()
+        lo_u, n_u, lo_v, n_v = eng.loc[0][0], eng.loc[0][1], eng.loc[1][0], eng.loc[1][1]
+        self._samples = None
+        for key in ('_all_U', '_all_V', '_cache_U', '_cache_V'):
+            self.__dict__.pop(key, None)
+        if summary is not None:
+            burn_in, thinning = int(summary[0]), int(summary[1])
+            assert thinning >= 1 and 0 <= burn_in < max(1, iterations), "summary=(burn_in, thinning) selects no iteration"
+            keepers = set(range(burn_in, iterations, thinning))
+            sums = (torch.zeros((max(n_u, 1), self.K), dtype=torch.float64, device=dev),
+                    torch.zeros((max(n_v, 1), self.K), dtype=torch.float64, device=dev))
+            store = {'kind': 'sums', 'window': (burn_in, thinning), 'count': len(keepers), 'U': sums[0], 'V': sums[1]}
 
-        def keep(it):
-            all_U[it].copy_(eng.U.fac[:self.I]), all_V[it].copy_(eng.V.fac[:self.J])
+            def keep(it):
+                if it in keepers:
+                    if n_u:
+                        _lib.call("bnmtf_accumulate_f64", _ptr(sums[0]), _ptr(eng.U.fac, lo_u), n_u * self.K, _stream())
+                    if n_v:
+                        _lib.call("bnmtf_accumulate_f64", _ptr(sums[1]), _ptr(eng.V.fac, lo_v), n_v * self.K, _stream())
+        else:
+            need = iterations * (n_u + n_v) * self.K * 8
+            free = torch.cuda.mem_get_info(dev)[0]
+            if need > 0.8 * free:
+                raise _lib.BnmtfError("run(%d) would keep %.1f GB of samples on the device (%.1f GB free): pass "
+                                      "summary=(burn_in, thinning) to keep running sums instead" % (iterations, need / 1e9, free / 1e9))
+            all_U = torch.zeros((iterations, max(n_u, 1), self.K), dtype=torch.float64, device=dev)
+            all_V = torch.zeros((iterations, max(n_v, 1), self.K), dtype=torch.float64, device=dev)
+            store = {'kind': 'all', 'U': all_U, 'V': all_V}
+
+            def keep(it):
+                # own rows only: nobody else writes them, so a faster peer's next sweep cannot interleave with this copy
+                if n_u:
+                    all_U[it, :n_u].copy_(eng.U.fac[lo_u:lo_u + n_u])
+                if n_v:
+                    all_V[it, :n_v].copy_(eng.V.fac[lo_v:lo_v + n_v])
+        self._init_trace_lists()
         tr = self._run_loop(eng, iterations, per_iteration=keep)
-        self.U, self.V = self._down_s('U', eng.U.fac, self.I), self._down_s('V', eng.V.fac, self.J)
-        self.all_U, self.all_V = self._down(all_U), self._down(all_V)      # (synchronises)
+        store['iterations'] = iterations
+        self._samples = store
+        self.U, self.V = self._down_s('U', eng.U.fac, eng.U), self._down_s('V', eng.V.fac, eng.V)
+        self._pull_done(eng)
         self.all_tau = tr[:, 0].copy()
         if iterations > 0:
             self.tau = float(tr[-1, 0])
@@ -303,7 +480,39 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
             for it in range(iterations):
                 print("Iteration %s. MSE: %s. R^2: %s. Rp: %s." % (it + 1, tr[it, 1], tr[it, 2], tr[it, 3]))
         self._xfer_mark(x0)
-        return (self.all_U, self.all_V, self.all_tau)
+        return _LazySamples(self)
+
+    # all_U / all_V: host copies of the device-resident draws, made on first access; assignable as in the reference's tests
+    def _materialise(self, which):
+        if '_all_' + which in self.__dict__:              # assigned by the caller
+            return self.__dict__['_all_' + which]
+        cache = self.__dict__.get('_cache_' + which)
+        if cache is not None:
+            return cache
+        st = self.__dict__.get('_samples')
+        if st is None:
+            raise AttributeError("all_%s: no samples yet (call run())" % which)
+        if st['kind'] != 'all':
+            raise AttributeError("all_%s was not kept: run(..., summary=%r) stores running sums only" % (which, st['window']))
+        eng = self._engine()
+        f = eng.U if which == 'U' else eng.V
+        lo, cnt = eng.loc[0 if which == 'U' else 1]
+        its = st['iterations']
+        if eng.comm.world > 1:
+            # every rank holds its own rows of every draw: all-gather them per draw into the replicated layout
+            full = torch.zeros((its, f.part.n_pad, self.K), dtype=torch.float64, device=eng.ds.device)
+            if cnt:
+                full[:, lo:lo + cnt] = st[which][:, :cnt]
+            for it in range(its):
+                eng.comm.gather_rows(full[it], f.part)
+            host = self._down(full[:, :f.n])
+        else:
+            host = self._down(st[which][:, :f.n])
+        self.__dict__['_cache_' + which] = host
+        return host
+
+    all_U = property(lambda self: self._materialise('U'), lambda self, v: self.__dict__.__setitem__('_all_U', v))
+    all_V = property(lambda self: self._materialise('V'), lambda self, v: self.__dict__.__setitem__('_all_V', v))
 
     # ---- conditional parameters (reference :161-177) -----------------------------------------------------
     def alpha_s(self):
@@ -338,12 +547,42 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
 
     # ---- posterior summaries (reference :182-251) -------------------------------------------------------------
     def approx_expectation(self, burn_in, thinning):
-        indices = range(burn_in, len(self.all_U), thinning)
+        """Posterior means over range(burn_in, iterations, thinning) (reference :182-187), averaged on the device from the
+        device-resident draws or running sums; draws assigned by the caller as host arrays are uploaded first."""
+        st = self.__dict__.get('_samples')
+        own_host = '_all_U' in self.__dict__ or st is None          # draws assigned by the caller as host arrays
+        indices = range(burn_in, len(self.all_U) if own_host else st['iterations'], thinning)
         n = float(len(indices))
-        exp_U = np.array([self.all_U[i] for i in indices]).sum(axis=0) / n
-        exp_V = np.array([self.all_V[i] for i in indices]).sum(axis=0) / n
         exp_tau = sum([self.all_tau[i] for i in indices]) / n
-        return (exp_U, exp_V, exp_tau)
+        eng = self._engine()
+        dev = eng.ds.device
+        if own_host:
+            out = []
+            for a in (self.all_U, self.all_V):
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                d = torch.from_numpy(a).to(dev)
+                o = torch.zeros(a.shape[1:], dtype=torch.float64, device=dev)
+                _lib.call("bnmtf_sample_mean_f64", _ptr(d), int(np.prod(a.shape[1:])), a.shape[0], burn_in, thinning, _ptr(o), _stream())
+                out.append(self._down(o))
+            return (out[0], out[1], exp_tau)
+        out = []
+        for which, f, side in (('U', eng.U, 0), ('V', eng.V, 1)):
+            lo, cnt = eng.loc[side]
+            full = torch.zeros((f.part.n_pad, self.K), dtype=torch.float64, device=dev)
+            if cnt:
+                if st['kind'] == 'sums':
+                    assert (burn_in, thinning) == st['window'], \
+                        "this chain kept running sums for (burn_in, thinning) = %r only" % (st['window'],)
+                    full[lo:lo + cnt] = st[which][:cnt]            # the sums; divided by the count on the host below
+                else:
+                    dense = st[which] if st[which].shape[1] == cnt else st[which][:, :cnt].contiguous()
+                    tmp = torch.zeros((cnt, self.K), dtype=torch.float64, device=dev)
+                    _lib.call("bnmtf_sample_mean_f64", _ptr(dense), cnt * self.K, st['iterations'], burn_in, thinning, _ptr(tmp), _stream())
+                    full[lo:lo + cnt] = tmp
+            eng.comm.gather_rows(full, f.part)
+            host = self._down(full, f.n)
+            out.append(host / float(st['count']) if st['kind'] == 'sums' else host)
+        return (out[0], out[1], exp_tau)
 
     def predict(self, M_pred, burn_in, thinning):
         (exp_U, exp_V, _) = self.approx_expectation(burn_in, thinning)
@@ -398,8 +637,8 @@ class nmf_icm(_TwoFactorBase):
         self._init_trace_lists()
         tr = self._run_loop(eng, iterations, minimum_TN=minimum_TN)
         self.all_tau = tr[:, 0].copy()
-        self.U, self.V = self._down_s('U', eng.U.fac, self.I), self._down_s('V', eng.V.fac, self.J)
-        torch.cuda.current_stream().synchronize()
+        self.U, self.V = self._down_s('U', eng.U.fac, eng.U), self._down_s('V', eng.V.fac, eng.V)
+        self._pull_done(eng)
         if iterations > 0:
             self.tau = float(tr[-1, 0])
         self._xfer_mark(x0)
@@ -456,18 +695,21 @@ class bnmf_vb_optimised(_TwoFactorBase):
             for attr, t in (('exp', f.fac), ('var', f.var), ('mu', f.mu), ('tau', f.tauf)):
                 value = getattr(self, attr + s, None)
                 if value is not None:
-                    self._up_s(attr + s, t, value)
-            self._up(f.lam, getattr(self, 'lambda' + s))
+                    self._up_s(attr + s, t, value, f, replicate=attr in ('exp', 'var'))
+            self._up_lam('lambda' + s, f, getattr(self, 'lambda' + s))
         self._set_scalars(eng, {S_TAU: float(getattr(self, 'exptau', 1.0)), S_LOGTAU: float(getattr(self, 'explogtau', 0.0)),
                                   S_BETA_S: float(getattr(self, 'beta_s', 1.0))})
+        self._push_done(eng)
         return eng
 
     def _pull(self, eng, names=None):
+        if not self._own_rows(eng.U)[0]:
+            eng.gather_params()          # mu / tau of the other ranks' rows (with shared host buffers each rank writes its own)
         for f, s in ((eng.U, 'U'), (eng.V, 'V')):
             for attr, t in (('exp', f.fac), ('var', f.var), ('mu', f.mu), ('tau', f.tauf)):
                 if names is None or attr + s in names:
-                    setattr(self, attr + s, self._down_s(attr + s, t, f.n))
-        torch.cuda.current_stream().synchronize()
+                    setattr(self, attr + s, self._down_s(attr + s, t, f))
+        self._pull_done(eng)
 
     def run(self, iterations):
         x0 = self._xfer_mark()
@@ -476,7 +718,6 @@ class bnmf_vb_optimised(_TwoFactorBase):
         tr = self._run_loop(eng, iterations)
         self.all_exp_tau = [float(v) for v in tr[:, 0]]
         self.all_elbo = [float(v) for v in tr[:, 4]]
-        eng.gather_params()
         self._pull(eng)
         if iterations > 0:
             sc = eng.scalars.cpu().numpy()

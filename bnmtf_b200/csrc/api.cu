@@ -29,6 +29,11 @@ int launch_stats_rx(const double*, const uint32_t*, int, int, const double*, int
 long long rxu_planes_bytes(long long, long long);
 long long rxu_workspace_bytes(int, long long);
 int launch_rxu_pack(const double*, const uint32_t*, int, int, uint8_t*, double*, int*, int*, cudaStream_t);
+long long peer_sync_bytes();
+int launch_peer_sync(const unsigned long long*, unsigned long long*, int, int, int, double*, int, cudaStream_t);
+int launch_peer_put(const double*, const unsigned long long*, long long, long long, int, int, cudaStream_t);
+int launch_accumulate(double*, const double*, long long, cudaStream_t);
+int launch_sample_mean(const double*, long long, int, int, int, double*, cudaStream_t);
 int launch_range_guard(const double*, int, int, const double*, int, int, int, const void*, int*, unsigned long long*, cudaStream_t);
 int launch_stats_rx_umma(const uint8_t*, const double*, const double*, const uint32_t*, int, int, int, const double*, int, int,
                          int, double*, void*, long long, cudaStream_t);
@@ -174,6 +179,30 @@ int64_t bnmtf_rx_planes_bytes(int64_t rows, int64_t ld) {
 int bnmtf_rx_planes_pack_f64(const double* R, const uint32_t* bits, int64_t rows, int64_t ld, uint8_t* planes,
                              double* rscale, int32_t* rexp_scratch, int32_t* wide_flag, void* stream) {
   return launch_rxu_pack(R, bits, (int)rows, (int)ld, planes, rscale, rexp_scratch, wide_flag, ST(stream));
+}
+
+int64_t bnmtf_peer_sync_bytes(void) { return peer_sync_bytes(); }
+
+int bnmtf_peer_sync_f64(const uint64_t* blocks, uint64_t* epoch, int world, int rank, int channel, double* data, int n,
+                        void* stream) {
+  if (!blocks || !epoch) { set_error("peer_sync: NULL sync block table / epoch array"); return -2; }
+  return launch_peer_sync(reinterpret_cast<const unsigned long long*>(blocks), reinterpret_cast<unsigned long long*>(epoch),
+                          world, rank, channel, data, n, ST(stream));
+}
+
+int bnmtf_peer_put_f64(const double* local, const uint64_t* peers, int64_t offset, int64_t elems, int world, int rank,
+                       void* stream) {
+  if (!local || !peers || world < 1 || rank < 0 || rank >= world || offset < 0) { set_error("peer_put: bad arguments"); return -2; }
+  return launch_peer_put(local, reinterpret_cast<const unsigned long long*>(peers), offset, elems, world, rank, ST(stream));
+}
+
+int bnmtf_accumulate_f64(double* dst, const double* src, int64_t n, void* stream) {
+  return launch_accumulate(dst, src, n, ST(stream));
+}
+
+int bnmtf_sample_mean_f64(const double* samples, int64_t elems, int n_iter, int burn_in, int thinning, double* out,
+                          void* stream) {
+  return launch_sample_mean(samples, elems, n_iter, burn_in, thinning, out, ST(stream));
 }
 
 int bnmtf_range_guard_f64(const double* Gpart, int nseg, int64_t rows, const double* Gfull, int polarity, int K,

@@ -90,6 +90,7 @@ class Comm:
 
     def __init__(self, world=1, rank=0, group=None):
         self.world, self.rank, self.group = world, rank, group
+        self.sync = None           # (sync block, device table of every rank's block, epochs, ...) once setup_sync() ran
 
     def gather_rows(self, full, part):
         """full: (part.n_pad, ...) tensor whose rows [rank*S, rank*S+S) hold this rank's fresh values -> all ranks'."""
@@ -103,8 +104,44 @@ class Comm:
     def allreduce(self, t):
         if self.world == 1:
             return
+        if self.sync is not None and t.dtype == torch.float64 and t.numel() <= 32 and t.is_contiguous():
+            # <= 32 doubles: our own kernel over the peer-mapped sync blocks (csrc/peer.cu; rank-ordered sum, identical
+            # on every rank, capturable in the sweep's CUDA graph)
+            _lib.call("bnmtf_peer_sync_f64", _ptr(self.sync[1]), _ptr(self.sync[2]), self.world, self.rank, 2,
+                      _ptr(t), t.numel(), _stream())
+            return
         import torch.distributed as dist
         dist.all_reduce(t, group=self.group)
+
+    def barrier(self, channel):
+        """Cross-GPU barrier on the current stream (after it, every rank sees what every rank wrote before it)."""
+        if self.world == 1:
+            return
+        if self.sync is not None:
+            _lib.call("bnmtf_peer_sync_f64", _ptr(self.sync[1]), _ptr(self.sync[2]), self.world, self.rank, int(channel),
+                      0, 0, _stream())
+            return
+        import torch.distributed as dist
+        dist.barrier(group=self.group)
+
+    def setup_sync(self, device):
+        """One sync block per rank in symmetric memory + a private epoch array (include/bnmtf_b200.h, bnmtf_peer_sync_f64).
+        Called by the engine once the fused peer exchange is in use."""
+        if self.sync is None and self.peer_enabled(device):
+            n = _lib.call("bnmtf_peer_sync_bytes") // 8
+            t, hdl, ptrs, keep = self.symmetric((n,), device)
+            epoch = torch.zeros(8, dtype=torch.int64, device=device)
+            self.sync = (t, ptrs, epoch, keep, hdl)
+        return self.sync is not None
+
+    def put_rows(self, full, part, peers_ptrs):
+        """This rank's rows of the replicated array `full` -> every other rank's copy (NVLink P2P stores); the caller
+        follows up with barrier()."""
+        lo, cnt = part.lo(), part.cnt()
+        if self.world == 1 or cnt == 0:
+            return
+        w = full.shape[1] if full.dim() > 1 else 1
+        _lib.call("bnmtf_peer_put_f64", _ptr(full, lo), _ptr(peers_ptrs), lo * w, cnt * w, self.world, self.rank, _stream())
 
     # ---- fused exchange over peer memory (NVLink P2P stores from inside the solver kernel) ------------------------
     def peer_enabled(self, device):
@@ -294,11 +331,11 @@ class BNMFEngine:
         # become co-resident: different shared-memory carveouts; forcing the same carveout slows the streaming kernel)
         self.overlap = int(os.environ.get("BNMTF_OVERLAP", "0")) if self.gram == "umma" else 0
         self.umma_stages = int(os.environ.get("BNMTF_UMMA_STAGES", "3" if self.overlap else "0"))
-        # 1: replay the sweep as a CUDA graph (single-GPU runs); 2: also when sharded (NCCL collectives captured)
+        # 1: replay the sweep as a CUDA graph (0: launch by launch).  Sharded runs are captured too when the exchange runs
+        # over peer memory with our own barrier / all-reduce kernels (csrc/peer.cu) -- with NCCL collectives inside the
+        # capture (round 1's BNMTF_GRAPH=2) the process group did not shut down cleanly
         g = int(os.environ.get("BNMTF_GRAPH", "1"))
-        # one GPU only: with the NCCL all-reduce and the symmetric-memory barriers captured (tried as BNMTF_GRAPH=2 on
-        # 2 GPUs: +1.5 %) the process group does not shut down cleanly
-        self.use_graph = g >= 1 and dataset.world == 1
+        self.use_graph = g >= 1 and dataset.world == 1          # sharded: decided below, once the exchange path is known
         self._graph = self._graph_key = self._graph_seen = None
         self.split = int(os.environ.get("BNMTF_SPLIT", "72"))    # SMs given to the R.X kernel when both run concurrently (0: one after the other)
         self.umma_pair = int(os.environ.get("BNMTF_UMMA_PAIR", "1"))   # CTA pairs (cta_group::2) in the Gram kernel
@@ -311,6 +348,10 @@ class BNMFEngine:
         I, J = dataset.I, dataset.J
         self.U = Factor(dataset.partI, K, dev, self.vb, self.comm)
         self.V = Factor(dataset.partJ, K, dev, self.vb, self.comm)
+        if dataset.world > 1 and self.U.peer is not None and self.V.peer is not None and self.comm.setup_sync(dev):
+            # fused exchange + our own barrier / all-reduce kernels: the sharded sweep contains no NCCL call and no torch
+            # collective, so it is captured and replayed exactly like the single-GPU sweep
+            self.use_graph = g >= 1
         self.scalars = torch.zeros(16, dtype=torch.float64, device=dev)
         self.iter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.iter_scratch = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -559,7 +600,7 @@ class BNMFEngine:
                       self.comm.world if fused else 0, self.comm.rank,
                       _ptr(self.range_flag) if self.range_guard else 0, _stream())
         if fused:
-            me.peer[0].barrier(channel=side)          # every rank's rows have landed in every copy before anyone reads
+            self.comm.barrier(side)                   # every rank's rows have landed in every copy before anyone reads
         elif gather and self.comm.world > 1:
             if apply:
                 self.comm.gather_rows(me.fac, me.part)

@@ -256,6 +256,34 @@ int bnmtf_gamma_draw_f64(double shape, double rate, int64_t n, uint64_t seed, ui
 int bnmtf_exponential_draw_f64(const double* lambda, int64_t n, uint64_t seed, uint64_t stream_id, double* out,
                                void* stream);
 
+/* ---- row-sharded runs: synchronisation and the small exchanges over peer-mapped memory (csrc/peer.cu) ----------
+ * GPU p owns a block of rows of R (row phase) and of R^T (column phase), the factors are
+ * replicated.  The updated factor rows are stored into the peers' copies by bnmf_row_solve_f64 itself (peer_fac);
+ * these entry points are the rest of the exchange, as ordinary kernels on `stream` (no NCCL call, no host round trip:
+ * a sharded sweep is a fixed launch sequence that can be captured in a CUDA graph).
+ *
+ * Every rank provides one zero-initialised SYNC BLOCK of bnmtf_peer_sync_bytes() bytes in memory that is peer-mapped
+ * into every other rank's process (symmetric memory / CUDA IPC: the caller's business) and a private zero-initialised
+ * array of 8 uint64 epochs.  blocks: device array of `world` device pointers, entry r = rank r's block as mapped here.
+ * bnmtf_peer_sync_f64: barrier across the ranks on `channel` (0..7; one channel per call site, every rank must make
+ * the same sequence of calls per channel); all device writes issued on this GPU before the call -- including peer
+ * stores of earlier kernels on the stream -- are visible to every rank after it.  data != NULL: additionally an
+ * all-reduce (sum, in rank order: bitwise identical on every rank) of n <= 32 doubles in place.
+ * bnmtf_peer_put_f64: copies local[0..elems) into every OTHER rank's array at element offset `offset` (peers: device
+ * array of the `world` base pointers of the replicated array); follow it with bnmtf_peer_sync_f64. */
+int64_t bnmtf_peer_sync_bytes(void);
+int bnmtf_peer_sync_f64(const uint64_t* blocks, uint64_t* epoch, int world, int rank, int channel,
+                        double* data /*or NULL*/, int n, void* stream);
+int bnmtf_peer_put_f64(const double* local, const uint64_t* peers, int64_t offset, int64_t elems, int world, int rank,
+                       void* stream);
+
+/* ---- posterior summaries over Gibbs samples on the device (bnmf_gibbs_optimised.py:182-187) --------------------- */
+/* dst[i] += src[i]: running sums over the kept iterations */
+int bnmtf_accumulate_f64(double* dst, const double* src, int64_t n, void* stream);
+/* out[e] = mean over it in range(burn_in, n_iter, thinning) of samples[it][e]; samples: n_iter x elems, contiguous */
+int bnmtf_sample_mean_f64(const double* samples, int64_t elems, int n_iter, int burn_in, int thinning, double* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

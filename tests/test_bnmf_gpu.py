@@ -130,6 +130,57 @@ def test_gibbs_chain_matches_reference_in_distribution(models, golden):
     assert m.tau != t_before
 
 
+def test_posterior_summaries_stay_on_the_device(models, golden):
+    """bnmf_gibbs_optimised.py:182-245.  The draws stay on the device; all_U / all_V are downloaded on first access and
+    the summaries are averaged on the device: approx_expectation / predict / quality agree with numpy on the downloaded
+    draws, with the host path for draws the caller assigns (the reference's white-box tests), and with the running-sums
+    mode run(..., summary=(burn_in, thinning)), which never stores iterations x I x K."""
+    import torch
+    g = golden("toy_bnmf_gibbs")
+    K = int(g["K"])
+
+    def chain(summary=None):
+        m = models.bnmf_gibbs_optimised(g["R"], g["M"], K, priors2(g), seed=5)
+        m.initialise("exp")
+        m.U, m.V = g["init_U"].copy(), g["init_V"].copy()
+        m.tau = m.alpha_s() / m.beta_s()
+        ret = m.run(40, summary=summary)
+        return m, ret
+    m, ret = chain()
+    assert "_cache_U" not in m.__dict__ and m._samples["U"].is_cuda          # nothing downloaded yet
+    eU, eV, etau = m.approx_expectation(10, 3)
+    assert "_cache_U" not in m.__dict__                                        # ... and the summary did not need it
+    all_U, all_V, all_tau = ret                                                # the reference's return value, materialised now
+    assert all_U.shape == (40, 100, K) and all_U is m.all_U and len(ret) == 3 and ret[2] is m.all_tau
+    idx = list(range(10, 40, 3))
+    np.testing.assert_allclose(eU, np.array([all_U[i] for i in idx]).sum(axis=0) / len(idx), rtol=1e-14, atol=0)
+    np.testing.assert_allclose(eV, np.array([all_V[i] for i in idx]).sum(axis=0) / len(idx), rtol=1e-14, atol=0)
+    assert etau == sum(all_tau[i] for i in idx) / float(len(idx))
+    np.testing.assert_array_equal(all_U[-1], m.U)
+    perf = m.predict(g["M"], 10, 3)
+    # running sums only: same chain (same seed), same summaries, no sample store
+    s, _ = chain(summary=(10, 3))
+    assert s._samples["kind"] == "sums" and s._samples["U"].shape == (100, K)
+    sU, sV, stau = s.approx_expectation(10, 3)
+    np.testing.assert_allclose(sU, eU, rtol=1e-14), np.testing.assert_allclose(sV, eV, rtol=1e-14)
+    assert stau == etau and s.predict(g["M"], 10, 3)["MSE"] == pytest.approx(perf["MSE"], rel=1e-13)
+    assert s.quality("MSE", 10, 3) == pytest.approx(m.quality("MSE", 10, 3), rel=1e-13)
+    with pytest.raises(AttributeError):
+        s.all_U
+    with pytest.raises(AssertionError):
+        s.approx_expectation(5, 3)
+    # draws assigned by the caller (host arrays): same answers
+    w = models.bnmf_gibbs_optimised(g["R"], g["M"], K, priors2(g), seed=5)
+    w.all_U, w.all_V, w.all_tau = [a for a in all_U], [a for a in all_V], list(all_tau)
+    wU, wV, wtau = w.approx_expectation(10, 3)
+    np.testing.assert_allclose(wU, eU, rtol=1e-14), np.testing.assert_allclose(wV, eV, rtol=1e-14)
+    # a chain too long for the device refuses instead of allocating iterations x (I + J) x K
+    free = torch.cuda.mem_get_info()[0]
+    too_many = int(free / ((100 + 80) * K * 8)) + 10
+    with pytest.raises(Exception, match="summary="):
+        m.run(too_many)
+
+
 def test_tn_moments_and_draws_device(golden):
     from scipy.stats import ks_2samp, kstest, truncnorm
     from bnmtf_b200 import distributions as D

@@ -122,3 +122,25 @@ def test_sharded_sweep_equals_unsharded_gloo():
         np.testing.assert_allclose(U, o.U, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(V, o.V, rtol=1e-12, atol=1e-13)
         assert e2 == pytest.approx(o.sum_sq_residual(), rel=1e-12)
+
+
+def _shared_host(rank, world):
+    from bnmtf_b200.bnmf import _shared_pinned
+    t, arr, keep = _shared_pinned((6, 3), register=False)     # page-locking needs a GPU; the sharing itself does not
+    part = Partition(6, world, rank)
+    arr[part.lo():part.lo() + part.cnt()] = rank + 1.0         # each rank fills its own rows, as its device->host copy would
+    dist.barrier()
+    seen = arr.copy()
+    dist.barrier()
+    return seen, os.path.exists("/dev/shm/" + keep.name.lstrip("/"))
+
+
+def test_shared_host_buffers_give_every_rank_the_whole_array():
+    """Sharded runs download only a rank's own factor rows; the host arrays live in shared memory so that every rank
+    still sees the complete state (bnmtf_b200/bnmf.py::_shared_pinned).  The segment is unlinked as soon as all ranks
+    have attached: nothing stays behind in /dev/shm."""
+    res = run_world(_shared_host)
+    want = np.repeat(np.array([1.0, 1.0, 1.0, 2.0, 2.0, 2.0])[:, None], 3, axis=1)
+    for seen, still_there in res:
+        np.testing.assert_array_equal(seen, want)
+        assert not still_there

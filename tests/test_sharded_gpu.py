@@ -24,12 +24,23 @@ for k in range(int(g["K"])): m.update_exp_U(k)
 for k in range(int(g["K"])): m.update_exp_V(k)
 m.update_tau(); m.update_exp_tau()
 m.run(int(g["its"]))
+vb_xfer = m._xfer_bytes()
+vb_graph = m._engine()._graph is not None
 gb = bnmf.bnmf_gibbs_optimised(g["R"], g["M"], 5, pri, seed=7, distributed=True)
 gb.initialise("exp")
-gb.run(5)
+ret = gb.run(6)
+gb_xfer = gb._xfer_bytes()
+eU, eV, etau = gb.approx_expectation(2, 2)
+allU = ret[0]                      # first access: own rows of every draw gathered from both ranks, then downloaded
+gs = bnmf.bnmf_gibbs_optimised(g["R"], g["M"], 5, pri, seed=7, distributed=True)
+gs.initialise("exp")
+gs.run(6, summary=(2, 2))
+sU, sV, stau = gs.approx_expectation(2, 2)
 if rank == 0:
-    np.savez(sys.argv[1], expU=m.expU, expV=m.expV, muU=m.muU, mse=np.array(m.all_performances["MSE"]),
-             elbo=np.array(m.all_elbo), gU=gb.U, gtau=np.array(gb.all_tau))
+    np.savez(sys.argv[1], expU=m.expU, expV=m.expV, muU=m.muU, tauV=m.tauV, mse=np.array(m.all_performances["MSE"]),
+             elbo=np.array(m.all_elbo), gU=gb.U, gtau=np.array(gb.all_tau), allU=allU, eU=eU, eV=eV, sU=sU, sV=sV,
+             vb_xfer=np.array(vb_xfer), gb_xfer=np.array(gb_xfer), vb_graph=np.array(vb_graph),
+             shared=np.array(not gb.__dict__.get("_no_shared_host", False)))
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()
 '''
@@ -58,9 +69,22 @@ def test_two_gpu_sharded_matches_reference_and_single_gpu(tmp_path, golden):
     pri = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
     gb = bnmf.bnmf_gibbs_optimised(g["R"], g["M"], 5, pri, seed=7)
     gb.initialise("exp")
-    gb.run(5)
+    gb.run(6)
     np.testing.assert_allclose(r["gU"], gb.U, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(r["gtau"], gb.all_tau, rtol=1e-10)
+    # every draw, gathered lazily from the two ranks' own rows; posterior means from the stored draws and from running sums
+    np.testing.assert_allclose(r["allU"], gb.all_U, rtol=1e-10, atol=1e-12)
+    eU, eV, _ = gb.approx_expectation(2, 2)
+    for a, b in ((r["eU"], eU), (r["eV"], eV), (r["sU"], eU), (r["sV"], eV)):
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12)
+    # the other rank's rows of mu / tau arrive through the shared host buffers
+    np.testing.assert_allclose(r["muU"], g["final_muU"], rtol=1e-9, atol=1e-11 * np.abs(g["final_muU"]).max())
+    np.testing.assert_allclose(r["tauV"], g["final_tauV"], rtol=1e-9)
+    assert bool(r["vb_graph"]), "the sharded sweep must have been replayed as a CUDA graph"
+    if bool(r["shared"]):
+        I, J, K = g["R"].shape[0], g["R"].shape[1], int(g["K"])
+        full_vb = 4 * (I + J) * K * 8
+        assert r["vb_xfer"][1] < 0.6 * full_vb + 4096, "a rank must only download its own rows: %r of %d" % (r["vb_xfer"], full_vb)
 
 
 def test_fused_peer_exchange_equals_the_nccl_all_gather():
