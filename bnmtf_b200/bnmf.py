@@ -88,9 +88,19 @@ def _shared_pinned(shape, register=True):
     arr = np.ndarray(tuple(shape), dtype=np.float64, buffer=shm.buf)
     t = torch.from_numpy(arr)
     if register:
-        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
+        ptr = t.data_ptr()
+        rc = torch.cuda.cudart().cudaHostRegister(ptr, nbytes, 0)
         if int(rc) != 0:
             raise RuntimeError("cudaHostRegister failed (%s)" % rc)
+
+        def _unregister(p=ptr):
+            # before the mapping goes away: a later segment mapped at the same address could not be registered otherwise
+            try:
+                torch.cuda.cudart().cudaHostUnregister(p)
+            except Exception:
+                pass
+        import weakref
+        weakref.finalize(arr, _unregister)
     if rank == 0:
         arr[...] = 0.0
     dist.barrier()
