@@ -46,7 +46,7 @@ class BNMTFEngine:
         self.col = {"RX": f64(J, KPk), "G": f64(J, GLk), "SV": f64(J, KPk), "full": f64(GLk + KPk)}
         n, KPm, GLm = max(I, J), max(KPk, KPl), max(GLk, GLl)
         self.eff = {"RX": f64(n, KPm), "G": f64(n, GLm), "SV": f64(n, KPm)}      # effective-factor statistics
-        self.gscratch = f64(64 * (GLm + KPm))
+        self.gscratch = f64(296 * (GLm + KPm))       # bnmtf_gram_full_f64: up to 296 partial results
         self.nparts = 64
         self.sq_len = D * D + 2 * D
         self.sq_part, self.sq_out = f64(self.nparts * self.sq_len), f64(self.sq_len)

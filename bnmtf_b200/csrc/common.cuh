@@ -57,6 +57,7 @@ enum Scalar {
   S_SUM_R = 10, S_SUM_R2 = 11, S_OMEGA = 12,
   S_COUNT = 16
 };
+constexpr int kGramFullParts = 296;   // CTAs (partial results) of the unmasked-total reduction bnmtf_gram_full_f64
 constexpr int kTraceWidth = 8;  // tau, MSE, R2, Rp, ELBO, sum_e2, esd, logtau
 
 struct RowSolveArgs {

@@ -39,26 +39,32 @@ struct UmmaPlan {
   int K, vb, sums;
   int ng;       // K(K+1)/2 Gram columns
   int nc;       // ng (+K variance columns) (+K plain columns X_jk: masked column sums, for the metrics)
-  int nch;      // chunks
-  int cpc;      // P-columns per chunk
-  int n_half;   // UMMA N of each of the two accumulators (multiple of 16, <= 256)
-  int nb;       // digit rows per chunk in the staged B matrix = 2*n_half
+  int nch;      // chunks: all but the last hold cpc P-columns in two accumulators of 256 tensor-memory columns
+  int cpc;      // P-columns per full chunk: 512 / kDigits (85 with six digits)
+  int cpc_last; // P-columns of the last chunk
+  int nh_last;  // UMMA N of each accumulator of the last chunk (multiple of 32 for CTA pairs, else 16; <= 256)
+  int gran;
 };
+constexpr int UG_CHUNK_ROWS = 512;   // digit rows reserved per chunk in the staged B matrix
 
+// Chunks are UNEVEN: 210 products x 6 digits = 1260 digit columns run as 512 + 512 + 256 tensor-memory columns (three
+// equal chunks of 70 products would need 3 x 448; with the K column sums / VB variances 3 x 512 instead of 512 + 512 +
+// 384): the MMA work follows the columns actually needed.
 __host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums, int pair) {
   UmmaPlan p;
   p.K = K; p.vb = vb; p.sums = sums;
   p.ng = K * (K + 1) / 2;
   p.nc = p.ng + (vb ? K : 0) + (sums ? K : 0);
-  const int cmax = 512 / UG_SLICES;                   // 85 (73 with seven digits)
-  p.nch = (p.nc + cmax - 1) / cmax;
-  p.cpc = (p.nc + p.nch - 1) / p.nch;
-  const int nd = p.cpc * UG_SLICES;
-  const int gran = pair ? 32 : 16;                    // UMMA N granularity (CTA pair: each CTA holds n_half/2 digit rows)
-  p.n_half = ((nd + 1) / 2 + gran - 1) / gran * gran;
-  p.nb = 2 * p.n_half;
+  p.cpc = 512 / UG_SLICES;                   // 85 (73 with seven digits)
+  p.nch = (p.nc + p.cpc - 1) / p.cpc;
+  p.cpc_last = p.nc - (p.nch - 1) * p.cpc;
+  p.gran = pair ? 32 : 16;                   // UMMA N granularity (CTA pair: each CTA holds n_half/2 digit rows)
+  const int nd = p.cpc_last * UG_SLICES;
+  p.nh_last = ((nd + 1) / 2 + p.gran - 1) / p.gran * p.gran;
   return p;
 }
+__host__ __device__ inline int umma_cols_of(const UmmaPlan& p, int ch) { return ch == p.nch - 1 ? p.cpc_last : p.cpc; }
+__host__ __device__ inline int umma_nhalf_of(const UmmaPlan& p, int ch) { return ch == p.nch - 1 ? p.nh_last : 256; }
 
 // column c of P  ->  (a, b) with a <= b < K: X_a X_b;  (k, -1): Var_k;  (k, -2): X_k
 __host__ __device__ inline void umma_col_pair(int c, const UmmaPlan& pl, int& a, int& b) {
@@ -80,27 +86,43 @@ __global__ void __launch_bounds__(256) k_ug_colmax(const double* __restrict__ Xp
                                                   int KP, UmmaPlan pl, unsigned long long* __restrict__ colmax) {
   extern __shared__ double xs[];           // [2][K][JT+1]
   constexpr int JT = 64;
-  const int j0 = blockIdx.x * JT;
   const int K = pl.K;
-  for (int i = threadIdx.x; i < JT * K; i += blockDim.x) {
-    const int jj = i / K, k = i - jj * K;
-    const int j = j0 + jj;
-    xs[k * (JT + 1) + jj] = (j < n) ? Xp[(size_t)j * KP + k] : 0.0;
-    if (pl.vb) xs[(K + k) * (JT + 1) + jj] = (j < n) ? Vp[(size_t)j * KP + k] : 0.0;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < pl.nc; c += blockDim.x) {
-    int a, b;
-    umma_col_pair(c, pl, a, b);
-    const double* xa = xs + (b == -1 ? (K + a) : a) * (JT + 1);
-    const double* xb = b < 0 ? nullptr : xs + b * (JT + 1);
-    unsigned long long m = 0ull;
-    for (int jj = 0; jj < JT; ++jj) {
-      const double p = xb ? xa[jj] * xb[jj] : xa[jj];
-      const unsigned long long u = (unsigned long long)__double_as_longlong(fabs(p));
-      m = u > m ? u : m;
+  // persistent CTAs: a thread keeps the running maximum of "its" product columns over all the tiles of the CTA and
+  // issues ONE atomic per column at the end (a CTA per tile meant ~1000 colliding atomics per address)
+  unsigned long long m[4] = {0ull, 0ull, 0ull, 0ull};      // columns threadIdx.x + 256 q (nc <= 1024: K <= 43; larger K loops below)
+  for (int j0 = blockIdx.x * JT; j0 < n; j0 += gridDim.x * JT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < JT * K; i += blockDim.x) {
+      const int jj = i / K, k = i - jj * K;
+      const int j = j0 + jj;
+      xs[k * (JT + 1) + jj] = (j < n) ? Xp[(size_t)j * KP + k] : 0.0;
+      if (pl.vb) xs[(K + k) * (JT + 1) + jj] = (j < n) ? Vp[(size_t)j * KP + k] : 0.0;
     }
-    atomicMax(colmax + c, m);
+    __syncthreads();
+    auto tile_max = [&](int c) {
+      int a, b;
+      umma_col_pair(c, pl, a, b);
+      const double* xa = xs + (b == -1 ? (K + a) : a) * (JT + 1);
+      const double* xb = b < 0 ? nullptr : xs + b * (JT + 1);
+      unsigned long long mm = 0ull;
+      for (int jj = 0; jj < JT; ++jj) {
+        const double p = xb ? xa[jj] * xb[jj] : xa[jj];
+        const unsigned long long u = (unsigned long long)__double_as_longlong(fabs(p));
+        mm = u > mm ? u : mm;
+      }
+      return mm;
+    };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = threadIdx.x + 256 * q;
+      if (c < pl.nc) { const unsigned long long mm = tile_max(c); m[q] = mm > m[q] ? mm : m[q]; }
+    }
+    for (int c = threadIdx.x + 1024; c < pl.nc; c += 256) atomicMax(colmax + c, tile_max(c));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = threadIdx.x + 256 * q;
+    if (c < pl.nc && m[q]) atomicMax(colmax + c, m[q]);
   }
 }
 
@@ -128,42 +150,57 @@ __global__ void k_ug_scales(const unsigned long long* __restrict__ colmax, int n
 __global__ void __launch_bounds__(128) k_ug_quantize(const double* __restrict__ Xp, const double* __restrict__ Vp, int n,
                                                     int KP, long long ldb, UmmaPlan pl, const int* __restrict__ cexp,
                                                     uint8_t* __restrict__ Bd) {
-  extern __shared__ double xs[];           // [2][K][JT+2]
+  extern __shared__ double xs[];           // [2][K][JT+2], then the (a, b) table of the product columns
   constexpr int JT = 128, XS = JT + 2;
   const int j0 = blockIdx.x * JT;
   const int K = pl.K;
+  int16_t* tab = reinterpret_cast<int16_t*>(xs + (size_t)(pl.vb ? 2 : 1) * K * XS);     // [nc][2]
   for (int i = threadIdx.x; i < JT * K; i += blockDim.x) {
     const int jj = i / K, k = i - jj * K;
     const int j = j0 + jj;
     xs[k * XS + jj] = (j < n) ? Xp[(size_t)j * KP + k] : 0.0;
     if (pl.vb) xs[(K + k) * XS + jj] = (j < n) ? Vp[(size_t)j * KP + k] : 0.0;
   }
+  for (int c = threadIdx.x; c < pl.nc; c += blockDim.x) {
+    int a, b;
+    umma_col_pair(c, pl, a, b);
+    tab[2 * c] = (int16_t)a; tab[2 * c + 1] = (int16_t)b;
+  }
   __syncthreads();
   const int jg = (threadIdx.x & 31) * 4, sub = threadIdx.x >> 5;
-  for (int c = sub; c < pl.nch * pl.cpc; c += 4) {
+  const int nvalid = n - (j0 + jg);        // elements of this thread's group of four that exist
+  // grid.y CTAs share a column tile and take interleaved subsets of the product columns (more CTAs in flight).  The
+  // kernel is instruction-bound (6 nc bytes per factor row: 15 M elements per call at 65536 rows), hence: the scale as
+  // one multiplication by an exact power of two, one cvt.rni, and the 4 x 6 digit bytes transposed with byte permutes.
+  for (int c = sub + 4 * blockIdx.y; c < pl.nc; c += 4 * gridDim.y) {
     const int ch = c / pl.cpc, cl = c - ch * pl.cpc;
-    uint32_t w[UG_SLICES];
+    const int a = tab[2 * c], b = tab[2 * c + 1];
+    const double* xa = xs + (b == -1 ? (K + a) : a) * XS + jg;
+    const double* xb = b < 0 ? nullptr : xs + b * XS + jg;
+    const int sh = UG_TOP - cexp[c];
+    const bool fast = sh > -1000 && sh < 1000;
+    const double pw = fast ? __longlong_as_double((long long)(sh + 1023) << 52) : 0.0;   // 2^sh, exact
+    uint32_t lo[4], hi[4];
 #pragma unroll
-    for (int s = 0; s < UG_SLICES; ++s) w[s] = 0u;
-    if (c < pl.nc) {
-      int a, b;
-      umma_col_pair(c, pl, a, b);
-      const double* xa = xs + (b == -1 ? (K + a) : a) * XS + jg;
-      const double* xb = b < 0 ? nullptr : xs + b * XS + jg;
-      const int sh = UG_TOP - cexp[c];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (j0 + jg + i < n) {
-          const double p = xb ? xa[i] * xb[i] : xa[i];
-          long long q = llrint(scalbn(p, sh));
-          q = q > (1ll << UG_TOP) - 1 ? (1ll << UG_TOP) - 1 : (q < -(1ll << UG_TOP) ? -(1ll << UG_TOP) : q);   // rounding at the scale's edge
-          q += 1ll << UG_TOP;
-#pragma unroll
-          for (int s = 0; s < UG_SLICES; ++s) w[s] |= (uint32_t)((q >> (8 * s)) & 0xff) << (8 * i);
-        }
-      }
+    for (int i = 0; i < 4; ++i) {
+      const double p = xb ? xa[i] * xb[i] : xa[i];
+      long long q = fast ? __double2ll_rn(p * pw) : llrint(scalbn(p, sh));
+      q = q > (1ll << UG_TOP) - 1 ? (1ll << UG_TOP) - 1 : (q < -(1ll << UG_TOP) ? -(1ll << UG_TOP) : q);   // rounding at the scale's edge
+      const unsigned long long u = i < nvalid ? (unsigned long long)(q + (1ll << UG_TOP)) : 0ull;
+      lo[i] = (uint32_t)u; hi[i] = (uint32_t)(u >> 32);
     }
-    uint8_t* dst = Bd + ((size_t)ch * pl.nb + (size_t)cl * UG_SLICES) * ldb + j0 + jg;
+    uint32_t w[8];
+    {
+      const uint32_t a01 = __byte_perm(lo[0], lo[1], 0x5140), a23 = __byte_perm(lo[2], lo[3], 0x5140);
+      const uint32_t c01 = __byte_perm(lo[0], lo[1], 0x7362), c23 = __byte_perm(lo[2], lo[3], 0x7362);
+      const uint32_t e01 = __byte_perm(hi[0], hi[1], 0x5140), e23 = __byte_perm(hi[2], hi[3], 0x5140);
+      const uint32_t g01 = __byte_perm(hi[0], hi[1], 0x7362), g23 = __byte_perm(hi[2], hi[3], 0x7362);
+      w[0] = __byte_perm(a01, a23, 0x5410); w[1] = __byte_perm(a01, a23, 0x7632);
+      w[2] = __byte_perm(c01, c23, 0x5410); w[3] = __byte_perm(c01, c23, 0x7632);
+      w[4] = __byte_perm(e01, e23, 0x5410); w[5] = __byte_perm(e01, e23, 0x7632);
+      w[6] = __byte_perm(g01, g23, 0x5410); w[7] = __byte_perm(g01, g23, 0x7632);
+    }
+    uint8_t* dst = Bd + ((size_t)ch * UG_CHUNK_ROWS + (size_t)cl * UG_SLICES) * ldb + j0 + jg;
     if (j0 + jg < ldb) {
 #pragma unroll
       for (int s = 0; s < UG_SLICES; ++s) *reinterpret_cast<uint32_t*>(dst + (size_t)s * ldb) = w[s];
@@ -178,7 +215,7 @@ struct UmmaGramArgs {
   const double* cscale;
   double* Gout; double* SVout;
   int KP, gl;       // padded factor width, doubles per Gram record (NTP*64)
-  int stages;
+  int stages_of[2]; // pipeline depth of the full chunks / of the last chunk (its stages are smaller)
   int dbg;   // timing experiments only: 1 = skip TMA loads after the first fill, 2 = skip the A-tile stores
 };
 
@@ -187,14 +224,18 @@ struct UmmaGramArgs {
 // accumulator (the hardware reads the other half from the partner's shared memory), which halves the shared-memory
 // and L2 traffic per MMA -- the limit of the single-CTA form.
 template <int KT, bool PAIR>
-__global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_constant__ CUtensorMap tmap, UmmaGramArgs a) {
+__global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_constant__ CUtensorMap tmap_full,
+                                                            const __grid_constant__ CUtensorMap tmap_last, UmmaGramArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const UmmaPlan& pl = a.pl;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const int A_BYTES = UG_ROWS * KT, B_BYTES = (PAIR ? pl.n_half : pl.nb) * KT, STAGE = A_BYTES + B_BYTES;
-  const int stages = a.stages;
+  const int rb = blockIdx.x, ch = blockIdx.y, seg = blockIdx.z;
+  const int n_half = umma_nhalf_of(pl, ch), cpc = umma_cols_of(pl, ch);       // this chunk: UMMA N per accumulator, P-columns
+  const CUtensorMap& tmap = ch == pl.nch - 1 ? tmap_last : tmap_full;           // box height = this chunk's digit rows per load
+  const int A_BYTES = UG_ROWS * KT, B_BYTES = (PAIR ? n_half : 2 * n_half) * KT, STAGE = A_BYTES + B_BYTES;
+  const int stages = ch == pl.nch - 1 ? a.stages_of[1] : a.stages_of[0];    // (no dynamic index into the parameter struct)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);   // full[stages], empty[stages], accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
   int* cnt_smem = reinterpret_cast<int*>(tmem_slot + 2);           // [256]
@@ -205,7 +246,6 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(stages + (s)))
 #define ACCUM_BAR (bar_base + 8u * (uint32_t)(2 * stages))
 
-  const int rb = blockIdx.x, ch = blockIdx.y, seg = blockIdx.z;
   const int kt_begin = seg * a.tiles_per_seg;
   const int kt_end = min(a.ktiles, kt_begin + a.tiles_per_seg);
   const int ntile = kt_end - kt_begin;                 // >= 1 by construction of the grid
@@ -228,7 +268,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  for (int cl = tid; cl < pl.cpc; cl += UG_THREADS) {
+  for (int cl = tid; cl < cpc; cl += UG_THREADS) {
     const int c = ch * pl.cpc + cl;
     int pa = 0xff, pb = 0xfe;                          // 0xfe: column beyond nc (nothing to store)
     if (c < pl.nc) { int x, y; umma_col_pair(c, pl, x, y); pa = x; pb = y == -1 ? 0xff : (y == -2 ? 0xfd : y); }
@@ -305,33 +345,48 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     double* grow = a.Gout + ((size_t)seg * a.rows + (live ? row : 0)) * a.gl;
     double* srow = a.SVout ? a.SVout + ((size_t)seg * a.rows + (live ? row : 0)) * a.KP : nullptr;
     const int NT = a.KP >> 3;
-    for (int cl = half; cl < pl.cpc; cl += 2) {
-      uint32_t d[UG_SLICES];
+    // groups of 8 P-columns = 8 * kDigits consecutive tensor-memory columns, fetched with wide tcgen05.ld's (one
+    // round trip per group instead of one per column); the two threads of a row take alternate groups
+    constexpr int GRP = 8, GCOLS = GRP * UG_SLICES;            // 48 columns with six digits
+    static_assert(GCOLS % 16 == 0, "group width must be a multiple of the 16-column load");
+    for (int g0 = half * GRP; g0 < cpc; g0 += 2 * GRP) {
+      uint32_t d[GCOLS / 16][16];
 #pragma unroll
-      for (int s = 0; s < UG_SLICES; ++s) d[s] = tmem_ld1(tlane + (uint32_t)(cl * UG_SLICES + s));
-      tmem_ld_wait();
-      const uint32_t pr = pair_tab[cl];
-      const int pa = pr >> 8, pb = pr & 0xff;
-      if (!live || pb == 0xfe) continue;
-      // the top digit carries the +2^TOP offset of every summed term: 128 * 256^(SLICES-1) * cnt
-      const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
-      long long hi = 0;
-#pragma unroll
-      for (int s = 4; s < UG_SLICES; ++s)
-        hi += ((long long)(int)d[s] - (s == UG_SLICES - 1 ? 128ll * cnt : 0ll)) << (8 * (s - 4));
-      const double v = fma((double)hi, 4294967296.0, (double)lo) * a.cscale[ch * pl.cpc + cl];
-      if (pb == 0xff) {
-        if (srow) srow[pa] = v;
-      } else if (pb == 0xfd) {
-        // masked column sum of X_k: the slot (k, K) of the packed tiles, where the DMMA kernel's ones-column puts it
-        const int ta = pa >> 3, tb = pl.K >> 3;
-        grow[(ta * NT - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (pa & 7) * 8 + (pl.K & 7)] = v;
-      } else {
-        const int ta = pa >> 3, tb = pb >> 3;
-        const int p = ta * NT - ta * (ta - 1) / 2 + (tb - ta);
-        grow[p * 64 + (pa & 7) * 8 + (pb & 7)] = v;
-        if (ta == tb) grow[p * 64 + (pb & 7) * 8 + (pa & 7)] = v;
+      for (int q = 0; q < GCOLS / 16; ++q) {
+        // the last group of a chunk may reach past the chunk's accumulator columns but never past the 512 allocated
+        if (g0 * UG_SLICES + 16 * q + 16 <= 512) tmem_ld16(tlane + (uint32_t)(g0 * UG_SLICES + 16 * q), d[q]);
       }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < GRP; ++i) {
+        const int cl = g0 + i;
+        if (cl >= cpc || !live) break;
+        const uint32_t pr = pair_tab[cl];
+        const int pa = pr >> 8, pb = pr & 0xff;
+        if (pb == 0xfe) continue;
+#define DD(sl) d[(i * UG_SLICES + (sl)) / 16][(i * UG_SLICES + (sl)) % 16]
+        // the top digit carries the +2^TOP offset of every summed term: 128 * 256^(SLICES-1) * cnt
+        const long long lo = (long long)DD(0) + ((long long)DD(1) << 8) + ((long long)DD(2) << 16) + ((long long)DD(3) << 24);
+        long long hi = 0;
+#pragma unroll
+        for (int sl = 4; sl < UG_SLICES; ++sl)
+          hi += ((long long)(int)DD(sl) - (sl == UG_SLICES - 1 ? 128ll * cnt : 0ll)) << (8 * (sl - 4));
+#undef DD
+        const double v = fma((double)hi, 4294967296.0, (double)lo) * a.cscale[ch * pl.cpc + cl];
+        if (pb == 0xff) {
+          if (srow) srow[pa] = v;
+        } else if (pb == 0xfd) {
+          // masked column sum of X_k: the slot (k, K) of the packed tiles, where the DMMA kernel's ones-column puts it
+          const int ta = pa >> 3, tb = pl.K >> 3;
+          grow[(ta * NT - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (pa & 7) * 8 + (pl.K & 7)] = v;
+        } else {
+          const int ta = pa >> 3, tb = pb >> 3;
+          const int p = ta * NT - ta * (ta - 1) / 2 + (tb - ta);
+          grow[p * 64 + (pa & 7) * 8 + (pb & 7)] = v;
+          if (ta == tb) grow[p * 64 + (pb & 7) * 8 + (pa & 7)] = v;
+        }
+      }
+      __syncwarp();                                      // the next group's tcgen05.ld is warp-collective
     }
     if (live && ch == 0 && half == 0) {                  // |S(i)| in the (K, K) slot
       const int tk = pl.K >> 3;
@@ -351,15 +406,15 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
           // this CTA's half of the digit rows of each accumulator; the bytes of both CTAs are expected by the leader
           const uint32_t lead_full = mapa_u32(FULL_BAR(s), 0);
           if (rank == 0) mbar_expect_tx(FULL_BAR(s), 2u * (uint32_t)B_BYTES);
-          const int hh = pl.n_half >> 1;
-          tma_load_2d_pair(bdst, &tmap, x, ch * pl.nb + (int)rank * hh, lead_full);
-          tma_load_2d_pair(bdst + (uint32_t)hh * KT, &tmap, x, ch * pl.nb + pl.n_half + (int)rank * hh, lead_full);
+          const int hh = n_half >> 1;
+          tma_load_2d_pair(bdst, &tmap, x, ch * UG_CHUNK_ROWS + (int)rank * hh, lead_full);
+          tma_load_2d_pair(bdst + (uint32_t)hh * KT, &tmap, x, ch * UG_CHUNK_ROWS + n_half + (int)rank * hh, lead_full);
           continue;
         }
         if ((a.dbg & 1) && it >= stages) { mbar_arrive(FULL_BAR(s)); continue; }
         mbar_expect_tx(FULL_BAR(s), (uint32_t)B_BYTES);
-        tma_load_2d(bdst, &tmap, x, ch * pl.nb, FULL_BAR(s));
-        tma_load_2d(bdst + (uint32_t)pl.n_half * KT, &tmap, x, ch * pl.nb + pl.n_half, FULL_BAR(s));
+        tma_load_2d(bdst, &tmap, x, ch * UG_CHUNK_ROWS, FULL_BAR(s));
+        tma_load_2d(bdst + (uint32_t)n_half * KT, &tmap, x, ch * UG_CHUNK_ROWS + n_half, FULL_BAR(s));
       }
     }
     __syncwarp();
@@ -377,16 +432,16 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     if (rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, N = n_half,
       // M = 128 (256 for the CTA pair)
-      const uint32_t idesc = (2u << 4) | ((uint32_t)(pl.n_half >> 3) << 17) | ((uint32_t)((PAIR ? 2 * UG_ROWS : UG_ROWS) >> 4) << 24);
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(n_half >> 3) << 17) | ((uint32_t)((PAIR ? 2 * UG_ROWS : UG_ROWS) >> 4) << 24);
       // The whole warp runs this loop (convergent code keeps descriptors in uniform registers: with a single-lane
       // loop every tcgen05.mma needed five R2UR moves, ~150 dependent instructions per stage, and the issuing thread
       // itself limited the tensor pipe); only the tcgen05 instructions are predicated on one elected lane.  No
       // divisions, no clock reads, descriptors by addition.
       const uint64_t ad0 = umma_desc<KT>(smem_base);
       const uint64_t bd00 = umma_desc<KT>(smem_base + A_BYTES);
-      const uint64_t bd10 = umma_desc<KT>(smem_base + A_BYTES + (uint32_t)(PAIR ? pl.n_half >> 1 : pl.n_half) * KT);
+      const uint64_t bd10 = umma_desc<KT>(smem_base + A_BYTES + (uint32_t)(PAIR ? n_half >> 1 : n_half) * KT);
       const uint64_t dstep = (uint64_t)(STAGE >> 4);
-      const uint32_t tm1 = tmem_base + (uint32_t)pl.n_half;
+      const uint32_t tm1 = tmem_base + (uint32_t)n_half;
       int s = 0;
       uint32_t ph = 0;
       uint64_t soff = 0;
@@ -486,7 +541,7 @@ static size_t ws_digits_offset(const UmmaPlan& pl) {
 }
 
 static long long plan_workspace_bytes(const UmmaPlan& pl, long long ld) {
-  return (long long)ws_digits_offset(pl) + (long long)pl.nch * pl.nb * ld;
+  return (long long)ws_digits_offset(pl) + (long long)pl.nch * UG_CHUNK_ROWS * ld;
 }
 
 long long umma_workspace_bytes(int K, int vb, long long ld) {
@@ -522,21 +577,26 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   cudaMemsetAsync(colmax, 0, (size_t)pl.nc * 8, st);
   {
     const size_t sm = (size_t)(vb ? 2 : 1) * K * 65 * sizeof(double);
-    k_ug_colmax<<<(cols + 63) / 64, 256, sm, st>>>(Xp, Vp, cols, KP, pl, colmax);
+    int nbm = (cols + 63) / 64;
+    if (nbm > 296) nbm = 296;
+    k_ug_colmax<<<nbm, 256, sm, st>>>(Xp, Vp, cols, KP, pl, colmax);
     k_ug_scales<<<(pl.nc + 127) / 128, 128, 0, st>>>(colmax, pl.nc, cscale, cexp);
-    const size_t sq = (size_t)(vb ? 2 : 1) * K * 130 * sizeof(double);
+    const size_t sq = (size_t)(vb ? 2 : 1) * K * 130 * sizeof(double) + (size_t)pl.nc * 4;
     if (sq > 48 * 1024) cudaFuncSetAttribute(k_ug_quantize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sq);
-    k_ug_quantize<<<(ld + 127) / 128, 128, sq, st>>>(Xp, Vp, cols, KP, (long long)ld, pl, cexp, Bd);
+    k_ug_quantize<<<dim3((ld + 127) / 128, 4), 128, sq, st>>>(Xp, Vp, cols, KP, (long long)ld, pl, cexp, Bd);
   }
   if (check_launch("stats_gram_umma prepass")) return -1;
 
-  CUtensorMap tmap;
-  {
-    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)pl.nch * pl.nb};
+  // two tiled views of the digit matrix: the box height is the number of digit rows one load brings in, which differs
+  // between the full chunks (n_half = 256) and the last one
+  CUtensorMap tmaps[2];
+  for (int which = 0; which < 2; ++which) {
+    const int nh = which ? pl.nh_last : 256;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)pl.nch * UG_CHUNK_ROWS};
     const cuuint64_t gstr[1] = {(cuuint64_t)ld};
-    const cuuint32_t box[2] = {(cuuint32_t)kt, (cuuint32_t)(pair ? pl.n_half / 2 : pl.n_half)};
+    const cuuint32_t box[2] = {(cuuint32_t)kt, (cuuint32_t)(pair ? nh / 2 : nh)};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, Bd, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = encode(&tmaps[which], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, Bd, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               kt == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("stats_gram_umma: cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
@@ -549,21 +609,26 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   const int nseg_eff = (a.ktiles + a.tiles_per_seg - 1) / a.tiles_per_seg;
   if (nseg_eff != nseg) { set_error("stats_gram_umma: nseg=%d leaves empty segments (use <= %d)", nseg, nseg_eff); return -2; }
   a.pl = pl; a.cscale = cscale; a.Gout = Gout; a.SVout = SVout; a.KP = KP; a.gl = nt * (nt + 1) / 2 * 64;
-  const int stage_bytes = (UG_ROWS + (pair ? pl.n_half : pl.nb)) * kt;
   const int tail = (2 * 16 + 1) * 8 + 16 + UG_EXP_WARPS * 32 * 4 + 2 * pl.cpc + 64;
-  int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
-  if (stages > 16) stages = 16;
-  if (max_stages > 0 && stages > max_stages) stages = max_stages;
-  if (stages < 2) { set_error("stats_gram_umma: stage does not fit"); return -2; }
-  a.stages = stages;
+  size_t smem = 0;
+  for (int which = 0; which < 2; ++which) {
+    const int nh = which ? pl.nh_last : 256;
+    const int stage_bytes = (UG_ROWS + (pair ? nh : 2 * nh)) * kt;
+    int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
+    if (stages > 16) stages = 16;
+    if (max_stages > 0 && stages > max_stages) stages = max_stages;
+    if (stages < 2) { set_error("stats_gram_umma: stage does not fit"); return -2; }
+    a.stages_of[which] = stages;
+    const size_t need = (size_t)stages * stage_bytes + tail + 1024;
+    smem = need > smem ? need : smem;
+  }
   { const char* e = getenv("BNMTF_UMMA_DBG"); a.dbg = e ? atoi(e) : 0; }
   // > half of the SM's shared memory: one CTA per SM, so the 512-column tensor-memory allocation never waits
-  size_t smem = (size_t)stages * stage_bytes + tail + 1024;
   if (smem < 116 * 1024) smem = 116 * 1024;
   int rbs = (rows + UG_ROWS - 1) / UG_ROWS;
   if (pair) rbs = (rbs + 1) / 2 * 2;                   // a padding CTA (no live rows) completes the last pair
   dim3 grid(rbs, pl.nch, nseg);
-  void (*kern)(const CUtensorMap, UmmaGramArgs) =
+  void (*kern)(const CUtensorMap, const CUtensorMap, UmmaGramArgs) =
       kt == 128 ? (pair ? k_gram_umma<128, true> : k_gram_umma<128, false>) : (pair ? k_gram_umma<64, true> : k_gram_umma<64, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
@@ -572,7 +637,7 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmaps[0], tmaps[1], a);
   if (le != cudaSuccess) { set_error("stats_gram_umma: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return -1; }
   return check_launch("stats_gram_umma");
 }

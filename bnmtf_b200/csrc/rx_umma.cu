@@ -143,8 +143,12 @@ __global__ void __launch_bounds__(256) k_rxu_pack(const double* __restrict__ R, 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rxu_colmax(const double* __restrict__ Xp, int n, int K, int KP,
                                                    unsigned long long* __restrict__ colmax, int* __restrict__ flag) {
-  // thread <-> column k (threadIdx.x % 32 when K <= 32), rows strided
+  // thread <-> column k (threadIdx.x % 32 when K <= 32), rows strided; one atomic per (CTA, column): the eight row
+  // groups of a CTA are combined in shared memory first
+  __shared__ unsigned long long red[8][32];
+  __shared__ int bad_any;
   const int k = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  if (threadIdx.x == 0) bad_any = 0;
   unsigned long long m = 0ull;
   bool bad = false;
   if (k < K) {
@@ -154,9 +158,17 @@ __global__ void __launch_bounds__(256) k_rxu_colmax(const double* __restrict__ X
       const unsigned long long u = (unsigned long long)__double_as_longlong(fabs(v));
       m = u > m ? u : m;
     }
+  }
+  red[sub][k] = m;
+  __syncthreads();
+  if (bad) bad_any = 1;
+  __syncthreads();
+  if (sub == 0 && k < K) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = red[w][k] > m ? red[w][k] : m;
     atomicMax(colmax + k, m);
   }
-  if (bad) atomicOr(flag, 1);
+  if (threadIdx.x == 0 && bad_any) atomicOr(flag, 1);
 }
 
 __global__ void k_rxu_colscale(const unsigned long long* __restrict__ colmax, int K, int* __restrict__ cexp,
@@ -458,8 +470,8 @@ int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const doub
   uint8_t* Bd = ws + 1024;
 
   cudaMemsetAsync(ws, 0, 1024, st);
-  int nb = (cols + 7) / 8;
-  if (nb > 592) nb = 592;
+  int nb = (cols + 63) / 64;
+  if (nb > 296) nb = 296;
   k_rxu_colmax<<<nb, 256, 0, st>>>(Xp, cols, K, KP, colmax, flag);
   k_rxu_colscale<<<1, 32, 0, st>>>(colmax, K, cexp, cscale);
   const long long qthreads = (long long)(ld / 4) * KPAD;

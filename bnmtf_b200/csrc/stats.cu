@@ -281,12 +281,15 @@ __global__ void __launch_bounds__(256) k_gram_full(const double* __restrict__ Xp
   for (int i = threadIdx.x; i < OUT; i += 256) partial[(size_t)blockIdx.x * OUT + i] = red[i];
 }
 
-__global__ void k_sum_partials(const double* __restrict__ partial, int nparts, int len, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride over the partials, fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partial, int nparts, int len,
+                                                     double* __restrict__ out) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= len) return;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * len + i];
-  out[i] = s;
+  for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * len + i];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -330,20 +333,20 @@ int launch_stats_gram(const uint32_t* bits, int rows, int ld, const double* Xp, 
   return check_launch("stats_gram");
 }
 
-// out: NTP*64 Gram tiles followed by KP variance sums.  scratch: >= 64 * (NTP*64+KP) doubles.
+// out: NTP*64 Gram tiles followed by KP variance sums.  scratch: >= kGramFullParts * (NTP*64+KP) doubles.
 int launch_gram_full(const double* Xp, const double* Vp, int n, int K, int dummy_row, double* out, double* scratch,
                      cudaStream_t st) {
   const int nt = tiles_for(K);
   const int len = nt * (nt + 1) / 2 * 64 + 8 * nt;
   int nparts = (n + 255) / 256;
-  if (nparts > 64) nparts = 64;
+  if (nparts > kGramFullParts) nparts = kGramFullParts;
   if (nparts < 1) nparts = 1;
   if (Vp) {
     BNMTF_DISPATCH_NT(nt, (k_gram_full<NT, true><<<nparts, 256, 0, st>>>(Xp, Vp, n, K, dummy_row, scratch)));
   } else {
     BNMTF_DISPATCH_NT(nt, (k_gram_full<NT, false><<<nparts, 256, 0, st>>>(Xp, nullptr, n, K, dummy_row, scratch)));
   }
-  k_sum_partials<<<(len + 127) / 128, 128, 0, st>>>(scratch, nparts, len, out);
+  k_sum_partials<<<(len + 7) / 8, 256, 0, st>>>(scratch, nparts, len, out);
   return check_launch("gram_full");
 }
 

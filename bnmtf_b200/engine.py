@@ -430,7 +430,7 @@ class BNMFEngine:
                                 for ld in (dataset.ldJ, dataset.ldI))
             self.ws = torch.zeros(self.ws_bytes + 1024, dtype=torch.uint8, device=dev)
             self.ws_ptr = (self.ws.data_ptr() + 1023) // 1024 * 1024
-        self.gscratch = f64(64 * (GL + KP))
+        self.gscratch = f64(296 * (GL + KP))          # bnmtf_gram_full_f64: up to 296 partial results
         self.extra = f64(max(rI, rJ)) if self.vb else None
         self.red = f64(24)          # [0:8] metric sums, [8:16] factor ELBO terms, [16] VB extra term
         self.m8, self.el8, self.ex1, self.sums4 = self.red[0:8], self.red[8:16], self.red[16:17], self.red[17:21]

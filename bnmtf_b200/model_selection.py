@@ -179,22 +179,32 @@ class _Search:
                         best, best_ll = model, ll
                 out.append({m: best.quality(m, *qa) for m in metrics})
             return out
-        models = []
-        for p in points:
-            for _ in range(self.restarts):
-                with self.pool.on(len(models)):          # an engine created by initialise() lands on the job's device
-                    model = self._build(p)
-                _pin_seed(model)
-                models.append(model)
-        lls = self.pool.map(run, models)
-        for ip in range(len(points)):
-            best, best_ll = None, None
-            for r in range(self.restarts):
-                model, ll = models[ip * self.restarts + r], lls[ip * self.restarts + r]
-                if best is None or ll > best_ll:
-                    best, best_ll = model, ll
-            with _home(best):
-                out.append({m: best.quality(m, *qa) for m in metrics})
+        # Several devices: the fits of a WAVE (about one model per device) are built in the reference's order -- so the
+        # host random streams keep their positions -- run concurrently, summarised, and their engines released before the
+        # next wave is built: only one wave's copies of R / masks / digit planes are resident at a time.
+        per_wave = max(1, len(self.pool.devices) // self.restarts)
+        for w0 in range(0, len(points), per_wave):
+            wave = points[w0:w0 + per_wave]
+            models = []
+            for p in wave:
+                for _ in range(self.restarts):
+                    with self.pool.on(len(models)):      # an engine created by initialise() lands on the device map() will use
+                        model = self._build(p)
+                    _pin_seed(model)
+                    models.append(model)
+            lls = self.pool.map(run, models)
+            for ip in range(len(wave)):
+                best, best_ll = None, None
+                for r in range(self.restarts):
+                    model, ll = models[ip * self.restarts + r], lls[ip * self.restarts + r]
+                    if best is None or ll > best_ll:
+                        best, best_ll = model, ll
+                with _home(best):
+                    out.append({m: best.quality(m, *qa) for m in metrics})
+            for model in models:                                  # device buffers of this wave (host state stays)
+                if hasattr(model, '_eng'):
+                    model._eng = None
+                model.__dict__.pop('_samples', None)
         return out
 
     def all_values(self, metric):

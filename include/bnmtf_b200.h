@@ -137,7 +137,7 @@ int bnmtf_range_guard_f64(const double* Gpart, int nseg, int64_t rows, const dou
 int bnmtf_stats_gated_f64(const int32_t* run_flag, const double* R, const uint32_t* bits, int64_t rows, int64_t ld,
                           const double* Xp, const double* Vp /*or NULL*/, int K, int polarity, int nseg_rx, int nseg_gram,
                           double* RXpart /*or NULL*/, double* Gpart, double* SVpart /*or NULL*/, void* stream);
-/* scratch: >= 64 * (bnmtf_gram_len(K) + KP) doubles */
+/* scratch: >= 296 * (bnmtf_gram_len(K) + KP) doubles */
 int bnmtf_gram_full_f64(const double* Xp, const double* Vp /*or NULL*/, int64_t n, int K, int64_t dummy_row,
                         double* Gfull, double* scratch, void* stream);
 

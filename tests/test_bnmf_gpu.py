@@ -210,7 +210,7 @@ def test_tn_moments_in_the_tail_follow_scipys_erfc():
     lambda = pdf(x) / (0.5 erfc(x / sqrt 2)) by ~x^4, and SciPy's erfc (Cephes: exp(-a*a) * P/Q) carries up to 2e-13 of
     rounding from the product a*a.  The device reproduces that rounding (common.cuh: erfc_ref), so the moments agree
     with the reference's evaluation -- not just with the exact value -- right up to the 30-sigma switch:
-    5e-9 here (an exactly rounded erfc gives 1.3e-7, tools/gpu_debug3.py)."""
+    5e-9 here (an exactly rounded erfc gives 1.3e-7, measured in round 1)."""
     from bnmtf_b200 import distributions as D
     from oracle import bnmtf_oracle as orc
     rng = np.random.RandomState(11)
@@ -327,7 +327,7 @@ def test_vb_and_icm_against_the_oracle_on_fresh_inputs(models, I, J, K, frac):
     close(m.exptau, o.exptau), close(m.quality("ELBO"), o.elbo()), close(m.quality("BIC"), o.quality("BIC"))
     # factors: 1e-9, except the 64 x 1030 case, whose VB iteration doubles a perturbation every sweep: 3e-11 after one
     # sweep, 2e-8 after eight -- the same figures with the fp64 mma.sync statistics (BNMTF_GRAM=dmma BNMTF_RX=dmma) as
-    # with the tcgen05 fixed-point ones and with either solver (tools/fresh_debug.py), i.e. the conditioning of that
+    # with the tcgen05 fixed-point ones and with either solver (measured in round 1: BNMTF_GRAM=dmma BNMTF_RX=dmma give the same 2e-8), i.e. the conditioning of that
     # problem, not a property of a kernel.  Checked at 1e-7 there; its traces above still hold 1e-9
     ftol = 1e-7 if min(I, J) < 100 and max(I, J) > 1000 else 1e-9
     close(m.expU, o.U, rtol=ftol, what="expU"), close(m.expV, o.V, rtol=ftol, what="expV")

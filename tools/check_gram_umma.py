@@ -37,6 +37,8 @@ CASES = [
     (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 3),
     (65536, 32768, 20, 0, 0, 1, 128, 0, 3, 0, 2),
     (65536, 32768, 20, 1, 0, 1, 128, 0, 3, 0, 0),    # 19: VB row phase
+    (8192, 32768, 20, 0, 0, 3, 128, 0, 3, 0, 0),     # 20: one rank of 8, row phase (Gibbs)
+    (4096, 65536, 20, 1, 0, 3, 128, 0, 3, 1, 0),     # 21: one rank of 8, column phase (VB, with the column sums)
 ]
 
 
@@ -46,6 +48,8 @@ def run_case(idx):
     from bnmtf_b200 import _lib
     from bnmtf_b200.engine import _ptr, _stream, ld_for, kp_for, gram_len
     rows, cols, K, vb, pol, nseg, tile, signed, reps, sums, stages = CASES[idx]
+    if reps:
+        reps = int(os.environ.get("REPS", reps))
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + idx)
