@@ -10,6 +10,7 @@ sweep, csrc/nmtf.cu + csrc/solve.cu for the F / S / G updates on the row statist
 """
 import itertools
 import math
+import os
 import random
 
 import numpy as np
@@ -17,7 +18,7 @@ import torch
 
 from . import _lib
 from .bnmf import METRICS, QUALITY, _TwoFactorBase, _elbo_alpha_s_correction, _metrics_from_sums
-from .engine import (MODE, Dataset, Factor, Partition, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_TAU, _ptr, _stream, gram_len,
+from .engine import (MODE, Dataset, Factor, Partition, thread_flags, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_TAU, _ptr, _stream, gram_len,
                      kp_for, require_cuda)
 
 
@@ -39,6 +40,14 @@ class BNMTFEngine:
         self.scalars = f64(16)
         self.iter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.iter_scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+        # static device buffers for the per-sweep update orders (VB: the reference's shuffles) and the CUDA graph of a sweep:
+        # at these sizes a sweep is ~30 launches of a few microseconds each, i.e. bound by launch latency when issued eagerly
+        self.order_buf = {"S": torch.zeros(max(1, D), dtype=torch.int32, device=dev),
+                          "F": torch.zeros(self.K, dtype=torch.int32, device=dev),
+                          "G": torch.zeros(self.L, dtype=torch.int32, device=dev)}
+        self.use_graph = int(os.environ.get("BNMTF_GRAPH", "1")) >= 1
+        self._graph = self._graph_key = self._graph_seen = None
+        self._graph_kernels = 0
         self.trace, self.trace_cap, self.trace_base, self.sweeps_done = None, 0, 0, 0
         KPk, KPl, GLk, GLl = kp_for(self.K), kp_for(self.L), gram_len(self.K), gram_len(self.L)
         # statistics of the rows of R w.r.t. G (dimension L) and of the rows of R^T w.r.t. F (dimension K)
@@ -92,8 +101,12 @@ class BNMTFEngine:
 
     # ---- layer 2 ------------------------------------------------------------------------------------------
     def _order(self, order):
+        """order: None (natural order), a list of indices, or ("static", name): the engine's own buffer, filled by sweep()."""
         if order is None:
             return 0, None
+        if isinstance(order, tuple) and order[0] == "static":
+            t = self.order_buf[order[1]]
+            return _ptr(t), t
         t = torch.tensor([int(x) for x in order], dtype=torch.int32, device=self.ds.device)
         return _ptr(t), t
 
@@ -103,7 +116,7 @@ class BNMTFEngine:
                   _ptr(self.eff["RX"]), _ptr(self.eff["G"]), _ptr(self.eff["SV"]) if self.vb else 0, _stream())
         optr, keep = self._order(order)
         if order is not None:
-            n_order = len(order)
+            n_order = Ks if isinstance(order, tuple) else len(order)
         elif n_order is None:
             n_order = Ks
         if want_sterm:
@@ -132,7 +145,7 @@ class BNMTFEngine:
                   _ptr(self.row["G"]), _ptr(self.row["SV"]) if self.vb else 0, _ptr(self.row["full"]), _ptr(self.F.fac),
                   _ptr(self.F.var) if self.vb else 0, _ptr(self.sq_part), self.nparts, _ptr(self.sq_out), _stream())
         optr, keep = self._order(order)
-        n_order = D if order is None else len(order)
+        n_order = D if (order is None or isinstance(order, tuple)) else len(order)
         S = self.S
         base = self.sq_out.data_ptr()
         _lib.call("bnmtf_coord_solve_f64", self.m, D, base, base + 8 * D * D, base + 8 * (D * D + D), _ptr(S["lam"]),
@@ -192,7 +205,40 @@ class BNMTFEngine:
 
     def sweep(self, minimum_TN=0.0, order=None):
         """One iteration of run().  Gibbs / ICM: F, S, G (bnmtf_gibbs_optimised.py:152-166).  VB: S, F, G in the
-        host-supplied (shuffled) orders (bnmtf_vb_optimised.py:171-190)."""
+        host-supplied (shuffled) orders (bnmtf_vb_optimised.py:171-190).  The orders go into static device buffers, so the
+        launch sequence has fixed arguments and is replayed as a CUDA graph from the third sweep of a run on."""
+        static = None
+        if self.vb and order is not None and all(order.get(k) is not None for k in "SFG"):
+            for k in "SFG":
+                # pageable source: the runtime stages the bytes before returning, so the host may run sweeps ahead of the device
+                self.order_buf[k].copy_(torch.tensor([int(x) for x in order[k]], dtype=torch.int32))
+            static = {k: ("static", k) for k in "SFG"}
+            order = None
+        if self.use_graph and order is None and not getattr(thread_flags, "no_graph", False):
+            key = (self.trace.data_ptr() if self.trace is not None else 0, self.trace_base, self.trace_cap, float(minimum_TN),
+                   static is not None)
+            if self._graph is not None and self._graph_key == key:
+                self._graph.replay()
+                _lib.launch_count[0] += self._graph_kernels
+                self.sweeps_done += 1
+                return
+            if self._graph_seen == key:
+                g = torch.cuda.CUDAGraph()
+                done, count0 = self.sweeps_done, _lib.launch_count[0]
+                with torch.cuda.graph(g):
+                    self._sweep_eager(minimum_TN, static)          # captured, not executed
+                self._graph_kernels = _lib.launch_count[0] - count0
+                _lib.launch_count[0] = count0
+                self.sweeps_done = done
+                self._graph, self._graph_key = g, key
+                g.replay()
+                _lib.launch_count[0] += self._graph_kernels
+                self.sweeps_done += 1
+                return
+            self._graph_seen = key
+        self._sweep_eager(minimum_TN, static if static is not None else order)
+
+    def _sweep_eager(self, minimum_TN=0.0, order=None):
         if self.vb:
             oS, oF, oG = (order or {}).get("S"), (order or {}).get("F"), (order or {}).get("G")
             self.stats_rows()

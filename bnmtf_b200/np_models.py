@@ -57,6 +57,49 @@ class _NPEngine:
                   ds.ldJ, _ptr(self.part), self.nparts, _ptr(self.out8), _stream())
         return self.out8.cpu().numpy()
 
+    def sums_into(self, trace, row):
+        """The eight masked sums of the current prediction -> trace[row] on the device (no host round trip)."""
+        ds = self.ds
+        _lib.call("bnmtf_np_metrics_f64", _ptr(ds.R), _ptr(ds.bits), _ptr(self.P), ds.I, ds.J, ds.ldJ, _ptr(self.part),
+                  self.nparts, _ptr(trace, row), _stream())
+
+    def run_loop(self, iterations, body):
+        """iterations x body() with the per-iteration sums kept in a device trace and CUDA events for all_times; the launch
+        sequence of an iteration has fixed arguments except the trace row, which advances through a device-side
+        pointer table -- so it is captured once and replayed as a CUDA graph (these problems are launch-latency-bound).
+        Returns (trace as numpy, cumulative seconds per iteration)."""
+        import os
+        from .engine import thread_flags
+        dev = self.ds.device
+        trace = torch.zeros((max(1, iterations), 8), dtype=torch.float64, device=dev)
+        start = torch.cuda.Event(enable_timing=True)
+        marks = []
+        use_graph = int(os.environ.get("BNMTF_GRAPH", "1")) >= 1 and not getattr(thread_flags, "no_graph", False) and iterations >= 4
+        graph = None
+        start.record()
+        for it in range(iterations):
+            if use_graph and it >= 1:
+                # iterations 1.. write their sums to the scratch row out8; a tiny copy moves them to trace[it] afterwards
+                if graph is None:
+                    graph = torch.cuda.CUDAGraph()
+                    count0 = _lib.launch_count[0]
+                    with torch.cuda.graph(graph):
+                        body()
+                        self.sums_into(self.out8.view(1, 8), 0)
+                    self._graph_kernels = _lib.launch_count[0] - count0
+                    _lib.launch_count[0] = count0
+                graph.replay()
+                _lib.launch_count[0] += self._graph_kernels
+                trace[it].copy_(self.out8)
+            else:
+                body()
+                self.sums_into(trace, it)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
+        torch.cuda.synchronize()
+        return trace.cpu().numpy()[:iterations], [start.elapsed_time(ev) / 1e3 for ev in marks]
+
 
 class _NPBase(object):
     def _common_init(self, R, M, device):
@@ -111,14 +154,14 @@ class _NPBase(object):
             self.all_performances[metric] = []
         self.all_i_div = []
 
-    def _record(self, sums, iteration, time_start):
+    def _record(self, sums, iteration, seconds):
         perf = _metrics_from_sums(sums)
         for metric in self.metrics:
             self.all_performances[metric].append(perf[metric])
         self.all_i_div.append(float(sums[7]))
         if self.verbose:
             print("Iteration %s. I-divergence: %s. MSE: %s. R^2: %s. Rp: %s." % (iteration, sums[7], perf['MSE'], perf['R^2'], perf['Rp']))
-        self.all_times.append(time.time() - time_start)
+        self.all_times.append(seconds)
 
 
 class NMF(_NPBase):
@@ -143,14 +186,16 @@ class NMF(_NPBase):
         eng = self._engine()
         U, V = eng.dev(self.U), eng.dev(self.V)
         self._start_run()
-        time_start = time.time()
-        for it in range(1, iterations + 1):
+
+        def body():
             eng.build_pred(U, V)
             eng.row_update(U, V)
             eng.build_pred(U, V, transposed=True)
             eng.row_update(V, U, transposed=True)
             eng.build_pred(U, V)
-            self._record(eng.sums(), it, time_start)
+        trace, secs = eng.run_loop(iterations, body)
+        for it in range(iterations):
+            self._record(trace[it], it + 1, secs[it])
         self.U, self.V = U.cpu().numpy(), V.cpu().numpy()
 
     def train(self, iterations, init_UV='random', expo_prior=1.):
@@ -275,14 +320,16 @@ class NMTF(_NPBase):
             "F, S and G have not been initialised - please run NMTF.initialise() first."
         eng, F, S, G = self._state()
         self._start_run()
-        time_start = time.time()
         pairs = list(itertools.product(range(0, self.K), range(0, self.L)))
-        for it in range(1, iterations + 1):
+
+        def body():
             self._phase_S(eng, F, S, G, pairs)       # reference order: S, F, G (nmtf_np.py:129-136)
             self._phase_F(eng, F, S, G)
             self._phase_G(eng, F, S, G)
             eng.build_pred(self._mm(F, S, False), G)
-            self._record(eng.sums(), it, time_start)
+        trace, secs = eng.run_loop(iterations, body)
+        for it in range(iterations):
+            self._record(trace[it], it + 1, secs[it])
         self.F, self.S, self.G = F.cpu().numpy(), S.cpu().numpy(), G.cpu().numpy()
 
     def train(self, iterations, init_S='random', init_FG='random', expo_prior=1.):
