@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .bnmf import METRICS, QUALITY, _TwoFactorBase, _elbo_alpha_s_correction, _metrics_from_sums
-from .engine import (MODE, Dataset, Factor, Partition, thread_flags, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_TAU, _ptr, _stream, gram_len,
+from .engine import (MODE, Dataset, Factor, Partition, capture_graph, thread_flags, S_BETA_S, S_ELBO, S_ESD, S_LOGTAU, S_TAU, _ptr, _stream, gram_len,
                      kp_for, require_cuda)
 
 
@@ -222,11 +222,9 @@ class BNMTFEngine:
                 _lib.launch_count[0] += self._graph_kernels
                 self.sweeps_done += 1
                 return
-            if self._graph_seen == key:
-                g = torch.cuda.CUDAGraph()
+            if self._graph_seen == key and self.trace_cap >= 8:       # (a short run does not repay the capture)
                 done, count0 = self.sweeps_done, _lib.launch_count[0]
-                with torch.cuda.graph(g):
-                    self._sweep_eager(minimum_TN, static)          # captured, not executed
+                g = capture_graph(lambda: self._sweep_eager(minimum_TN, static))          # captured, not executed
                 self._graph_kernels = _lib.launch_count[0] - count0
                 _lib.launch_count[0] = count0
                 self.sweeps_done = done

@@ -25,6 +25,30 @@ TRACE_COLS = ("tau", "MSE", "R^2", "Rp", "ELBO", "sum_e2", "exp_square_diff", "e
 S_TAU, S_LOGTAU, S_ALPHA_S, S_BETA_S, S_SUM_E2, S_ESD, S_MSE, S_R2, S_RP, S_ELBO = range(10)
 
 
+_capture_streams = {}
+
+
+def capture_graph(body):
+    """Record the launches body() makes into a CUDA graph (not executed).  torch.cuda.graph() would do the same after a
+    device synchronisation, gc.collect() and empty_cache() -- tens of milliseconds, which is longer than a whole toy-size
+    run; here only the stream switch capture needs (a side stream per device, ordered after the current one)."""
+    dev = torch.cuda.current_device()
+    side = _capture_streams.get(dev)
+    if side is None:
+        side = _capture_streams[dev] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        g.capture_begin()
+        try:
+            body()
+        finally:
+            g.capture_end()
+    main.wait_stream(side)
+    return g
+
+
 def require_cuda(device=None):
     if not torch.cuda.is_available():
         raise _lib.BnmtfError("no CUDA device visible: bnmtf_b200 has no CPU path")
@@ -692,11 +716,9 @@ class BNMFEngine:
                 _lib.launch_count[0] += self._graph_kernels       # a replay launches every kernel node of the capture
                 self.sweeps_done += 1
                 return
-            if self._graph_seen == key:
-                g = torch.cuda.CUDAGraph()
+            if self._graph_seen == key and self.trace_cap >= 8:       # (a short run does not repay the capture)
                 done, count0 = self.sweeps_done, _lib.launch_count[0]
-                with torch.cuda.graph(g):
-                    self._sweep_eager(minimum_TN)          # captured, not executed
+                g = capture_graph(lambda: self._sweep_eager(minimum_TN))          # captured, not executed
                 self._graph_kernels = _lib.launch_count[0] - count0
                 _lib.launch_count[0] = count0
                 self.sweeps_done = done

@@ -69,23 +69,24 @@ class _NPEngine:
         pointer table -- so it is captured once and replayed as a CUDA graph (these problems are launch-latency-bound).
         Returns (trace as numpy, cumulative seconds per iteration)."""
         import os
-        from .engine import thread_flags
+        from .engine import capture_graph, thread_flags
         dev = self.ds.device
         trace = torch.zeros((max(1, iterations), 8), dtype=torch.float64, device=dev)
         start = torch.cuda.Event(enable_timing=True)
         marks = []
-        use_graph = int(os.environ.get("BNMTF_GRAPH", "1")) >= 1 and not getattr(thread_flags, "no_graph", False) and iterations >= 4
+        use_graph = int(os.environ.get("BNMTF_GRAPH", "1")) >= 1 and not getattr(thread_flags, "no_graph", False) and iterations >= 8
         graph = None
         start.record()
         for it in range(iterations):
             if use_graph and it >= 1:
                 # iterations 1.. write their sums to the scratch row out8; a tiny copy moves them to trace[it] afterwards
                 if graph is None:
-                    graph = torch.cuda.CUDAGraph()
                     count0 = _lib.launch_count[0]
-                    with torch.cuda.graph(graph):
+
+                    def captured():
                         body()
                         self.sums_into(self.out8.view(1, 8), 0)
+                    graph = capture_graph(captured)
                     self._graph_kernels = _lib.launch_count[0] - count0
                     _lib.launch_count[0] = count0
                 graph.replay()

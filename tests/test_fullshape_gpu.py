@@ -123,7 +123,7 @@ def test_vb_sweeps_at_the_headline_configuration(dataset):
     np.random.seed(21)
     m.initialise("random")
     eng = m._push()
-    eng.alloc_trace(3)
+    eng.alloc_trace(8)                        # (runs shorter than 8 sweeps are not captured as a graph)
     rng = np.random.RandomState(5)
     ri = np.sort(np.concatenate([rng.choice(I, 40, replace=False), [0, 127, 128, I - 1]]))      # incl. block edges, last (ragged) block
     cj = np.sort(np.concatenate([rng.choice(J, 40, replace=False), [0, 4127, 4128, J - 1]]))    # incl. the segment seam
