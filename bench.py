@@ -3,7 +3,7 @@
 (BASELINE.json config 4).  One JSON line on stdout; see DESIGN.md section "Measurement".
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows I --cols J --K K]
-                    [--workload sweep|cv|small]
+                    [--workload sweep|cv|small|nmtf]
 
 A "step" is one Gibbs sweep plus one VB sweep (all U columns, all V columns, tau, train metrics each);
 value = sweeps per second over both.  N>1 (torchrun): rows of R / R^T are sharded across ranks
@@ -14,7 +14,8 @@ from baseline/_ref when that copy exists, else the oracle port) run the same 409
 seeded 'random' start, and the largest relative differences of factors, MSE, ELBO and tau are printed.  The CPU side
 of that run is also the cpu_baseline sample.
 
---workload cv / small: the replica decomposition (independent fits, one per GPU) -- see bench_replicas.py.
+--workload cv / small: the replica decomposition (independent fits, one per GPU); --workload nmtf: the tri-factorisation
+at the headline shape -- see bench_replicas.py.
 """
 import argparse
 import contextlib
@@ -500,7 +501,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "cv", "small"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "cv", "small", "nmtf"])
     ap.add_argument("--rows", type=int, default=65536)
     ap.add_argument("--cols", type=int, default=32768)
     ap.add_argument("--K", type=int, default=20)

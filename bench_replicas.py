@@ -16,7 +16,14 @@ small  the reference's own timing experiments (plots/time_toy, plots/time_Sanger
        the other; a STEP is one pass over that list; value = problem-iterations/s summed over ranks (every rank runs
        its own chains: "weak"), iterations/s per problem beside it.
 
-Both legs time the reference's own classes (baseline/_ref) on the host cores for a bounded sample of the same work
+nmtf   the tri-factorisation at the headline shape (SURVEY.md section 8d "NMTF at C4-like sizes"; north-star (2)):
+       BNMTF Gibbs + VB sweeps on the synthetic 65536 x 32768, 20 %-missing matrix with K = L = 10.  Its statistics
+       passes are the two-factor model's tcgen05 kernels (the statistics of R ~ F S G^T w.r.t. G and w.r.t. F are
+       two-factor statistics); the K*L sequential S updates run on the (KL x KL) normal equations reduced over rows.
+       A STEP is one Gibbs + one VB sweep; value = sweeps/s (every rank its own chains at N > 1: "weak").  The line
+       carries a parity block: GPU classes with the tcgen05 statistics forced vs the reference's classes at 2048 x 1024.
+
+All legs time the reference's own classes (baseline/_ref) on the host cores for a bounded sample of the same work
 (`cpu_baseline`, rank 0 only); `--impl reference` prints that as the reference arm.
 """
 import contextlib
@@ -163,6 +170,124 @@ def cpu_small(its_sample=20):
     return out, (time.process_time() - c0) / max(1e-9, time.time() - w0)
 
 
+def nmtf_parity(K, L, shape=(2048, 1024)):
+    """GPU tri-factor classes (tcgen05 statistics forced) vs the reference's classes from the same seeded starts."""
+    import bench
+    import bnmtf_b200
+    ref = reference_models()
+    I, J = shape
+    R, M = bench.sample_problem(I, J, max(K, L))
+    R = np.abs(R) + 0.5
+    out = {"problem": "%dx%d, K=%d, L=%d, 20%% missing, seeded 'random' starts, BNMTF_NMTF_STATS=umma" % (I, J, K, L),
+           "checker": "reference classes (baseline/_ref)" if ref is not None else None}
+    if ref is None:
+        return out
+    os.environ["BNMTF_NMTF_STATS"] = "umma"
+    try:
+        worst = 0.0
+        for name, gcls, rcls, its in (("vb", bnmtf_b200.bnmtf_vb_optimised, ref.bnmtf_vb_optimised, 2),
+                                      ("icm", bnmtf_b200.nmtf_icm, ref.nmtf_icm, 2)):
+            res = []
+            for cls in (gcls, rcls):
+                np.random.seed(31), random.seed(31)
+                m = cls(R, M, K, L, priors3())
+                with quiet():
+                    m.initialise("random", "random")
+                    m.run(its) if name == "vb" else m.run(its, minimum_TN=0.1)
+                res.append(m)
+            g, r = res
+            if name == "vb":
+                assert g._engine().stats_impl == "umma"
+                d = {"max_rel_factors": max(bench.rel_err(g.expF, r.expF), bench.rel_err(g.expS, r.expS), bench.rel_err(g.expG, r.expG)),
+                     "max_rel_mse": max(abs(a / b - 1.0) for a, b in zip(g.all_performances["MSE"], r.all_performances["MSE"])),
+                     "max_rel_exptau": abs(g.exptau / r.exptau - 1.0)}
+            else:
+                d = {"max_rel_factors": max(bench.rel_err(g.F, r.F), bench.rel_err(g.S, r.S), bench.rel_err(g.G, r.G)),
+                     "max_rel_mse": max(abs(a / b - 1.0) for a, b in zip(g.all_performances["MSE"], r.all_performances["MSE"])),
+                     "max_rel_tau": abs(g.tau / r.tau - 1.0)}
+            out[name] = d
+            worst = max(worst, *d.values())
+        out["worst"], out["tolerance"], out["pass"] = worst, 1e-9, bool(worst <= 1e-9)
+    finally:
+        del os.environ["BNMTF_NMTF_STATS"]
+    return out
+
+
+def run_nmtf(args, rank, world, device, dist, barrier, max_over_ranks, sum_over_ranks, sampler, line):
+    import torch
+    import bench
+    from bnmtf_b200 import _lib, bnmtf, engine
+    I, J, K = args.rows, args.cols, 10
+    R, bits, n_obs = bench.make_synthetic(I, J, K, device)
+    ds = engine.Dataset.from_device(R, bits, I, J, n_obs=n_obs)
+    models = {}
+    for i, (mode, cls) in enumerate((("gibbs", bnmtf.bnmtf_gibbs_optimised), ("vb", bnmtf.bnmtf_vb_optimised))):
+        m = cls.from_dataset(ds, K, K, priors3(), seed=1)
+        np.random.seed(1 + i), random.seed(1 + i)
+        m.initialise("random", "random")
+        m._push()
+        models[mode] = m
+    engs = {k: m._engine() for k, m in models.items()}
+    for e in engs.values():
+        e.alloc_trace(args.warmup + args.steps + 8)
+    for _ in range(args.warmup):
+        for e in engs.values():
+            e.sweep()
+    barrier()
+    sampler.start()
+    l0 = _lib.launch_count[0]
+    ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in engs}
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k, e in engs.items():
+        ev[k][0].record()
+        for _ in range(args.steps):
+            e.sweep()
+        ev[k][1].record()
+    t1.record()
+    barrier()
+    total_ms = max_over_ranks(t0.elapsed_time(t1))
+    launches = sum_over_ranks(_lib.launch_count[0] - l0)
+    sampler.stop_flag = True
+    ms = {k: ev[k][0].elapsed_time(ev[k][1]) for k in engs}
+    sc = {k: e.scalars.cpu().numpy() for k, e in engs.items()}
+    N = float(I) * J
+    hbm, kind = bench.measured_peaks()
+    sweep_s = total_ms / 1e3 / (2.0 * args.steps)
+    b_alg = 2.0 * N * 8.125 + N * 8.125          # F and G phases stream R once each (as BNMF) + the prediction metrics pass
+    line.update({"metric": "BNMTF Gibbs+VB sweeps/sec at %dx%d K=L=%d" % (I, J, K), "value": world * 2.0 * args.steps / (total_ms / 1e3),
+                 "unit": "sweeps/s", "ms_per_step": total_ms / (2.0 * args.steps), "scaling": "weak",
+                 "dtype": bench.DTYPE, "data": "synthetic",
+                 "config": {"workload": "BNMTF Gibbs+VB sweep (F, S, G, tau, train metrics), %dx%d fp64, 20%% missing, K=L=%d; "
+                                        "every rank its own chains" % (I, J, K),
+                            "stats_kernels": engs["vb"].stats_impl, "gibbs_sweeps_per_s": args.steps / (ms["gibbs"] / 1e3),
+                            "vb_sweeps_per_s": args.steps / (ms["vb"] / 1e3),
+                            "train_MSE_after": {k: float(v[engine.S_MSE]) for k, v in sc.items()},
+                            "l2": "inputs (2 x %.1f GiB of digit planes + one 16 GiB pass for the metrics per sweep) far larger than L2" % (N * 6 / 2 ** 30)},
+                 "roofline": {"bound": "hbm", "kernel": "whole sweep (two statistics phases on the tcgen05 kernels + the direct metrics pass)",
+                              "achieved": b_alg / sweep_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": b_alg / sweep_s / 1e9 / hbm,
+                              "traffic": None, "algorithmic_bytes_per_sweep": b_alg, "peak_kind": kind},
+                 "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary()})
+    # end to end: run(1) through the class API (host state in and out)
+    if not args.no_e2e:
+        for m in models.values():
+            m.run(1)
+        barrier()
+        w0 = time.time()
+        for m in models.values():
+            for _ in range(max(3, args.steps // 4)):
+                m.run(1)
+        barrier()
+        dt = max_over_ranks(time.time() - w0)
+        line["e2e"] = {"value": world * 2.0 * max(3, args.steps // 4) / dt, "unit": "sweeps/s",
+                       "h2d_bytes_per_step": int((I + J) * K * 8 * 3.5), "d2h_bytes_per_step": int((I + J) * K * 8 * 3),
+                       "note": "model.run(1) per step: factor state uploaded from host numpy, one sweep, state read back"}
+    del models, engs, ds, R, bits
+    torch.cuda.empty_cache()
+    if rank == 0 and not args.no_parity:
+        line["parity"] = nmtf_parity(6, 5)
+
+
 # ------------------------------------------------------------------------------------------------------
 def main(args, rank, world):
     if args.impl == "reference":
@@ -204,7 +329,9 @@ def main(args, rank, world):
             "dtype": "f64 (fp64 kernels throughout: the toy / GDSC shapes use the fp64 statistics kernels of the tri-factor "
                      "engine and, for the two-factor models, the tcgen05 fixed-point ones)",
             "data": "the reference's own matrices (toy 100x80, GDSC 622x138) as stored in tests/golden/*.npz"}
-    if args.workload == "cv":
+    if args.workload == "nmtf":
+        run_nmtf(args, rank, world, device, dist, barrier, max_over_ranks, sum_over_ranks, sampler, line)
+    elif args.workload == "cv":
         R, folds_train, folds_test, jobs = cv_jobs()
         todo = jobs[:args.warmup + args.steps] if args.warmup + args.steps <= len(jobs) else \
             [jobs[i % len(jobs)] for i in range(args.warmup + args.steps)]

@@ -66,6 +66,24 @@ class BNMTFEngine:
         self.mpart = f64(((I + 127) // 128) * self.nseg_m * 8)
         self.nb_terms = 32
         self.elpart = f64(3 * self.nb_terms * 8)
+        # Statistics kernels: the fp64 mma.sync ones at toy / GDSC sizes (latency-bound there, fewer launches), the tcgen05
+        # fixed-point ones of the two-factor engine for large matrices (BNMTF_NMTF_STATS=umma|dmma overrides).  A dataset
+        # with outlier rows (Dataset.wide) keeps fp64; the per-phase dynamic-range guard of the two-factor engine is not
+        # wired into the tri-factor kernels.
+        want = os.environ.get("BNMTF_NMTF_STATS", "umma" if I * J >= (1 << 22) else "dmma")
+        self.stats_impl = "dmma"
+        if want == "umma" and max(self.K, self.L) <= 32:
+            for side in (0, 1):
+                ds.ensure_planes(side)
+            if not any(ds.wide.values()):
+                self.stats_impl = "umma"
+                self.wsrx_bytes = max(_lib.call("bnmtf_rx_umma_workspace_bytes", d, ld) for d, ld in ((self.L, ds.ldJ), (self.K, ds.ldI)))
+                self.wsrx = torch.zeros(self.wsrx_bytes + 1024, dtype=torch.uint8, device=dev)
+                self.wsrx_ptr = (self.wsrx.data_ptr() + 1023) // 1024 * 1024
+                self.ws_bytes = max(_lib.call("bnmtf_gram_umma_workspace_bytes", d, int(self.vb), ld)
+                                    for d, ld in ((self.L, ds.ldJ), (self.K, ds.ldI)))
+                self.ws = torch.zeros(self.ws_bytes + 1024, dtype=torch.uint8, device=dev)
+                self.ws_ptr = (self.ws.data_ptr() + 1023) // 1024 * 1024
         self.statics = f64(3)
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(ds.bits), I, ds.ldJ, _ptr(self.FS.Xp), _ptr(self.G.Xp),
                   self.L, self.nseg_m, 0, _ptr(self.mpart), _ptr(self.m8), 0, _stream())
@@ -86,6 +104,19 @@ class BNMTFEngine:
         if self.polarity == 0:
             _lib.call("bnmtf_gram_full_f64", _ptr(other.Xp), _ptr(other.Vp), other.n, dim, ld, _ptr(st["full"]),
                       _ptr(self.gscratch), _stream())
+        if self.stats_impl == "umma":
+            # the two-factor model's tcgen05 kernels (exact fixed-point int8 GEMMs, csrc/rx_umma.cu, csrc/gram_umma.cu): the
+            # statistics of the tri-factorisation ARE two-factor statistics w.r.t. G (rows) and F (columns); one segment,
+            # because the transform / S-reduction kernels read one record per row
+            side = 0 if R is self.ds.R else 1
+            if need_rx:
+                planes, rscale = self.ds.ensure_planes(side)[:2]
+                _lib.call("bnmtf_stats_rx_umma_f64", planes.data_ptr(), _ptr(rscale), _ptr(R), _ptr(bits), rows, ld, other.n,
+                          _ptr(other.Xp), dim, 1, 0, _ptr(st["RX"]), self.wsrx_ptr, self.wsrx_bytes, _stream())
+            _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, other.n, _ptr(other.Xp), _ptr(other.Vp), dim,
+                      self.polarity, 1, 128 if ld >= 256 else 64, 1, 0, 0, _ptr(st["G"]), _ptr(st["SV"]) if self.vb else 0,
+                      self.ws_ptr, self.ws_bytes, _stream())
+            return
         if need_rx:
             _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), dim, 1, _ptr(st["RX"]), _stream())
         _lib.call("bnmtf_stats_gram_f64", _ptr(bits), rows, ld, _ptr(other.Xp), _ptr(other.Vp), dim, self.polarity, 1,
@@ -301,6 +332,24 @@ class _ThreeFactorBase(object):
         assert self.lambdaG.shape == (self.J, self.L), "Prior matrix lambdaG has the wrong shape: %s instead of (%s, %s)." % (self.lambdaG.shape, self.J, self.L)
         self._device_arg, self._seed, self._eng = device, seed, None
         self.verbose = False
+
+    @classmethod
+    def from_dataset(cls, dataset, K, L, priors, seed=None):
+        """Build a model on an engine.Dataset that already lives on the GPU (matrices too large for, or never present in,
+        host memory).  R and M stay None on the host, so init_FG='kmeans' (a host algorithm on R) is not available."""
+        self = cls.__new__(cls)
+        self.R = self.M = None
+        self.K, self.L = K, L
+        (self.I, self.J) = (dataset.I, dataset.J)
+        self.size_Omega = float(dataset.n_obs)
+        self.alpha, self.beta = float(priors['alpha']), float(priors['beta'])
+        for name, shape in (('lambdaF', (self.I, K)), ('lambdaS', (K, L)), ('lambdaG', (self.J, L))):
+            lam = np.array(priors[name], dtype=float)
+            setattr(self, name, lam * np.ones(shape) if lam.shape == () else lam)
+        self._device_arg, self._seed, self.verbose = dataset.device, seed, False
+        self._eng = BNMTFEngine(dataset, K, L, cls._mode, self.alpha, self.beta,
+                                seed=seed if seed is not None else _lib.derive_seed())
+        return self
 
     def _engine(self):
         if self._eng is None:
