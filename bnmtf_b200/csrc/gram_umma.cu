@@ -33,10 +33,12 @@ constexpr int UG_SLICES = kDigits;          // bytes per product column (common.
 constexpr int UG_TOP = 8 * UG_SLICES - 1;    // products are stored as llrint(P 2^(TOP-e)) + 2^TOP, 2^e > max|P|
 constexpr int UG_ROWS = 128;     // rows per CTA = UMMA M
 constexpr int UG_EXP_WARPS = 8;   // mask-expander / epilogue warps (two threads per row)
-constexpr int UG_THREADS = (UG_EXP_WARPS + 2) * 32;
+constexpr int UG_THREADS = (UG_EXP_WARPS + 3) * 32;   // + TMA producer of the digit tiles, MMA issuer, TMA producer of the mask windows
+constexpr int UG_MASK_BUFS = 3;      // mask windows in flight
 
 struct UmmaPlan {
-  int K, vb, sums;
+  int K, vb, sums, sp;
+  int nh_full;  // UMMA N of each accumulator of a full chunk (256; 240 in the 2:4-sparse form, which keeps 32 columns for the metadata)
   int ng;       // K(K+1)/2 Gram columns
   int nc;       // ng (+K variance columns) (+K plain columns X_jk: masked column sums, for the metrics)
   int nch;      // chunks: all but the last hold cpc P-columns in two accumulators of 256 tensor-memory columns
@@ -46,25 +48,27 @@ struct UmmaPlan {
   int gran;
 };
 constexpr int UG_CHUNK_ROWS = 512;   // digit rows reserved per chunk in the staged B matrix
+constexpr int UG_SP_ACC_COLS = 480;  // 2:4-sparse form: tensor-memory columns of the accumulators; [480, 512) hold the metadata
 
 // Chunks are UNEVEN: 210 products x 6 digits = 1260 digit columns run as 512 + 512 + 256 tensor-memory columns (three
 // equal chunks of 70 products would need 3 x 448; with the K column sums / VB variances 3 x 512 instead of 512 + 512 +
 // 384): the MMA work follows the columns actually needed.
-__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums, int pair) {
+__host__ __device__ inline UmmaPlan make_umma_plan(int K, int vb, int sums, int pair, int sp = 0) {
   UmmaPlan p;
-  p.K = K; p.vb = vb; p.sums = sums;
+  p.K = K; p.vb = vb; p.sums = sums; p.sp = sp;
   p.ng = K * (K + 1) / 2;
   p.nc = p.ng + (vb ? K : 0) + (sums ? K : 0);
-  p.cpc = 512 / UG_SLICES;                   // 85 (73 with seven digits)
+  p.cpc = (sp ? UG_SP_ACC_COLS : 512) / UG_SLICES;      // 85 (73 with seven digits); sparse: 80 (68)
+  p.nh_full = ((p.cpc * UG_SLICES + 1) / 2 + 15) / 16 * 16;
   p.nch = (p.nc + p.cpc - 1) / p.cpc;
   p.cpc_last = p.nc - (p.nch - 1) * p.cpc;
-  p.gran = pair ? 32 : 16;                   // UMMA N granularity (CTA pair: each CTA holds n_half/2 digit rows)
+  p.gran = (pair && !sp) ? 32 : 16;          // UMMA N granularity (CTA pair: each CTA holds n_half/2 digit rows)
   const int nd = p.cpc_last * UG_SLICES;
   p.nh_last = ((nd + 1) / 2 + p.gran - 1) / p.gran * p.gran;
   return p;
 }
 __host__ __device__ inline int umma_cols_of(const UmmaPlan& p, int ch) { return ch == p.nch - 1 ? p.cpc_last : p.cpc; }
-__host__ __device__ inline int umma_nhalf_of(const UmmaPlan& p, int ch) { return ch == p.nch - 1 ? p.nh_last : 256; }
+__host__ __device__ inline int umma_nhalf_of(const UmmaPlan& p, int ch) { return ch == p.nch - 1 ? p.nh_last : p.nh_full; }
 
 // column c of P  ->  (a, b) with a <= b < K: X_a X_b;  (k, -1): Var_k;  (k, -2): X_k
 __host__ __device__ inline void umma_col_pair(int c, const UmmaPlan& pl, int& a, int& b) {
@@ -208,6 +212,22 @@ __global__ void __launch_bounds__(128) k_ug_quantize(const double* __restrict__ 
   }
 }
 
+// 2:4 split of 32 selection bits = eight groups of four columns (one nibble each, computed for all eight at once).
+// Per group: idx0 < idx1 are the positions of the first two selected columns (idx1 = 3 / idx0 = 0 when there are
+// fewer), v0 / v1 (bit 4g) say whether the column at idx0 / idx1 is selected, meta holds idx0 | idx1 << 2 in nibble g.
+// Returns the selected columns that do NOT fit (the third and fourth of a group): the fix-up kernel's share.
+__host__ __device__ __forceinline__ uint32_t sparse_split(uint32_t v, uint32_t& v0, uint32_t& v1, uint32_t& meta) {
+  const uint32_t m = 0x11111111u;
+  const uint32_t b0 = v & m, b1 = (v >> 1) & m, b2 = (v >> 2) & m, b3 = (v >> 3) & m;
+  const uint32_t c1 = b0 & b1;              // second selected column at position 1
+  const uint32_t c2 = (b0 ^ b1) & b2;       // ... at position 2
+  const uint32_t i0b0 = b1 & ~b0, i0b1 = b2 & ~(b0 | b1);
+  meta = i0b0 | (i0b1 << 1) | ((m & ~c2) << 2) | ((m & ~c1) << 3);
+  v0 = b0 | b1 | b2;
+  v1 = c1 | c2 | (b3 & ~(c1 | c2));
+  return ((c1 & b2) << 2) | ((b3 & (c1 | c2)) << 3);
+}
+
 struct UmmaGramArgs {
   const uint32_t* bits; int rows, wpr, cols, polarity;
   int ktiles, tiles_per_seg;
@@ -215,6 +235,7 @@ struct UmmaGramArgs {
   const double* cscale;
   double* Gout; double* SVout;
   int KP, gl;       // padded factor width, doubles per Gram record (NTP*64)
+  int mask_tma;     // mask words arrive through TMA windows (needs ld % 128 == 0: a 16-byte row pitch); else direct loads
   int stages_of[2]; // pipeline depth of the full chunks / of the last chunk (its stages are smaller)
   int dbg;   // timing experiments only: 1 = skip TMA loads after the first fill, 2 = skip the A-tile stores
 };
@@ -223,9 +244,18 @@ struct UmmaGramArgs {
 // instruction of M = 256: each CTA expands its own 128 mask rows and loads only HALF of the digit rows of each
 // accumulator (the hardware reads the other half from the partner's shared memory), which halves the shared-memory
 // and L2 traffic per MMA -- the limit of the single-CTA form.
-template <int KT, bool PAIR>
+//
+// SP: the 2:4-sparse form (tcgen05.mma.sp).  W is the 0/1 indicator of a set that holds ~20 % of the entries, so in
+// most groups of four consecutive columns at most two are selected: the A operand is stored compressed (two value
+// bytes per group of four columns, 64 bytes per row and 128-column stage) with its metadata (two 2-bit column indices
+// per group, idx0 < idx1) in tensor memory -- lane = row, one 32-bit column per 32 logical columns, written by the
+// expander threads with tcgen05.st -- and one MMA covers K = 64 logical columns in the time of a dense K = 32.  The
+// third and fourth selected entries of a group (0.7 % of the entries at 20 %) are left out here (sparse_overflow()
+// is the rule) and added by k_gram_fixup as one more segment of the partial statistics.
+template <int KT, bool PAIR, bool SP>
 __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_constant__ CUtensorMap tmap_full,
-                                                            const __grid_constant__ CUtensorMap tmap_last, UmmaGramArgs a) {
+                                                            const __grid_constant__ CUtensorMap tmap_last,
+                                                            const __grid_constant__ CUtensorMap tmap_bits, UmmaGramArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -234,10 +264,18 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   const int rb = blockIdx.x, ch = blockIdx.y, seg = blockIdx.z;
   const int n_half = umma_nhalf_of(pl, ch), cpc = umma_cols_of(pl, ch);       // this chunk: UMMA N per accumulator, P-columns
   const CUtensorMap& tmap = ch == pl.nch - 1 ? tmap_last : tmap_full;           // box height = this chunk's digit rows per load
-  const int A_BYTES = UG_ROWS * KT, B_BYTES = (PAIR ? n_half : 2 * n_half) * KT, STAGE = A_BYTES + B_BYTES;
+  constexpr int AKT = SP ? KT / 2 : KT;                 // bytes per row of an A tile
+  static_assert(!SP || KT == 128, "the sparse form runs 128-column stages");
+  const int A_BYTES = UG_ROWS * AKT, B_BYTES = (PAIR ? n_half : 2 * n_half) * KT, STAGE = A_BYTES + B_BYTES;
   const int stages = ch == pl.nch - 1 ? a.stages_of[1] : a.stages_of[0];    // (no dynamic index into the parameter struct)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE);   // full[stages], empty[stages], accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  // mask windows: the bit words of the CTA's 128 rows x 512 columns (16 words = 64 bytes per row, 64-byte swizzle) arrive
+  // through TMA (a warp of its own, UG_MASK_BUFS windows in flight: never in the way of the digit tiles).  (A thread per row reading its own words from global memory costs one L1
+  // wavefront per thread and word -- 512 per stage: at 75 % of the LSU data pipe this, not the tensor pipe, bounded
+  // the kernel.)
+  constexpr int MASK_WIN_BYTES = UG_ROWS * 64;
+  const uint32_t mask_base = smem_u32(smem) + (uint32_t)stages * STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE + UG_MASK_BUFS * MASK_WIN_BYTES);   // full[stages], empty[stages], accum, mask full[], mask empty[]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1 + 2 * UG_MASK_BUFS);
   int* cnt_smem = reinterpret_cast<int*>(tmem_slot + 2);           // [256]
   uint16_t* pair_tab = reinterpret_cast<uint16_t*>(cnt_smem + UG_EXP_WARPS * 32);   // [cpc] (a<<8 | b), b = 0xff: variance, 0xfd: sum
   const uint32_t smem_base = smem_u32(smem);
@@ -245,6 +283,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(stages + (s)))
 #define ACCUM_BAR (bar_base + 8u * (uint32_t)(2 * stages))
+#define MASK_FULL(b) (bar_base + 8u * (uint32_t)(2 * stages + 1 + (b)))
+#define MASK_EMPTY(b) (bar_base + 8u * (uint32_t)(2 * stages + 1 + UG_MASK_BUFS + (b)))
 
   const int kt_begin = seg * a.tiles_per_seg;
   const int kt_end = min(a.ktiles, kt_begin + a.tiles_per_seg);
@@ -256,6 +296,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     const uint32_t nfull = UG_EXP_WARPS / 2 + (PAIR ? (rank == 0 ? 2u : 0u) : 1u);
     for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), nfull); mbar_init(EMPTY_BAR(s), 1); }
     mbar_init(ACCUM_BAR, 1);
+    for (int b = 0; b < UG_MASK_BUFS; ++b) { mbar_init(MASK_FULL(b), 1); mbar_init(MASK_EMPTY(b), UG_EXP_WARPS); }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -291,11 +332,14 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     constexpr int CPT = KT / 16;                       // 16-byte chunks per tile row
     const uint32_t flip = a.polarity ? 0u : 0xffffffffu;
     // byte offset of this row inside an A tile, and its swizzle key (16-byte chunk index XOR)
-    const uint32_t row_off = (uint32_t)(r >> 3) * (8 * KT) + (uint32_t)(r & 7) * KT;
-    const uint32_t key = KT == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+    const uint32_t row_off = (uint32_t)(r >> 3) * (8 * AKT) + (uint32_t)(r & 7) * AKT;
+    const uint32_t key = AKT == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+    const uint32_t tlane_e = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)UG_SP_ACC_COLS;
     int cnt = 0;
+    constexpr int WIN = 16 / WPT;                      // stages per mask window
+    const bool mask_tma = a.mask_tma != 0;
     uint32_t nxt[WPT];
-    {
+    if (!mask_tma) {
       const int w0 = (kt_begin + half) * WPT;
 #pragma unroll
       for (int i = 0; i < WPT; ++i) nxt[i] = (live && half < ntile && w0 + i < a.wpr) ? mrow[w0 + i] : 0u;
@@ -304,34 +348,75 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
       const int wbase = (kt_begin + it) * WPT;
+      int release_win = -1;
+      if (mask_tma) {
+        const int q = it / WIN, c = it - q * WIN, qb = q % UG_MASK_BUFS;
+        mbar_wait(MASK_FULL(qb), (uint32_t)(q / UG_MASK_BUFS) & 1u);
+        const uint32_t rowb = mask_base + (uint32_t)qb * MASK_WIN_BYTES + (uint32_t)r * 64u;
+        if constexpr (WPT == 4) {
+          const uint32_t addr = rowb + ((((uint32_t)c) ^ (uint32_t)((r >> 1) & 3)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt[0]), "=r"(nxt[1]), "=r"(nxt[2]), "=r"(nxt[3]) : "r"(addr) : "memory");
+        } else {
+          const uint32_t addr = rowb + ((((uint32_t)(c >> 1)) ^ (uint32_t)((r >> 1) & 3)) << 4) + (uint32_t)(c & 1) * 8u;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(nxt[0]), "=r"(nxt[1]) : "r"(addr) : "memory");
+        }
+        release_win = (c + 2 >= WIN || it + 2 >= ntile) ? qb : -1;       // this warp's last stage inside the window
+      }
       uint32_t y[CPT][4];
+      uint32_t meta[WPT];
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
         uint32_t v = nxt[i] ^ flip;
         const int jb = (wbase + i) * 32;               // first column of this word
         if (jb + 32 > a.cols) v = jb >= a.cols ? 0u : (v & ((1u << (a.cols - jb)) - 1u));
         v = live ? v : 0u;
-        cnt += __popc(v);
-        // 4 mask bits -> 4 bytes: bit k of the nibble lands on bit 8k of (nibble * 0x00204081)
+        if constexpr (SP) {
+          // eight groups of four columns at once (one nibble each): positions of the first two selected columns ->
+          // metadata nibble idx0 | idx1 << 2, their values (0/1) -> two bytes per group = one 16-byte chunk per word
+          uint32_t v0, v1;
+          const uint32_t ovf = sparse_split(v, v0, v1, meta[i]);
+          cnt += __popc(v) - __popc(ovf);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) y[2 * i + (q >> 2)][q & 3] = (((v >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t t0 = (v0 >> (8 * q)) & 0x11u, t1 = (v1 >> (8 * q)) & 0x11u;
+            y[i][q] = ((t0 * 0x1001u) & 0x00010001u) | (((t1 * 0x1001u) & 0x00010001u) << 8);
+          }
+        } else {
+          cnt += __popc(v);
+          // 4 mask bits -> 4 bytes: bit k of the nibble lands on bit 8k of (nibble * 0x00204081)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) y[2 * i + (q >> 2)][q & 3] = (((v >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        }
       }
-      if (it + 2 < ntile) {
+      if (!mask_tma && it + 2 < ntile) {
         const int wn = wbase + 2 * WPT;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) nxt[i] = (live && wn + i < a.wpr) ? mrow[wn + i] : 0u;
       }
       mbar_wait(EMPTY_BAR(s), ph ^ 1u);                // the expansion above is done while the stage is still busy
       const uint32_t abase = smem_base + (uint32_t)s * STAGE + row_off;
+      if constexpr (SP) {
+        static_assert(WPT == 4, "four metadata columns per stage");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(tlane_e + 4u * (uint32_t)s), "r"(meta[0]), "r"(meta[1]), "r"(meta[2]), "r"(meta[3]) : "memory");
+      }
       if (!((a.dbg & 2) && it >= stages))
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
+      for (int c = 0; c < (SP ? WPT : CPT); ++c) {
         const uint32_t addr = abase + ((((uint32_t)c) ^ key) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y[c][0]), "r"(y[c][1]), "r"(y[c][2]), "r"(y[c][3]) : "memory");
       }
+      if constexpr (SP) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+      }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(FULL_BAR(s));           // one arrival per warp
+      if (lane == 0) {
+        mbar_arrive(FULL_BAR(s));           // one arrival per warp
+        // (the window is released only now: its words have been consumed, not merely requested, by every lane)
+        if (release_win >= 0) mbar_arrive(MASK_EMPTY(release_win));
+      }
     }
     // |S(i)| = the tiles of both groups
     cnt_smem[tid] = cnt;
@@ -418,6 +503,19 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp == UG_EXP_WARPS + 2) {
+    // ================= TMA producer of the mask windows =================
+    if (lane == 0 && a.mask_tma) {
+      constexpr int WIN = 512 / KT;
+      const int nwin = (ntile + WIN - 1) / WIN;
+      for (int q = 0; q < nwin; ++q) {                   // bit words of columns [(kt_begin + q WIN) KT, + 512) of the CTA's rows
+        const int qb = q % UG_MASK_BUFS;
+        if (q >= UG_MASK_BUFS) mbar_wait(MASK_EMPTY(qb), ((uint32_t)(q / UG_MASK_BUFS) & 1u) ^ 1u);
+        mbar_expect_tx(MASK_FULL(qb), (uint32_t)MASK_WIN_BYTES);
+        tma_load_2d(mask_base + (uint32_t)qb * MASK_WIN_BYTES, &tmap_bits, (kt_begin + q * WIN) * (KT / 32), rb * UG_ROWS, MASK_FULL(qb));
+      }
+    }
+    __syncwarp();
   } else {
     // ================= MMA issuer =================
     if (PAIR && lane == 0 && rank != 0) {
@@ -432,12 +530,14 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     if (rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, N = n_half,
       // M = 128 (256 for the CTA pair)
-      const uint32_t idesc = (2u << 4) | ((uint32_t)(n_half >> 3) << 17) | ((uint32_t)((PAIR ? 2 * UG_ROWS : UG_ROWS) >> 4) << 24);
+      // M = 128 (256 for the CTA pair); bit 2: sparse
+      const uint32_t idesc = (SP ? 4u : 0u) | (2u << 4) | ((uint32_t)(n_half >> 3) << 17) |
+                             ((uint32_t)((PAIR ? 2 * UG_ROWS : UG_ROWS) >> 4) << 24);
       // The whole warp runs this loop (convergent code keeps descriptors in uniform registers: with a single-lane
       // loop every tcgen05.mma needed five R2UR moves, ~150 dependent instructions per stage, and the issuing thread
       // itself limited the tensor pipe); only the tcgen05 instructions are predicated on one elected lane.  No
       // divisions, no clock reads, descriptors by addition.
-      const uint64_t ad0 = umma_desc<KT>(smem_base);
+      const uint64_t ad0 = umma_desc<AKT>(smem_base);
       const uint64_t bd00 = umma_desc<KT>(smem_base + A_BYTES);
       const uint64_t bd10 = umma_desc<KT>(smem_base + A_BYTES + (uint32_t)(PAIR ? n_half >> 1 : n_half) * KT);
       const uint64_t dstep = (uint64_t)(STAGE >> 4);
@@ -453,7 +553,19 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
         int sn = s + 1;
         uint32_t phn = ph;
         if (sn == stages) { sn = 0; phn ^= 1u; }
-        if (elect_one()) {
+        if (SP) {
+          // one MMA = 64 logical columns: 32 bytes of the compressed A row, 64 bytes of every digit row, two metadata columns
+          if (elect_one()) {
+            const uint32_t e0 = tmem_base + (uint32_t)UG_SP_ACC_COLS + 4u * (uint32_t)s;
+#pragma unroll
+            for (int kk = 0; kk < KT / 64; ++kk) {
+              const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+              umma_i8_sp<PAIR>(tmem_base, ad + 2 * kk, bd0 + 4 * kk, e0 + 2u * kk, idesc, acc);
+              umma_i8_sp<PAIR>(tm1, ad + 2 * kk, bd1 + 4 * kk, e0 + 2u * kk, idesc, acc);
+            }
+            if (PAIR) umma_commit_pair(EMPTY_BAR(s)); else umma_commit(EMPTY_BAR(s));
+          }
+        } else if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KT / 32; ++kk) {
             const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
@@ -485,6 +597,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
 #undef FULL_BAR
 #undef EMPTY_BAR
 #undef ACCUM_BAR
+#undef MASK_FULL
+#undef MASK_EMPTY
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -547,8 +661,8 @@ static long long plan_workspace_bytes(const UmmaPlan& pl, long long ld) {
 long long umma_workspace_bytes(int K, int vb, long long ld) {
   long long m = 0;
   for (int sums = 0; sums < 2; ++sums)
-    for (int pair = 0; pair < 2; ++pair) {
-      const long long b = plan_workspace_bytes(make_umma_plan(K, vb, sums, pair), ld);
+    for (int pair = 0; pair < 4; ++pair) {
+      const long long b = plan_workspace_bytes(make_umma_plan(K, vb, sums, pair & 1, pair >> 1), ld);
       m = b > m ? b : m;
     }
   return m;
@@ -561,7 +675,10 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   if (kt != 64 && kt != 128) { set_error("stats_gram_umma: tile width must be 64 or 128"); return -2; }
   if ((long long)ld * 255 >= 2147483647ll) { set_error("stats_gram_umma: more than 8.4M columns would overflow the int32 accumulators"); return -2; }
   const int vb = Vp != nullptr;
-  const UmmaPlan pl = make_umma_plan(K, vb, sums, pair);
+  const int sp = (pair >> 1) & 1;               // bit 1 of `pair`: the 2:4-sparse form (128-column stages)
+  pair &= 1;
+  if (sp && kt != 128) { set_error("stats_gram_umma: the sparse form needs tile width 128"); return -2; }
+  const UmmaPlan pl = make_umma_plan(K, vb, sums, pair, sp);
   if (workspace_bytes < plan_workspace_bytes(pl, ld)) { set_error("stats_gram_umma: workspace too small"); return -2; }
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("stats_gram_umma: cuTensorMapEncodeTiled not available"); return -3; }
@@ -591,7 +708,7 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   // between the full chunks (n_half = 256) and the last one
   CUtensorMap tmaps[2];
   for (int which = 0; which < 2; ++which) {
-    const int nh = which ? pl.nh_last : 256;
+    const int nh = which ? pl.nh_last : pl.nh_full;
     const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)pl.nch * UG_CHUNK_ROWS};
     const cuuint64_t gstr[1] = {(cuuint64_t)ld};
     const cuuint32_t box[2] = {(cuuint32_t)kt, (cuuint32_t)(pair ? nh / 2 : nh)};
@@ -609,13 +726,14 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   const int nseg_eff = (a.ktiles + a.tiles_per_seg - 1) / a.tiles_per_seg;
   if (nseg_eff != nseg) { set_error("stats_gram_umma: nseg=%d leaves empty segments (use <= %d)", nseg, nseg_eff); return -2; }
   a.pl = pl; a.cscale = cscale; a.Gout = Gout; a.SVout = SVout; a.KP = KP; a.gl = nt * (nt + 1) / 2 * 64;
-  const int tail = (2 * 16 + 1) * 8 + 16 + UG_EXP_WARPS * 32 * 4 + 2 * pl.cpc + 64;
+  const int tail = UG_MASK_BUFS * UG_ROWS * 64 + (2 * 16 + 1 + 2 * UG_MASK_BUFS) * 8 + 16 + UG_EXP_WARPS * 32 * 4 + 2 * pl.cpc + 64;
   size_t smem = 0;
   for (int which = 0; which < 2; ++which) {
-    const int nh = which ? pl.nh_last : 256;
-    const int stage_bytes = (UG_ROWS + (pair ? nh : 2 * nh)) * kt;
+    const int nh = which ? pl.nh_last : pl.nh_full;
+    const int stage_bytes = (sp ? UG_ROWS / 2 : UG_ROWS) * kt + (pair ? nh : 2 * nh) * kt;
     int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
     if (stages > 16) stages = 16;
+    if (sp && stages > 8) stages = 8;                  // four metadata columns per stage in tensor-memory columns [480, 512)
     if (max_stages > 0 && stages > max_stages) stages = max_stages;
     if (stages < 2) { set_error("stats_gram_umma: stage does not fit"); return -2; }
     a.stages_of[which] = stages;
@@ -628,8 +746,24 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   int rbs = (rows + UG_ROWS - 1) / UG_ROWS;
   if (pair) rbs = (rbs + 1) / 2 * 2;                   // a padding CTA (no live rows) completes the last pair
   dim3 grid(rbs, pl.nch, nseg);
-  void (*kern)(const CUtensorMap, const CUtensorMap, UmmaGramArgs) =
-      kt == 128 ? (pair ? k_gram_umma<128, true> : k_gram_umma<128, false>) : (pair ? k_gram_umma<64, true> : k_gram_umma<64, false>);
+  // the mask bits as a (rows x ld/32) uint32 tensor: windows of 128 rows x 16 words; rows / words past the end read as zero
+  CUtensorMap tmap_bits = tmaps[0];
+  a.mask_tma = (ld % 128 == 0 && reinterpret_cast<uintptr_t>(bits) % 16 == 0) ? 1 : 0;
+  { const char* e = getenv("BNMTF_GRAM_MASK_TMA"); if (e && atoi(e) == 0) a.mask_tma = 0; }
+  if (a.mask_tma) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)(ld / 32), (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)(ld / 32) * 4};
+    const cuuint32_t box[2] = {16, (cuuint32_t)UG_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&tmap_bits, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(bits), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("stats_gram_umma: cuTensorMapEncodeTiled (mask) failed (%d)", (int)r); return -3; }
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, UmmaGramArgs) =
+      sp ? (pair ? k_gram_umma<128, true, true> : k_gram_umma<128, false, true>)
+         : kt == 128 ? (pair ? k_gram_umma<128, true, false> : k_gram_umma<128, false, false>)
+                     : (pair ? k_gram_umma<64, true, false> : k_gram_umma<64, false, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(UG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -637,7 +771,7 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmaps[0], tmaps[1], a);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmaps[0], tmaps[1], tmap_bits, a);
   if (le != cudaSuccess) { set_error("stats_gram_umma: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return -1; }
   return check_launch("stats_gram_umma");
 }

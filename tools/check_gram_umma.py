@@ -48,6 +48,9 @@ def run_case(idx):
     from bnmtf_b200 import _lib
     from bnmtf_b200.engine import _ptr, _stream, ld_for, kp_for, gram_len
     rows, cols, K, vb, pol, nseg, tile, signed, reps, sums, stages = CASES[idx]
+    sparse = (PAIR >> 1) & 1          # PAIR=2|3: the 2:4-sparse form (128-column stages only)
+    if sparse:
+        tile = 128
     if reps:
         reps = int(os.environ.get("REPS", reps))
     dev = torch.device("cuda:0")
@@ -91,6 +94,14 @@ def run_case(idx):
     # reference on the first chunk of rows: W @ P in fp64
     nr = min(rows, chunk)
     W = M0[:nr] if pol == 1 else 1.0 - M0[:nr]
+    if sparse and not int(os.environ.get("FIXUP", "0")):
+        # the kernel alone keeps the first two selected columns of every aligned group of four
+        c4 = (cols + 3) // 4 * 4
+        Wp = torch.zeros((nr, c4), dtype=torch.float64, device=dev)
+        Wp[:, :cols] = W
+        g4 = Wp.view(nr, c4 // 4, 4)
+        W = (g4 * (g4.cumsum(2) <= 2)).reshape(nr, c4)[:, :cols].contiguous()
+        out["overflow_frac"] = float(1.0 - W.sum() / Wp.sum())
     ia, ib = np.triu_indices(K)
     P = X[:, ia] * X[:, ib]
     Gref = W @ P                                   # nr x ng
@@ -118,6 +129,24 @@ def run_case(idx):
         Sref = W @ Var
         Su = S1.view(nseg, rows, KP).sum(0)[:nr, :K]
         out["sv_vs_ref"] = float(((Su - Sref).abs() / Sref.abs().max(0).values.clamp_min(1e-300)).max())
+    if int(os.environ.get("STRESS", "0")):
+        # exact integer accumulation: every call must give the same bits; report where repeated calls differ
+        ref_bits = G1.clone()
+        bad = []
+        for rep_i in range(int(os.environ["STRESS"])):
+            G1.fill_(float("nan"))
+            umma()
+            torch.cuda.synchronize()
+            d = (G1 != ref_bits) & ~(torch.isnan(G1) & torch.isnan(ref_bits))
+            if bool(d.any()):
+                rws = torch.nonzero(d.any(1)).flatten()
+                cls = torch.nonzero(d.any(0)).flatten()
+                bad.append({"rep": rep_i, "rows": int(rws.numel()), "row_min": int(rws.min()), "row_max": int(rws.max()),
+                            "row_blocks": sorted(set((rws // 128).tolist()))[:12], "cols": int(cls.numel()),
+                            "max_rel": float(((G1 - ref_bits).abs() / ref_bits.abs().clamp_min(1e-300))[d].max()),
+                            "nan_new": int(torch.isnan(G1[d]).sum()), "nan_ref": int(torch.isnan(ref_bits[d]).sum()),
+                            "col_list": cls.tolist()[:24]})
+        out["stress_bad"] = bad
     # the DMMA kernel on the same input
     ng = max(1, min(-(-(ld // 32) // 32), -(-592 // ((rows + 7) // 8))))
     G0 = torch.zeros((ng * rows, GL), dtype=torch.float64, device=dev)
