@@ -32,7 +32,8 @@ namespace bnmtf {
 constexpr int UG_SLICES = kDigits;          // bytes per product column (common.cuh)
 constexpr int UG_TOP = 8 * UG_SLICES - 1;    // products are stored as llrint(P 2^(TOP-e)) + 2^TOP, 2^e > max|P|
 constexpr int UG_ROWS = 128;     // rows per CTA = UMMA M
-constexpr int UG_EXP_WARPS = 8;   // mask-expander / epilogue warps (two threads per row)
+constexpr int UG_GROUPS = 4;      // groups of 128 mask-expander / epilogue threads (one thread per row each)
+constexpr int UG_EXP_WARPS = 4 * UG_GROUPS;
 constexpr int UG_THREADS = (UG_EXP_WARPS + 3) * 32;   // + TMA producer of the digit tiles, MMA issuer, TMA producer of the mask windows
 constexpr int UG_MASK_BUFS = 3;      // mask windows in flight
 
@@ -252,7 +253,13 @@ struct UmmaGramArgs {
 // expander threads with tcgen05.st -- and one MMA covers K = 64 logical columns in the time of a dense K = 32.  The
 // third and fourth selected entries of a group (0.7 % of the entries at 20 %) are left out here (sparse_overflow()
 // is the rule) and added by k_gram_fixup as one more segment of the partial statistics.
-template <int KT, bool PAIR, bool SP>
+//
+// MC: clusters of FOUR CTAs = two CTA pairs (four adjacent row blocks, same chunk and segment) share every digit tile:
+// each CTA fetches ONE of the two boxes its position in the pair needs and multicasts it into the shared memory of
+// the CTA with the same position in the other pair, which halves the L2 -> SM traffic of the digit rows (12 GB per
+// launch at the headline shape; measured: that traffic, not the tensor pipe, bounds the kernel).  A stage is free
+// when BOTH pairs have consumed it (their commits arrive at all four CTAs).
+template <int KT, bool PAIR, bool SP, bool MC>
 __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_constant__ CUtensorMap tmap_full,
                                                             const __grid_constant__ CUtensorMap tmap_last,
                                                             const __grid_constant__ CUtensorMap tmap_bits, UmmaGramArgs a) {
@@ -260,7 +267,10 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const UmmaPlan& pl = a.pl;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  static_assert(!MC || PAIR, "the multicast form is built on CTA pairs");
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // rank in the cluster (0..3 with MC)
+  const uint32_t rank = crank & 1u;                         // position in the CTA pair (0: leader, issues the MMAs)
+  const uint32_t lead = crank & ~1u;                        // cluster rank of this pair's leader
   const int rb = blockIdx.x, ch = blockIdx.y, seg = blockIdx.z;
   const int n_half = umma_nhalf_of(pl, ch), cpc = umma_cols_of(pl, ch);       // this chunk: UMMA N per accumulator, P-columns
   const CUtensorMap& tmap = ch == pl.nch - 1 ? tmap_last : tmap_full;           // box height = this chunk's digit rows per load
@@ -293,10 +303,10 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   if (warp == UG_EXP_WARPS && lane == 0) {
     // full: every local expander thread + the TMA thread (+, CTA pair, leader: the partner's relay thread; the
     // partner's own full barrier only collects its expanders)
-    const uint32_t nfull = UG_EXP_WARPS / 2 + (PAIR ? (rank == 0 ? 2u : 0u) : 1u);
-    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), nfull); mbar_init(EMPTY_BAR(s), 1); }
+    const uint32_t nfull = 4u + (PAIR ? (rank == 0 ? 2u : 0u) : 1u);     // the four warps of the group that expands the stage
+    for (int s = 0; s < stages; ++s) { mbar_init(FULL_BAR(s), nfull); mbar_init(EMPTY_BAR(s), MC ? 2 : 1); }
     mbar_init(ACCUM_BAR, 1);
-    for (int b = 0; b < UG_MASK_BUFS; ++b) { mbar_init(MASK_FULL(b), 1); mbar_init(MASK_EMPTY(b), UG_EXP_WARPS); }
+    for (int b = 0; b < UG_MASK_BUFS; ++b) { mbar_init(MASK_FULL(b), 1); mbar_init(MASK_EMPTY(b), 4 * (stages < UG_GROUPS ? stages : UG_GROUPS)); }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -322,14 +332,18 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
 
   if (warp < UG_EXP_WARPS) {
     // ================= mask expanders, then epilogue =================
-    // two groups of 128 threads (thread <-> row) take alternate pipeline stages: the per-stage chain of one group
-    // (barrier wake-up, stores, proxy fence, arrive) overlaps the bit expansion of the other
+    // UG_GROUPS groups of 128 threads (thread <-> row) take the pipeline stages in turn: the per-stage chain of one group
+    // (barrier wake-up, stores, proxy fence, arrive) overlaps the bit expansion of the others, and every scheduler has
+    // several expander warps to pick from (with two groups the expanders' own issue rate bounded the sparse form)
     const int r = tid & (UG_ROWS - 1), half = tid >> 7;
     const int row = rb * UG_ROWS + r;
     const bool live = row < a.rows;
     const uint32_t* mrow = a.bits + (size_t)(live ? row : 0) * a.wpr;
     constexpr int WPT = KT / 32;                       // mask words per tile
     constexpr int CPT = KT / 16;                       // 16-byte chunks per tile row
+    // (a group must never be two barrier phases ahead of the MMAs -- parity waits cannot tell -- hence at most `stages`
+    // groups expand; the others only take part in the epilogue)
+    const int NG = stages < UG_GROUPS ? stages : UG_GROUPS;
     const uint32_t flip = a.polarity ? 0u : 0xffffffffu;
     // byte offset of this row inside an A tile, and its swizzle key (16-byte chunk index XOR)
     const uint32_t row_off = (uint32_t)(r >> 3) * (8 * AKT) + (uint32_t)(r & 7) * AKT;
@@ -338,37 +352,41 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     int cnt = 0;
     constexpr int WIN = 16 / WPT;                      // stages per mask window
     const bool mask_tma = a.mask_tma != 0;
-    uint32_t nxt[WPT];
-    if (!mask_tma) {
-      const int w0 = (kt_begin + half) * WPT;
-#pragma unroll
-      for (int i = 0; i < WPT; ++i) nxt[i] = (live && half < ntile && w0 + i < a.wpr) ? mrow[w0 + i] : 0u;
-    }
-    for (int it = half; it < ntile; it += 2) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+    // running indices of stage `it` (no divisions in the loop): pipeline slot / phase, mask window slot / phase / position
+    int s = half % stages;
+    uint32_t ph = (uint32_t)(half / stages) & 1u;
+    int c = half % WIN, qb = (half / WIN) % UG_MASK_BUFS;
+    uint32_t qph = (uint32_t)((half / WIN) / UG_MASK_BUFS) & 1u;
+    const int s_step = NG % stages, ph_step = (NG / stages) & 1;
+    for (int it = half < NG ? half : ntile; it < ntile; it += NG) {
       const int wbase = (kt_begin + it) * WPT;
+      uint32_t w[WPT];
       int release_win = -1;
       if (mask_tma) {
-        const int q = it / WIN, c = it - q * WIN, qb = q % UG_MASK_BUFS;
-        mbar_wait(MASK_FULL(qb), (uint32_t)(q / UG_MASK_BUFS) & 1u);
+        mbar_wait(MASK_FULL(qb), qph);
         const uint32_t rowb = mask_base + (uint32_t)qb * MASK_WIN_BYTES + (uint32_t)r * 64u;
         if constexpr (WPT == 4) {
           const uint32_t addr = rowb + ((((uint32_t)c) ^ (uint32_t)((r >> 1) & 3)) << 4);
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt[0]), "=r"(nxt[1]), "=r"(nxt[2]), "=r"(nxt[3]) : "r"(addr) : "memory");
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr) : "memory");
         } else {
           const uint32_t addr = rowb + ((((uint32_t)(c >> 1)) ^ (uint32_t)((r >> 1) & 3)) << 4) + (uint32_t)(c & 1) * 8u;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(nxt[0]), "=r"(nxt[1]) : "r"(addr) : "memory");
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(addr) : "memory");
         }
-        release_win = (c + 2 >= WIN || it + 2 >= ntile) ? qb : -1;       // this warp's last stage inside the window
+        release_win = (c + NG >= WIN || it + NG >= ntile) ? qb : -1;       // this warp's last stage inside the window
+      } else {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) w[i] = (live && wbase + i < a.wpr) ? mrow[wbase + i] : 0u;
       }
+      const bool edge = (wbase + WPT) * 32 > a.cols;     // the stage reaches past the last column
       uint32_t y[CPT][4];
       uint32_t meta[WPT];
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
-        uint32_t v = nxt[i] ^ flip;
-        const int jb = (wbase + i) * 32;               // first column of this word
-        if (jb + 32 > a.cols) v = jb >= a.cols ? 0u : (v & ((1u << (a.cols - jb)) - 1u));
+        uint32_t v = w[i] ^ flip;
+        if (edge) {
+          const int jb = (wbase + i) * 32;               // first column of this word
+          if (jb + 32 > a.cols) v = jb >= a.cols ? 0u : (v & ((1u << (a.cols - jb)) - 1u));
+        }
         v = live ? v : 0u;
         if constexpr (SP) {
           // eight groups of four columns at once (one nibble each): positions of the first two selected columns ->
@@ -376,22 +394,17 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
           uint32_t v0, v1;
           const uint32_t ovf = sparse_split(v, v0, v1, meta[i]);
           cnt += __popc(v) - __popc(ovf);
+          // z: bits 4g / 4g+1 = value at idx0 / idx1 of group g; the bits 0, 1, 4, 5 of each byte of z go to bits 0, 8, 16,
+          // 24 of one word (x 0x81081 puts them there; the cross terms never carry into those positions)
+          const uint32_t z = v0 | (v1 << 1);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t t0 = (v0 >> (8 * q)) & 0x11u, t1 = (v1 >> (8 * q)) & 0x11u;
-            y[i][q] = ((t0 * 0x1001u) & 0x00010001u) | (((t1 * 0x1001u) & 0x00010001u) << 8);
-          }
+          for (int q = 0; q < 4; ++q) y[i][q] = (((z >> (8 * q)) & 0x33u) * 0x00081081u) & 0x01010101u;
         } else {
           cnt += __popc(v);
           // 4 mask bits -> 4 bytes: bit k of the nibble lands on bit 8k of (nibble * 0x00204081)
 #pragma unroll
           for (int q = 0; q < 8; ++q) y[2 * i + (q >> 2)][q & 3] = (((v >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
         }
-      }
-      if (!mask_tma && it + 2 < ntile) {
-        const int wn = wbase + 2 * WPT;
-#pragma unroll
-        for (int i = 0; i < WPT; ++i) nxt[i] = (live && wn + i < a.wpr) ? mrow[wn + i] : 0u;
       }
       mbar_wait(EMPTY_BAR(s), ph ^ 1u);                // the expansion above is done while the stage is still busy
       const uint32_t abase = smem_base + (uint32_t)s * STAGE + row_off;
@@ -402,9 +415,9 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       }
       if (!((a.dbg & 2) && it >= stages))
 #pragma unroll
-      for (int c = 0; c < (SP ? WPT : CPT); ++c) {
-        const uint32_t addr = abase + ((((uint32_t)c) ^ key) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y[c][0]), "r"(y[c][1]), "r"(y[c][2]), "r"(y[c][3]) : "memory");
+      for (int cc = 0; cc < (SP ? WPT : CPT); ++cc) {
+        const uint32_t addr = abase + ((((uint32_t)cc) ^ key) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(y[cc][0]), "r"(y[cc][1]), "r"(y[cc][2]), "r"(y[cc][3]) : "memory");
       }
       if constexpr (SP) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -414,14 +427,21 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(FULL_BAR(s));           // one arrival per warp
-        // (the window is released only now: its words have been consumed, not merely requested, by every lane)
+        // (the window is released only now: its words have been consumed, not merely requested, by every lane -- an
+        // arrive right behind the ld.shared let the next TMA write overtake loads still in flight)
         if (release_win >= 0) mbar_arrive(MASK_EMPTY(release_win));
       }
+      s += s_step; ph ^= (uint32_t)ph_step;
+      if (s >= stages) { s -= stages; ph ^= 1u; }
+      c += NG;
+      while (c >= WIN) { c -= WIN; if (++qb == UG_MASK_BUFS) { qb = 0; qph ^= 1u; } }
     }
     // |S(i)| = the tiles of both groups
     cnt_smem[tid] = cnt;
     asm volatile("bar.sync 1, %0;" ::"n"(UG_EXP_WARPS * 32) : "memory");
-    cnt = cnt_smem[r] + cnt_smem[r + UG_ROWS];
+    cnt = 0;
+#pragma unroll
+    for (int g = 0; g < UG_GROUPS; ++g) cnt += cnt_smem[r + g * UG_ROWS];
 
     // ---- epilogue: the two threads of a row take alternate P-columns ----
     mbar_wait(ACCUM_BAR, 0u);
@@ -434,7 +454,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     // round trip per group instead of one per column); the two threads of a row take alternate groups
     constexpr int GRP = 8, GCOLS = GRP * UG_SLICES;            // 48 columns with six digits
     static_assert(GCOLS % 16 == 0, "group width must be a multiple of the 16-column load");
-    for (int g0 = half * GRP; g0 < cpc; g0 += 2 * GRP) {
+    for (int g0 = half * GRP; g0 < cpc; g0 += UG_GROUPS * GRP) {
       uint32_t d[GCOLS / 16][16];
 #pragma unroll
       for (int q = 0; q < GCOLS / 16; ++q) {
@@ -489,9 +509,19 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
         const int x = (kt_begin + it) * KT;
         if (PAIR) {
           // this CTA's half of the digit rows of each accumulator; the bytes of both CTAs are expected by the leader
-          const uint32_t lead_full = mapa_u32(FULL_BAR(s), 0);
+          if ((a.dbg & 1) && it >= stages) { if (rank == 0) mbar_arrive(FULL_BAR(s)); continue; }     // timing experiments
           if (rank == 0) mbar_expect_tx(FULL_BAR(s), 2u * (uint32_t)B_BYTES);
           const int hh = n_half >> 1;
+          if (MC) {
+            // box `crank >> 1` (accumulator 0 / 1) of this position's half, delivered to this CTA and to the CTA at the
+            // same position of the other pair; completion bytes go to the pair leader's barrier of each destination
+            // (barrier given as this CTA's own address with the peer bit cleared)
+            const uint32_t which = crank >> 1;
+            tma_load_2d_pair_mc(bdst + which * (uint32_t)hh * KT, &tmap, x, ch * UG_CHUNK_ROWS + (int)which * n_half + (int)rank * hh,
+                                FULL_BAR(s) & 0xFEFFFFFFu, (uint16_t)((1u << crank) | (1u << (crank ^ 2u))));
+            continue;
+          }
+          const uint32_t lead_full = mapa_u32(FULL_BAR(s), lead);
           tma_load_2d_pair(bdst, &tmap, x, ch * UG_CHUNK_ROWS + (int)rank * hh, lead_full);
           tma_load_2d_pair(bdst + (uint32_t)hh * KT, &tmap, x, ch * UG_CHUNK_ROWS + n_half + (int)rank * hh, lead_full);
           continue;
@@ -524,7 +554,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
       for (int it = 0; it < ntile; ++it) {
         const int s = it % stages;
         mbar_wait(FULL_BAR(s), (uint32_t)(it / stages) & 1u);
-        mbar_arrive_remote(mapa_u32(FULL_BAR(s), 0));
+        mbar_arrive_remote(mapa_u32(FULL_BAR(s), lead));
       }
     }
     if (rank == 0) {
@@ -563,7 +593,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
               umma_i8_sp<PAIR>(tmem_base, ad + 2 * kk, bd0 + 4 * kk, e0 + 2u * kk, idesc, acc);
               umma_i8_sp<PAIR>(tm1, ad + 2 * kk, bd1 + 4 * kk, e0 + 2u * kk, idesc, acc);
             }
-            if (PAIR) umma_commit_pair(EMPTY_BAR(s)); else umma_commit(EMPTY_BAR(s));
+            if (PAIR) umma_commit_pair(EMPTY_BAR(s), MC ? 0xFu : 3u); else umma_commit(EMPTY_BAR(s));
           }
         } else if (elect_one()) {
 #pragma unroll
@@ -577,14 +607,14 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
               umma_i8(tm1, ad + 2 * kk, bd1 + 2 * kk, idesc, acc);
             }
           }
-          if (PAIR) umma_commit_pair(EMPTY_BAR(s)); else umma_commit(EMPTY_BAR(s));
+          if (PAIR) umma_commit_pair(EMPTY_BAR(s), MC ? 0xFu : 3u); else umma_commit(EMPTY_BAR(s));
         }
         __syncwarp();
         if (it + 1 < ntile) mbar_wait(FULL_BAR(sn), phn);
         s = sn; ph = phn;
         soff = s == 0 ? 0 : soff + dstep;
       }
-      if (elect_one()) { if (PAIR) umma_commit_pair(ACCUM_BAR); else umma_commit(ACCUM_BAR); }
+      if (elect_one()) { if (PAIR) umma_commit_pair(ACCUM_BAR, 3u << lead); else umma_commit(ACCUM_BAR); }
     }
     __syncwarp();
   }
@@ -661,7 +691,7 @@ static long long plan_workspace_bytes(const UmmaPlan& pl, long long ld) {
 long long umma_workspace_bytes(int K, int vb, long long ld) {
   long long m = 0;
   for (int sums = 0; sums < 2; ++sums)
-    for (int pair = 0; pair < 4; ++pair) {
+    for (int pair = 0; pair < 4; ++pair) {          // (the multicast bit does not change the plan)
       const long long b = plan_workspace_bytes(make_umma_plan(K, vb, sums, pair & 1, pair >> 1), ld);
       m = b > m ? b : m;
     }
@@ -676,7 +706,9 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   if ((long long)ld * 255 >= 2147483647ll) { set_error("stats_gram_umma: more than 8.4M columns would overflow the int32 accumulators"); return -2; }
   const int vb = Vp != nullptr;
   const int sp = (pair >> 1) & 1;               // bit 1 of `pair`: the 2:4-sparse form (128-column stages)
+  const int mc = (pair >> 2) & 1;               // bit 2: clusters of two pairs, digit tiles multicast between them
   pair &= 1;
+  if (mc && !pair) { set_error("stats_gram_umma: the multicast form needs CTA pairs"); return -2; }
   if (sp && kt != 128) { set_error("stats_gram_umma: the sparse form needs tile width 128"); return -2; }
   const UmmaPlan pl = make_umma_plan(K, vb, sums, pair, sp);
   if (workspace_bytes < plan_workspace_bytes(pl, ld)) { set_error("stats_gram_umma: workspace too small"); return -2; }
@@ -745,6 +777,7 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
   if (smem < 116 * 1024) smem = 116 * 1024;
   int rbs = (rows + UG_ROWS - 1) / UG_ROWS;
   if (pair) rbs = (rbs + 1) / 2 * 2;                   // a padding CTA (no live rows) completes the last pair
+  if (mc) rbs = (rbs + 3) / 4 * 4;
   dim3 grid(rbs, pl.nch, nseg);
   // the mask bits as a (rows x ld/32) uint32 tensor: windows of 128 rows x 16 words; rows / words past the end read as zero
   CUtensorMap tmap_bits = tmaps[0];
@@ -761,15 +794,16 @@ int launch_stats_gram_umma(const uint32_t* bits, int rows, int ld, int cols, con
     if (r != CUDA_SUCCESS) { set_error("stats_gram_umma: cuTensorMapEncodeTiled (mask) failed (%d)", (int)r); return -3; }
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, UmmaGramArgs) =
-      sp ? (pair ? k_gram_umma<128, true, true> : k_gram_umma<128, false, true>)
-         : kt == 128 ? (pair ? k_gram_umma<128, true, false> : k_gram_umma<128, false, false>)
-                     : (pair ? k_gram_umma<64, true, false> : k_gram_umma<64, false, false>);
+      mc ? (sp ? k_gram_umma<128, true, true, true> : (kt == 128 ? k_gram_umma<128, true, false, true> : k_gram_umma<64, true, false, true>))
+      : sp ? (pair ? k_gram_umma<128, true, true, false> : k_gram_umma<128, false, true, false>)
+         : kt == 128 ? (pair ? k_gram_umma<128, true, false, false> : k_gram_umma<128, false, false, false>)
+                     : (pair ? k_gram_umma<64, true, false, false> : k_gram_umma<64, false, false, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(UG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = mc ? 4 : (pair ? 2 : 1); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmaps[0], tmaps[1], tmap_bits, a);
   if (le != cudaSuccess) { set_error("stats_gram_umma: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return -1; }

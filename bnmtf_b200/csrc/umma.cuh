@@ -144,6 +144,15 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(cluster_bar)
       : "memory");
 }
+// the same, delivered to every CTA of `cta_mask` (same shared-memory offset); `bar_off` is this CTA's own barrier address
+// with the peer bit cleared: in every destination the bytes are credited to the barrier of ITS pair leader
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar_off,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar_off), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -153,8 +162,8 @@ __device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, ui
       : "memory");
 }
 // arrive on the barrier at this shared-memory offset in both CTAs of the pair when the MMAs issued so far are done
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  const uint16_t mask = 3;
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint32_t cta_mask = 3u) {
+  const uint16_t mask = (uint16_t)cta_mask;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask)
                : "memory");
