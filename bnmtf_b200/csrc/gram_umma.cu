@@ -501,9 +501,11 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
   } else if (warp == UG_EXP_WARPS) {
     // ================= TMA producer of the digit tiles =================
     if (lane == 0) {
+      int s = -1;
+      uint32_t ph = 1u;
       for (int it = 0; it < ntile; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        if (++s == stages) s = 0;                        // (no divisions on the path from a freed stage to its next load)
+        if (s == 0) ph ^= 1u;
         mbar_wait(EMPTY_BAR(s), ph ^ 1u);
         const uint32_t bdst = smem_base + (uint32_t)s * STAGE + A_BYTES;
         const int x = (kt_begin + it) * KT;
@@ -551,9 +553,12 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     if (PAIR && lane == 0 && rank != 0) {
       // partner CTA: relay "my A tile is complete" to the leader's full barrier, one cluster-scope arrive per stage
       // (a release at cluster scope flushes L1: kept off the expander threads)
+      int s = -1;
+      uint32_t ph = 1u;
       for (int it = 0; it < ntile; ++it) {
-        const int s = it % stages;
-        mbar_wait(FULL_BAR(s), (uint32_t)(it / stages) & 1u);
+        if (++s == stages) s = 0;
+        if (s == 0) ph ^= 1u;
+        mbar_wait(FULL_BAR(s), ph);
         mbar_arrive_remote(mapa_u32(FULL_BAR(s), lead));
       }
     }

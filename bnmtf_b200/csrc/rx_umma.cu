@@ -43,6 +43,10 @@ constexpr int RXU_DRAIN = 64;                     // stages per accumulator peri
 constexpr int RXU_PLANE_TILE = 128 * RXU_KT;      // 8 KB
 constexpr int RXU_A_BYTES = RXU_PLANES * RXU_PLANE_TILE;
 constexpr int RXU_THREADS = 192;
+// Factor columns are padded to KPAD = 16, 24 or 32.  UMMA N must be a multiple of 16 at M = 128: with KPAD = 24 the MMAs of
+// an odd number of digits run 8 columns wide of their range, into digit rows past the last digit -- rows that exist in
+// the staged B operand and are zero (rxu_brows), so the extra columns add nothing.
+__host__ __device__ constexpr int rxu_brows(int kpad) { return (RXU_VDIG * kpad + (kpad % 16 ? 8 : 0) + 15) / 16 * 16; }
 
 __host__ __device__ inline size_t rxu_tile_offset(int rb, int kt, int ktiles) {
   return ((size_t)rb * ktiles + kt) * RXU_A_BYTES;
@@ -217,6 +221,13 @@ __global__ void __launch_bounds__(256) k_rxu_quantize(const double* __restrict__
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t addr, uint32_t (&r)[N]);
 template <>
+__device__ __forceinline__ void tmem_ld_n<8>(uint32_t addr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr)
+               : "memory");
+}
+template <>
 __device__ __forceinline__ void tmem_ld_n<16>(uint32_t addr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -257,7 +268,8 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int B_BYTES = RXU_VDIG * KPAD * RXU_KT;
+  constexpr int B_BYTES = rxu_brows(KPAD) * RXU_KT;
+  static_assert(B_BYTES % 1024 == 0, "stages stay 1024-byte aligned");
   constexpr int STAGE = RXU_A_BYTES + B_BYTES;
   constexpr int SET = RXU_NU * KPAD;                    // tensor-memory columns of one accumulator set
   const int stages = a.stages;
@@ -315,21 +327,22 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
         const uint32_t b = dg & 1u;
         mbar_wait(ACC_FULL(b), (dg >> 1) & 1u);
         tc_fence_after();
+        constexpr int HC = KPAD % 16 ? 8 : 16;           // factor columns at a time (keeps the register count down)
 #pragma unroll
-        for (int h = 0; h < KPAD / 16; ++h) {            // 16 factor columns at a time keeps the register count down
-          double v[16];
+        for (int h = 0; h < KPAD / HC; ++h) {
+          double v[HC];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = 0.0;
+          for (int k = 0; k < HC; ++k) v[k] = 0.0;
 #pragma unroll
           for (int u = RXU_NU - 1; u >= 0; --u) {
-            uint32_t reg[16];
-            tmem_ld_n<16>(tlane + (uint32_t)(b * SET + u * KPAD + 16 * h), reg);
+            uint32_t reg[HC];
+            tmem_ld_n<HC>(tlane + (uint32_t)(b * SET + u * KPAD + HC * h), reg);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = fma(v[k], 256.0, (double)(int)reg[k]);
+            for (int k = 0; k < HC; ++k) v[k] = fma(v[k], 256.0, (double)(int)reg[k]);
           }
 #pragma unroll
-          for (int k = 0; k < 16; ++k) c[16 * h + k] += v[k];
+          for (int k = 0; k < HC; ++k) c[HC * h + k] += v[k];
         }
 #pragma unroll
         for (int c0 = 0; c0 < SET; c0 += 16) tmem_st_zero16(tlane + (uint32_t)(b * SET + c0));
@@ -394,9 +407,9 @@ __global__ void __launch_bounds__(RXU_THREADS, 1) k_rx_umma(const __grid_constan
                 for (int p = 0; p < RXU_PLANES; ++p) {
                   const int tmin = p < RXU_UMIN ? RXU_UMIN - p : 0;
                   const int nt = RXU_VDIG - tmin;
-                  // D = s32, A = u8 (top plane: s8), B = u8, K-major both, N = nt*KPAD, M = 128
+                  // D = s32, A = u8 (top plane: s8), B = u8, K-major both, N = nt*KPAD (rounded up to 16: zero digit rows), M = 128
                   const uint32_t idesc = (2u << 4) | ((p == RXU_PLANES - 1 ? 1u : 0u) << 7) |
-                                         ((uint32_t)((nt * KPAD) >> 3) << 17) | (8u << 24);
+                                         ((uint32_t)(((nt * KPAD + 15) / 16 * 16) >> 3) << 17) | (8u << 24);
                   const uint64_t ad = umma_desc<RXU_KT>(sa + (uint32_t)p * RXU_PLANE_TILE) + 2 * kk;
                   const uint64_t bd = umma_desc<RXU_KT>(sa + RXU_A_BYTES + (uint32_t)(tmin * KPAD * RXU_KT)) + 2 * kk;
                   umma_i8(tmem_base + b * SET + (uint32_t)((p + tmin - RXU_UMIN) * KPAD), ad, bd, idesc, 1u);
@@ -445,10 +458,10 @@ int launch_rxu_pack(const double* R, const uint32_t* bits, int rows, int ld, uin
   return check_launch("rx_planes_pack");
 }
 
-static int rxu_kpad(int K) { return K <= 16 ? 16 : 32; }
+static int rxu_kpad(int K) { return K <= 16 ? 16 : (K <= 24 ? 24 : 32); }
 
 // workspace: colmax (32 u64) | cscale (32 f64) | cexp (32 i32) | flag (i32, 16-byte slot) | digits (7*KPAD x ld, 1024-aligned)
-long long rxu_workspace_bytes(int K, long long ld) { return 1024 + (long long)RXU_VDIG * rxu_kpad(K) * ld; }
+long long rxu_workspace_bytes(int K, long long ld) { return 1024 + (long long)rxu_brows(rxu_kpad(K)) * ld; }
 
 int launch_stats_rx(const double* R, const uint32_t* bits, int rows, int ld, const double* Xp, int K, int nseg, double* out,
                     const int* run_flag, cudaStream_t st);
@@ -470,6 +483,8 @@ int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const doub
   uint8_t* Bd = ws + 1024;
 
   cudaMemsetAsync(ws, 0, 1024, st);
+  const int brows = rxu_brows(KPAD);
+  if (brows > RXU_VDIG * KPAD) cudaMemsetAsync(Bd + (size_t)RXU_VDIG * KPAD * ld, 0, (size_t)(brows - RXU_VDIG * KPAD) * ld, st);   // the zero digit rows
   int nb = (cols + 63) / 64;
   if (nb > 296) nb = 296;
   k_rxu_colmax<<<nb, 256, 0, st>>>(Xp, cols, K, KP, colmax, flag);
@@ -480,9 +495,9 @@ int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const doub
 
   CUtensorMap tmap;
   {
-    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)(RXU_VDIG * KPAD)};
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)brows};
     const cuuint64_t gstr[1] = {(cuuint64_t)ld};
-    const cuuint32_t box[2] = {(cuuint32_t)RXU_KT, (cuuint32_t)(RXU_VDIG * KPAD)};
+    const cuuint32_t box[2] = {(cuuint32_t)RXU_KT, (cuuint32_t)brows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, Bd, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -494,7 +509,7 @@ int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const doub
   a.tiles_per_seg = (a.ktiles + nseg - 1) / nseg;
   if ((a.ktiles + a.tiles_per_seg - 1) / a.tiles_per_seg != nseg) { set_error("stats_rx_umma: nseg=%d leaves empty segments", nseg); return -2; }
   a.out = out; a.nseg = nseg;
-  const int stage_bytes = RXU_A_BYTES + RXU_VDIG * KPAD * RXU_KT;
+  const int stage_bytes = RXU_A_BYTES + brows * RXU_KT;
   const int tail = (2 * 8 + 4) * 8 + 64;
   int stages = (227 * 1024 - 1024 - tail) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -508,7 +523,7 @@ int launch_stats_rx_umma(const uint8_t* planes, const double* rscale, const doub
   int nctas = nitems;                                  // default: one item per CTA (the block scheduler balances the tail)
   int cluster = 1;
   if (max_ctas > 0 && max_ctas < nctas && max_ctas <= sm_count) { nctas = max_ctas; if (nctas >= 2) { nctas &= ~1; cluster = 2; } }
-  void (*kern)(const CUtensorMap, RxUmmaArgs) = KPAD == 32 ? k_rx_umma<32> : k_rx_umma<16>;
+  void (*kern)(const CUtensorMap, RxUmmaArgs) = KPAD == 32 ? k_rx_umma<32> : (KPAD == 24 ? k_rx_umma<24> : k_rx_umma<16>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nctas); cfg.blockDim = dim3(RXU_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
