@@ -40,6 +40,7 @@ int launch_stats_rx_umma(const uint8_t*, const double*, const double*, const uin
 int launch_stats_gram(const uint32_t*, int, int, const double*, const double*, int, int, int, double*, double*, const int*, cudaStream_t);
 int launch_gram_full(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
 long long umma_workspace_bytes(int, int, long long);
+int launch_stats_gram_fixup(const uint32_t*, int, int, int, const double*, const double*, int, int, double*, double*, cudaStream_t);
 int launch_stats_gram_umma(const uint32_t*, int, int, int, const double*, const double*, int, int, int, int, int, int, int,
                            double*, double*, void*, long long, cudaStream_t);
 int launch_pad_factor(const double*, const double*, int, int, int, double*, double*, cudaStream_t);
@@ -245,6 +246,13 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram: Vp and SVpart must be given together"); return -2; }
   return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, nullptr, ST(stream));
+}
+
+int bnmtf_stats_gram_fixup_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp, const double* Vp,
+                               int K, int polarity, double* Gseg, double* SVseg, void* stream) {
+  if (check_k(K)) return -2;
+  if ((Vp == nullptr) != (SVseg == nullptr)) { set_error("stats_gram_fixup: Vp and SVseg must be given together"); return -2; }
+  return launch_stats_gram_fixup(bits, (int)rows, (int)ld, (int)cols, Xp, Vp, K, polarity, Gseg, SVseg, ST(stream));
 }
 
 int64_t bnmtf_gram_umma_workspace_bytes(int K, int vb, int64_t ld) {

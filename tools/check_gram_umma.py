@@ -81,12 +81,17 @@ def run_case(idx):
     wsb = _lib.call("bnmtf_gram_umma_workspace_bytes", K, vb, ld)
     ws = torch.zeros(wsb + 1024, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 1023) // 1024 * 1024
-    G1 = torch.full((nseg * rows, GL), float("nan"), dtype=torch.float64, device=dev)
-    S1 = torch.full((nseg * rows, KP), float("nan"), dtype=torch.float64, device=dev) if vb else None
+    fixup = sparse and int(os.environ.get("FIXUP", "0"))
+    nsg = nseg + (1 if fixup else 0)
+    G1 = torch.full((nsg * rows, GL), float("nan"), dtype=torch.float64, device=dev)
+    S1 = torch.full((nsg * rows, KP), float("nan"), dtype=torch.float64, device=dev) if vb else None
 
     def umma():
         _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, cols, _ptr(Xp), _ptr(Vp) if vb else 0, K, pol, nseg,
                   tile, PAIR, sums, stages, _ptr(G1), _ptr(S1), wsp, wsb, _stream())
+        if fixup:
+            _lib.call("bnmtf_stats_gram_fixup_f64", _ptr(bits), rows, ld, cols, _ptr(Xp), _ptr(Vp) if vb else 0, K, pol,
+                      G1.data_ptr() + 8 * nseg * rows * GL, S1.data_ptr() + 8 * nseg * rows * KP if vb else 0, _stream())
     umma()
     torch.cuda.synchronize()
     out = {"case": idx, "shape": [rows, cols, K], "vb": vb, "pol": pol, "nseg": nseg, "tile": tile, "signed": signed,
@@ -105,7 +110,7 @@ def run_case(idx):
     ia, ib = np.triu_indices(K)
     P = X[:, ia] * X[:, ib]
     Gref = W @ P                                   # nr x ng
-    Gu = G1.view(nseg, rows, GL).sum(0)[:nr]
+    Gu = G1.view(nsg, rows, GL).nan_to_num(0.0).sum(0)[:nr]
     NT = KP // 8
 
     def tile_index(a, b):
@@ -127,7 +132,7 @@ def run_case(idx):
     out["count_err"] = float((Gu[:, tile_index(K, K)] - W.sum(1)).abs().max())
     if vb:
         Sref = W @ Var
-        Su = S1.view(nseg, rows, KP).sum(0)[:nr, :K]
+        Su = S1.view(nsg, rows, KP).sum(0)[:nr, :K]
         out["sv_vs_ref"] = float(((Su - Sref).abs() / Sref.abs().max(0).values.clamp_min(1e-300)).max())
     if int(os.environ.get("STRESS", "0")):
         # exact integer accumulation: every call must give the same bits; report where repeated calls differ
