@@ -339,8 +339,10 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     // running indices of stage `it` (no divisions in the loop): pipeline slot / phase, mask window slot / phase / position
     int s = half % stages;
     uint32_t ph = (uint32_t)(half / stages) & 1u;
-    int c = half % WIN, qb = (half / WIN) % UG_MASK_BUFS;
-    uint32_t qph = (uint32_t)((half / WIN) / UG_MASK_BUFS) & 1u;
+    // (a window starts at a 16-byte boundary of the mask row: with 64-column stages an odd first stage sits one stage into it)
+    const int koff = KT == 64 ? (kt_begin & 1) : 0;
+    int c = (half + koff) % WIN, qb = ((half + koff) / WIN) % UG_MASK_BUFS;
+    uint32_t qph = (uint32_t)(((half + koff) / WIN) / UG_MASK_BUFS) & 1u;
     const int s_step = NG % stages, ph_step = (NG / stages) & 1;
     for (int it = half < NG ? half : ntile; it < ntile; it += NG) {
       const int wbase = (kt_begin + it) * WPT;
@@ -523,12 +525,13 @@ __global__ void __launch_bounds__(UG_THREADS, 1) k_gram_umma(const __grid_consta
     // ================= TMA producer of the mask windows =================
     if (lane == 0 && a.mask_tma) {
       constexpr int WIN = 512 / KT;
-      const int nwin = (ntile + WIN - 1) / WIN;
-      for (int q = 0; q < nwin; ++q) {                   // bit words of columns [(kt_begin + q WIN) KT, + 512) of the CTA's rows
+      const int koff = KT == 64 ? (kt_begin & 1) : 0;   // TMA needs a 16-byte aligned start: four words
+      const int nwin = (ntile + koff + WIN - 1) / WIN;
+      for (int q = 0; q < nwin; ++q) {                   // bit words of columns [(kt_begin - koff + q WIN) KT, + 512) of the CTA's rows
         const int qb = q % UG_MASK_BUFS;
         if (q >= UG_MASK_BUFS) mbar_wait(MASK_EMPTY(qb), ((uint32_t)(q / UG_MASK_BUFS) & 1u) ^ 1u);
         mbar_expect_tx(MASK_FULL(qb), (uint32_t)MASK_WIN_BYTES);
-        tma_load_2d(mask_base + (uint32_t)qb * MASK_WIN_BYTES, &tmap_bits, (kt_begin + q * WIN) * (KT / 32), rb * UG_ROWS, MASK_FULL(qb));
+        tma_load_2d(mask_base + (uint32_t)qb * MASK_WIN_BYTES, &tmap_bits, (kt_begin - koff + q * WIN) * (KT / 32), rb * UG_ROWS, MASK_FULL(qb));
       }
     }
     __syncwarp();

@@ -39,6 +39,11 @@ CASES = [
     (65536, 32768, 20, 1, 0, 1, 128, 0, 3, 0, 0),    # 19: VB row phase
     (8192, 32768, 20, 0, 0, 3, 128, 0, 3, 0, 0),     # 20: one rank of 8, row phase (Gibbs)
     (4096, 65536, 20, 1, 0, 3, 128, 0, 3, 1, 0),     # 21: one rank of 8, column phase (VB, with the column sums)
+    (80, 100, 10, 1, 0, 1, 64, 0, 0, 1, 0),          # 22: the toy matrix's column phase (VB): two 64-column stages, eight slots
+    (80, 100, 10, 1, 0, 1, 64, 0, 0, 0, 0),
+    (80, 100, 10, 0, 0, 1, 64, 0, 0, 0, 0),
+    (80, 100, 10, 1, 0, 2, 64, 0, 0, 0, 0),          # 25: one stage per segment
+    (100, 80, 10, 1, 0, 2, 64, 0, 0, 1, 0),
 ]
 
 
