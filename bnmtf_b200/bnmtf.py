@@ -381,10 +381,11 @@ class _ThreeFactorBase(object):
 
     def _kmeans_init(self, offset):
         from .kmeans import KMeans
-        kmeans_F = KMeans(self.R, self.M, self.K)
+        dev = require_cuda(self._device_arg)            # the assignment step runs on the device (csrc/kmeans.cu)
+        kmeans_F = KMeans(self.R, self.M, self.K, device=dev)
         kmeans_F.initialise()
         kmeans_F.cluster()
-        kmeans_G = KMeans(self.R.T, self.M.T, self.L)
+        kmeans_G = KMeans(self.R.T, self.M.T, self.L, device=dev)
         kmeans_G.initialise()
         kmeans_G.cluster()
         return kmeans_F.clustering_results + offset, kmeans_G.clustering_results + offset

@@ -57,6 +57,7 @@ int launch_tn_draw(const double*, const double*, long long, unsigned long long, 
 int launch_gamma_draw(double, double, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
 int launch_exponential_draw(const double*, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
 
+int launch_kmeans_dist(const double*, const double*, int, int, const double*, const double*, int, double*, cudaStream_t);
 int launch_row_solve(const RowSolveArgs&, cudaStream_t);
 int launch_np_build_pred(const double*, const double*, int, int, int, int, double*, cudaStream_t);
 int launch_np_row_update(const double*, const uint32_t*, double*, int, int, int, double*, const double*, int, cudaStream_t);
@@ -246,6 +247,11 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram: Vp and SVpart must be given together"); return -2; }
   return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, nullptr, ST(stream));
+}
+
+int bnmtf_kmeans_distances_f64(const double* X, const double* M, int64_t n, int64_t d, const double* centroids,
+                               const double* mask_centroids, int K, double* dist, void* stream) {
+  return launch_kmeans_dist(X, M, (int)n, (int)d, centroids, mask_centroids, K, dist, ST(stream));
 }
 
 int bnmtf_stats_gram_fixup_f64(const uint32_t* bits, int64_t rows, int64_t ld, int64_t cols, const double* Xp, const double* Vp,

@@ -13,6 +13,11 @@ data: the 'singleton' rule binds the empty cluster's centroid to the ROW OF X IT
 `self.centroids[c] = self.X[index_furthest_away]`, a numpy view of the model's private copy of X), so every later
 centroid update of that cluster (kmeans.py:170) also overwrites that data point.  Here the centroids are a list of row
 arrays as well, and the singleton rule stores the view, so the same write-through happens.
+
+The assignment step -- the no_points x K x no_coordinates part, everything else is O(K x no_coordinates) bookkeeping -- runs
+on the GPU when a device is given (csrc/kmeans.cu through bnmtf_kmeans_distances_f64: the same bits as the numpy
+expression in _all_distances, so the clustering is the same); the model classes always pass their device.  Without a
+device the class is the plain host port (tests/test_kmeans.py pins it against the reference's goldens on CPU).
 """
 import random
 
@@ -22,7 +27,10 @@ MAX_ITERATIONS = 200
 
 
 class KMeans(object):
-    def __init__(self, X, M, K, resolve_empty='singleton'):
+    def __init__(self, X, M, K, resolve_empty='singleton', device=None):
+        self.device = device
+        self._dev = None                # (X, M, centroid, mask, distance) device tensors, made on first use
+        self._aliased = set()           # rows of X a centroid is a view of (they change under update_cluster)
         self.X = np.array(X, dtype=float)
         self.M = np.array(M, dtype=float)
         self.K = K
@@ -64,8 +72,31 @@ class KMeans(object):
                 break
         self.create_matrix()
 
+    def _all_distances_device(self):
+        import torch
+        from . import _lib
+        from .engine import _ptr, _stream
+        n, d, K = self.no_points, self.no_coordinates, self.K
+        if self._dev is None:
+            dev = torch.device(self.device)
+            f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+            self._dev = {"X": f(self.X), "M": f(self.M), "C": torch.empty((K, d), dtype=torch.float64, device=dev),
+                         "MC": torch.empty((K, d), dtype=torch.float64, device=dev),
+                         "D": torch.empty((n, K), dtype=torch.float64, device=dev)}
+        t = self._dev
+        for i in sorted(self._aliased):                 # data points overwritten through a centroid view (see top)
+            t["X"][i].copy_(torch.from_numpy(np.ascontiguousarray(self.X[i])))
+        t["C"].copy_(torch.from_numpy(np.stack(self.centroids)))
+        t["MC"].copy_(torch.from_numpy(np.ascontiguousarray(self.mask_centroids, dtype=np.float64)))
+        with torch.cuda.device(t["X"].device):
+            _lib.call("bnmtf_kmeans_distances_f64", _ptr(t["X"]), _ptr(t["M"]), n, d, _ptr(t["C"]), _ptr(t["MC"]), K, _ptr(t["D"]),
+                      _stream())
+        return t["D"].cpu().numpy()
+
     def _all_distances(self):
         """no_points x K matrix of masked mean squared differences (inf where nothing overlaps)."""
+        if self.device is not None:
+            return self._all_distances_device()
         both = self.M[:, None, :] * self.mask_centroids[None, :, :]
         overlap = both.sum(axis=2)
         sq = (both * (self.X[:, None, :] - np.stack(self.centroids)[None, :, :]) ** 2).sum(axis=2)
@@ -94,6 +125,7 @@ class KMeans(object):
                     far = int(self.distances.argmax())
                     old = int(self.cluster_assignments[far])
                     self.centroids[c] = self.X[far]          # a VIEW: later updates of c write through into X (see top)
+                    self._aliased.add(far)
                     self.mask_centroids[c] = self.M[far]
                     self.distances[far] = 0.0
                     self.cluster_assignments[far] = c

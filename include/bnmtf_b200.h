@@ -125,6 +125,13 @@ int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, in
                               const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, int pair, int sums,
                               int max_stages, double* Gpart, double* SVpart /*or NULL*/, void* workspace,
                               int64_t workspace_bytes, void* stream);
+/* K-means with missing values, assignment step (code/models/kmeans/kmeans.py:105-133, closest_cluster / compute_MSE):
+ * dist[i*K + c] = sum_j M_ij MC_cj (X_ij - C_cj)^2 / sum_j M_ij MC_cj, +inf when point and centroid share no observed
+ * coordinate.  X, M: n x d; centroids, mask_centroids: K x d; all dense row-major doubles.  The sums are taken in numpy's
+ * pairwise order with separately rounded operations, so the result equals the host evaluation bit for bit (near-ties decide
+ * cluster membership). */
+int bnmtf_kmeans_distances_f64(const double* X, const double* M, int64_t n, int64_t d, const double* centroids,
+                               const double* mask_centroids, int K, double* dist, void* stream);
 /* The share the 2:4-sparse form leaves out (third and fourth selected column of every aligned group of four: 0.7 % of
  * the entries at 20 % missing), summed in fp64 (mma.sync.m8n8k4.f64 on gathered factor rows) into ONE segment: Gseg /
  * SVseg point at `rows` records laid out like a segment of Gpart / SVpart; pass nseg + 1 segments to the solver.  K <= 31. */
