@@ -360,7 +360,7 @@ def main(args, rank, world):
                      "scaling": "strong",
                      "config": {"workload": "BASELINE.json config 5: VB-NMTF, GDSC 622x138, 10 folds x (K,L) in [5..10]^2 = 360 fits; "
                                             "the first %d of the fixed job list dealt round-robin to %d rank(s), %d sweeps per fit, "
-                                            "K-means start on the host" % (len(timed), world, CV_ITS),
+                                            "K-means start with the assignment step on the device" % (len(timed), world, CV_ITS),
                                 "fits_per_s": len(timed) / dt, "mean_test_MSE": mse, "slowest_rank_busy_s": dt,
                                 "this_rank_busy_s": dt_own, "l2": "a fit's working set (1.4 MB) lives in L2; every fit re-uploads its data"},
                      "roofline": None,

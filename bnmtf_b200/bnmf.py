@@ -463,7 +463,8 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
                         _lib.call("bnmtf_accumulate_f64", _ptr(sums[1]), _ptr(eng.V.fac, lo_v), n_v * self.K, _stream())
         else:
             need = iterations * (n_u + n_v) * self.K * 8
-            free = torch.cuda.mem_get_info(dev)[0]
+            # (cudaMemGetInfo costs milliseconds: only asked when the draws are sizeable)
+            free = torch.cuda.mem_get_info(dev)[0] if need > (1 << 28) else float("inf")
             if need > 0.8 * free:
                 raise _lib.BnmtfError("run(%d) would keep %.1f GB of samples on the device (%.1f GB free): pass "
                                       "summary=(burn_in, thinning) to keep running sums instead" % (iterations, need / 1e9, free / 1e9))
