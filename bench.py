@@ -35,9 +35,11 @@ sys.path.insert(0, ROOT)
 HBM_FALLBACK_GBS = 6650.0
 # ncu dram bytes (read + write) per launch at the full 65536 x 32768 shape on one GPU, by digit count
 # (profiles/r01d_ncu_summary.txt, re-measured in profiles/r02_ncu_summary.txt); scaled by 1/world for a shard
-RX_TRAFFIC_PER_ENTRY = {7: 15.15e9 / 2.0 ** 31, 6: 12.98e9 / 2.0 ** 31}
-GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9, 6: 1.29e9}
-TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch at the full shape on one GPU (profiles/r01d_ncu_summary.txt), not re-measured in this run"
+RX_TRAFFIC_PER_ENTRY = {7: 15.15e9 / 2.0 ** 31, 6: 12.97e9 / 2.0 ** 31}
+GRAM_TRAFFIC_PER_LAUNCH = {7: 1.6e9, 6: 1.25e9}
+TRAFFIC_SOURCE = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch at the full shape on one GPU, taken inside "
+                  "the sweep (profiles/r03_k_gram_umma_details.txt: 1.05 GB + 0.20 GB; profiles/r03_k_rx_umma_details.txt: "
+                  "12.93 GB + 0.04 GB), not re-measured in this run")
 FP64_PEAK_TFLOPS = 37.1   # measured here: tools/microbench/fp64_pipes.cu -> profiles/r01_microbench_fp64_pipes.txt
 DTYPE = "f64 (statistics: 48-bit fixed point, exact int8 tcgen05 accumulation; solver, moments, draws: IEEE fp64)"
 PRIORS = {"alpha": 1.0, "beta": 1.0, "lambdaU": 0.1, "lambdaV": 0.1}
