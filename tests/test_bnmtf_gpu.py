@@ -299,3 +299,47 @@ def test_gibbs_chain_matches_reference_in_distribution(golden):
     assert abs(mse - ref_mse.mean()) <= max(5 * ref_mse.std(), 0.10 * ref_mse.mean())
     exp_tau = m.approx_expectation(burn, thin)[3]
     assert abs(exp_tau - ref_tau.mean()) <= max(5 * ref_tau.std(), 0.10 * ref_tau.mean())
+
+
+@pytest.mark.parametrize("cls_name,its", [("bnmtf_vb_optimised", 3), ("nmtf_icm", 3), ("bnmtf_gibbs_optimised", 2)])
+def test_large_matrices_run_the_tcgen05_statistics(monkeypatch, cls_name, its):
+    """From 2^22 entries the tri-factor engine takes its two statistics passes from the two-factor model's tcgen05 kernels
+    (fixed-point int8 GEMMs; the statistics of R ~ F S G^T w.r.t. G and w.r.t. F are two-factor statistics:
+    bnmtf_vb_optimised.py:245-280, bnmtf_gibbs_optimised.py:195-211).  Same trajectories as with the fp64 kernels."""
+    import bnmtf_b200
+    rng = np.random.RandomState(3)
+    I, J, K, L = 1500, 3000, 6, 5
+    R = np.abs(rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (K, L)) @ rng.exponential(1.0, (J, L)).T + rng.normal(size=(I, J))) + 0.5
+    M = (rng.rand(I, J) >= 0.2).astype(float)
+    pri = {"alpha": 1.0, "beta": 1.0, "lambdaF": 0.1, "lambdaS": 0.1, "lambdaG": 0.1}
+    cls = getattr(bnmtf_b200, cls_name)
+    out = {}
+    for impl in ("umma", "dmma"):
+        monkeypatch.setenv("BNMTF_NMTF_STATS", impl)
+        np.random.seed(11), random.seed(11)
+        m = cls(R, M, K, L, pri, seed=5)
+        m.initialise("random", "random")
+        if cls_name == "nmtf_icm":
+            m.run(its, minimum_TN=0.1)
+        else:
+            m.run(its)
+        assert m._engine().stats_impl == impl
+        out[impl] = m
+    monkeypatch.delenv("BNMTF_NMTF_STATS")
+    a, b = out["umma"], out["dmma"]
+    if cls_name == "bnmtf_vb_optimised":
+        for name in ("expF", "expS", "expG", "muF", "muS", "muG"):
+            close(getattr(a, name), getattr(b, name), what=name)
+        close(a.exptau, b.exptau)
+    else:
+        # (Gibbs: the same Philox streams, so the same draws while the conditionals agree to rounding)
+        for name in ("F", "S", "G"):
+            close(getattr(a, name), getattr(b, name), rtol=1e-8 if cls_name == "bnmtf_gibbs_optimised" else 1e-9, what=name)
+        close(a.tau, b.tau, rtol=1e-8)
+    close(a.all_performances["MSE"], b.all_performances["MSE"], rtol=1e-8 if cls_name == "bnmtf_gibbs_optimised" else 1e-9)
+    # the automatic choice at this size
+    m = cls(R, M, K, L, pri, seed=5)
+    np.random.seed(11), random.seed(11)
+    m.initialise("random", "random")
+    m.run(1) if cls_name != "nmtf_icm" else m.run(1, minimum_TN=0.1)
+    assert m._engine().stats_impl == "umma"
