@@ -1,3 +1,4 @@
+"""One line per bench.py JSON line (stdin -> stdout): value, sustained, per-kernel times alone and inside the sweep."""
 import sys, json
 for l in sys.stdin:
     l = l.strip()

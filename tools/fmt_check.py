@@ -1,3 +1,4 @@
+"""One line per JSON result of tools/check_gram_umma.py (stdin -> stdout): shape, form, time, errors."""
 import sys, json
 for l in sys.stdin:
     try: d = json.loads(l)
