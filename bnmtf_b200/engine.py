@@ -361,7 +361,11 @@ class BNMFEngine:
         g = int(os.environ.get("BNMTF_GRAPH", "1"))
         self.use_graph = g >= 1 and dataset.world == 1          # sharded: decided below, once the exchange path is known
         self._graph = self._graph_key = self._graph_seen = None
-        self.split = int(os.environ.get("BNMTF_SPLIT", "64"))    # SMs given to the R.X kernel when both run concurrently (0: one after the other)
+        # SMs given to the R.X kernel when both statistics kernels run concurrently (0: one after the other).  The Gram
+        # kernel's work grows with K(K+1)/2, the R.X kernel's with K and never below the time to stream the planes:
+        # measured best 64 at K = 20 (127.3 / 129.6 / 127.6 sweeps/s at 72 / 64 / 60), 80 at K = 10 (208 vs 197 at 64),
+        # 96 at K = 5 (245 vs 228)
+        self.split = int(os.environ.get("BNMTF_SPLIT", "64" if self.K > 16 else ("80" if self.K > 8 else "96")))
         # Gram kernel form (bit 0: CTA pairs, cta_group::2; bit 1: 2:4-sparse MMAs + fp64 fix-up segment; bit 2: clusters of
         # two pairs with multicast digit tiles).  Measured at the headline shape: the sparse kernel
         # alone takes 1.15 ms against 1.62 ms, but the fix-up of the 0.7 % of entries it leaves out gathers 3-6 GB of factor
