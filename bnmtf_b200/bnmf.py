@@ -382,9 +382,23 @@ class _TwoFactorBase(object):
         for metric in METRICS:
             self.all_performances[metric] = []
 
-    def _run_loop(self, eng, iterations, minimum_TN=0.0, per_iteration=None):
-        """Enqueue `iterations` sweeps; CUDA events give the reference's cumulative all_times."""
+    def _run_loop(self, eng, iterations, minimum_TN=0.0, per_iteration=None, samples=None, sums=None):
+        """Enqueue `iterations` sweeps; CUDA events give the reference's cumulative all_times.  samples = (all_U, all_V):
+        device tensors for the draw of every sweep, filled by per_iteration -- or by the kernel itself when the problem is
+        small enough for the single-kernel sweep (csrc/small.cu: the whole run is then one launch, and all_times comes
+        from the device's own clock)."""
         eng.alloc_trace(iterations)
+        if iterations > 0 and eng.small_cluster() and (per_iteration is None or samples is not None or sums is not None):
+            times = torch.zeros(iterations + 1, dtype=torch.int64, device=eng.ds.device)
+            eng.sweep_many(iterations, minimum_TN, samples[0] if samples else None, samples[1] if samples else None, times, sums)
+            torch.cuda.synchronize()
+            t = times.cpu().numpy()
+            self.all_times = [float(x - t[0]) / 1e9 for x in t[1:]]
+            XFER[1] += eng.trace.numel() * 8
+            tr = eng.trace.cpu().numpy()[:iterations]
+            for i, metric in enumerate(METRICS):
+                self.all_performances[metric] = [float(v) for v in tr[:, 1 + i]]
+            return tr
         start = torch.cuda.Event(enable_timing=True)
         marks = []
         start.record()
@@ -479,7 +493,8 @@ class bnmf_gibbs_optimised(_TwoFactorBase):
                 if n_v:
                     all_V[it, :n_v].copy_(eng.V.fac[lo_v:lo_v + n_v])
         self._init_trace_lists()
-        tr = self._run_loop(eng, iterations, per_iteration=keep)
+        tr = self._run_loop(eng, iterations, per_iteration=keep, samples=(all_U, all_V) if summary is None else None,
+                            sums=(sums[0], sums[1], burn_in, thinning) if summary is not None else None)
         store['iterations'] = iterations
         self._samples = store
         self.U, self.V = self._down_s('U', eng.U.fac, eng.U), self._down_s('V', eng.V.fac, eng.V)

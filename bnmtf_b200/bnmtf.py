@@ -98,6 +98,9 @@ class BNMTFEngine:
         self.lgamma_alpha_s = float(gammaln(self.alpha_s))
         self.sterm = None
 
+    def small_cluster(self):
+        return 0                     # (the single-kernel sweep of csrc/small.cu covers the two-factor models only)
+
     # ---- layer 1 ------------------------------------------------------------------------------------------
     def _stats(self, st, R, bits, rows, ld, other, dim, need_rx=True):
         other.pad()

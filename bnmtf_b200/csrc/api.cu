@@ -57,6 +57,21 @@ int launch_tn_draw(const double*, const double*, long long, unsigned long long, 
 int launch_gamma_draw(double, double, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
 int launch_exponential_draw(const double*, long long, unsigned long long, unsigned long long, double*, cudaStream_t);
 
+struct SmallArgs {
+  int mode, I, J, K, ldJ, ldI, nrow[2];
+  const double* R; const uint32_t* bits; const double* RT; const uint32_t* bitsT;
+  double* fac[2]; double* var[2]; double* mu[2]; double* tauf[2]; const double* lam[2];
+  double* scalars; double* trace; unsigned long long* iter; int trace_cap;
+  double alpha, beta, digamma_alpha_s, lgamma_alpha, lgamma_alpha_s, min_tn;
+  unsigned long long seed;
+  int sweeps;
+  double* all_U; double* all_V;
+  double* sum_U; double* sum_V; int burn_in, thinning;
+  double* partial;
+  unsigned long long* times;
+};
+int small_cluster_size(int, int, int, int);
+int launch_small_sweeps(SmallArgs, cudaStream_t);
 int launch_kmeans_dist(const double*, const double*, int, int, const double*, const double*, int, double*, cudaStream_t);
 int launch_row_solve(const RowSolveArgs&, cudaStream_t);
 int launch_np_build_pred(const double*, const double*, int, int, int, int, double*, cudaStream_t);
@@ -247,6 +262,33 @@ int bnmtf_stats_gram_f64(const uint32_t* bits, int64_t rows, int64_t ld, const d
   if (check_k(K)) return -2;
   if ((Vp == nullptr) != (SVpart == nullptr)) { set_error("stats_gram: Vp and SVpart must be given together"); return -2; }
   return launch_stats_gram(bits, (int)rows, (int)ld, Xp, Vp, K, polarity, nseg, Gpart, SVpart, nullptr, ST(stream));
+}
+
+int bnmtf_small_cluster_size(int64_t I, int64_t J, int K, int vb) {
+  if (I > 1000000 || J > 1000000) return 0;
+  return small_cluster_size((int)I, (int)J, K, vb);
+}
+
+int bnmtf_small_sweeps_f64(int mode, const double* R, const uint32_t* bits, const double* RT, const uint32_t* bitsT, int64_t I,
+                           int64_t J, int64_t ldJ, int64_t ldI, int K, double* U, double* varU, double* muU, double* tauU,
+                           const double* lambdaU, double* V, double* varV, double* muV, double* tauV, const double* lambdaV,
+                           double* scalars, double* trace, uint64_t* iter, int64_t trace_cap, double alpha, double beta,
+                           double digamma_alpha_s, double lgamma_alpha, double lgamma_alpha_s, double minimum_TN, uint64_t seed,
+                           int sweeps, double* all_U, double* all_V, double* sum_U, double* sum_V, int burn_in, int thinning,
+                           double* partial, uint64_t* times, void* stream) {
+  if (mode < 0 || mode > 2) { set_error("small_sweeps: bad mode %d", mode); return -2; }
+  if (mode == 1 && (!varU || !varV)) { set_error("small_sweeps: VB needs the variance arrays"); return -2; }
+  SmallArgs a;
+  a.mode = mode; a.I = (int)I; a.J = (int)J; a.K = K; a.ldJ = (int)ldJ; a.ldI = (int)ldI; a.nrow[0] = a.nrow[1] = 0;
+  a.R = R; a.bits = bits; a.RT = RT; a.bitsT = bitsT;
+  a.fac[0] = U; a.var[0] = varU; a.mu[0] = muU; a.tauf[0] = tauU; a.lam[0] = lambdaU;
+  a.fac[1] = V; a.var[1] = varV; a.mu[1] = muV; a.tauf[1] = tauV; a.lam[1] = lambdaV;
+  a.scalars = scalars; a.trace = trace; a.iter = reinterpret_cast<unsigned long long*>(iter); a.trace_cap = (int)trace_cap;
+  a.alpha = alpha; a.beta = beta; a.digamma_alpha_s = digamma_alpha_s; a.lgamma_alpha = lgamma_alpha;
+  a.lgamma_alpha_s = lgamma_alpha_s; a.min_tn = minimum_TN; a.seed = seed; a.sweeps = sweeps;
+  a.all_U = all_U; a.all_V = all_V; a.sum_U = sum_U; a.sum_V = sum_V; a.burn_in = burn_in; a.thinning = thinning < 1 ? 1 : thinning;
+  a.partial = partial; a.times = reinterpret_cast<unsigned long long*>(times);
+  return launch_small_sweeps(a, ST(stream));
 }
 
 int bnmtf_kmeans_distances_f64(const double* X, const double* M, int64_t n, int64_t d, const double* centroids,

@@ -857,6 +857,32 @@ class BNMFEngine:
         out["_meta"] = {"gram": self.gram, "rx": self.rx, "metrics_mode": self.metrics_mode, "split": self.split}
         return out
 
+    # ---- small problems: the whole run as ONE kernel (csrc/small.cu) ----------------------------------------
+    def small_cluster(self):
+        """Cluster size of the single-kernel sweep for this problem, 0 when it does not qualify (large matrix, K > 16,
+        sharded run, BNMTF_SMALL=0)."""
+        if getattr(self, "_small_c", None) is None:
+            ok = self.comm.world == 1 and os.environ.get("BNMTF_SMALL", "1") != "0"
+            self._small_c = int(_lib.call("bnmtf_small_cluster_size", self.ds.I, self.ds.J, self.K, int(self.vb))) if ok else 0
+            if self._small_c:
+                self._small_partial = torch.zeros(16 * 16, dtype=torch.float64, device=self.ds.device)
+        return self._small_c
+
+    def sweep_many(self, sweeps, minimum_TN=0.0, all_U=None, all_V=None, times=None, sums=None):
+        """`sweeps` iterations of run() in one launch (small_cluster() must be non-zero).  all_U / all_V: device tensors
+        [sweeps, n, K] that receive the Gibbs draw of every sweep; sums = (sum_U, sum_V, burn_in, thinning): running sums of
+        the kept draws instead; times: int64 device tensor of sweeps + 1 timestamps."""
+        sU, sV, burn_in, thinning = sums if sums is not None else (None, None, 0, 1)
+        trace_ptr = _ptr(self.trace) - self.trace_base * 64 if self.trace is not None else 0
+        ds, U, V = self.ds, self.U, self.V
+        _lib.call("bnmtf_small_sweeps_f64", self.m, _ptr(ds.R), _ptr(ds.bits), _ptr(ds.RT), _ptr(ds.bitsT), ds.I, ds.J, ds.ldJ, ds.ldI,
+                  self.K, _ptr(U.fac), _ptr(U.var), _ptr(U.mu), _ptr(U.tauf), _ptr(U.lam), _ptr(V.fac), _ptr(V.var), _ptr(V.mu),
+                  _ptr(V.tauf), _ptr(V.lam), _ptr(self.scalars), trace_ptr, _ptr(self.iter), self.trace_base + self.trace_cap,
+                  self.alpha, self.beta, self.digamma_alpha_s, self.lgamma_alpha, self.lgamma_alpha_s, float(minimum_TN),
+                  self.seed, int(sweeps), _ptr(all_U), _ptr(all_V), _ptr(sU), _ptr(sV), int(burn_in), int(thinning),
+                  _ptr(self._small_partial), _ptr(times), _stream())
+        self.sweeps_done += int(sweeps)
+
     def alloc_trace(self, iterations):
         self.trace_cap = int(iterations)
         self.trace = torch.zeros((max(1, self.trace_cap), 8), dtype=torch.float64, device=self.ds.device)

@@ -125,6 +125,23 @@ int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, in
                               const double* Vp /*or NULL*/, int K, int polarity, int nseg, int tile, int pair, int sums,
                               int max_stages, double* Gpart, double* SVpart /*or NULL*/, void* workspace,
                               int64_t workspace_bytes, void* stream);
+/* Single-kernel sweeps for small two-factor problems (K <= 16, a few hundred rows and columns: the reference's toy and
+ * GDSC matrices).  One thread-block cluster runs `sweeps` whole iterations of bnmf_gibbs_optimised.run /
+ * bnmf_vb_optimised.run / nmf_icm.run (bnmf_gibbs_optimised.py:121-157, bnmf_vb_optimised.py:121-153, nmf_icm.py:114-149)
+ * on the same device state as the per-phase entry points above -- factor arrays n x K, scalars, trace rows, sweep counter --
+ * with the same formulas and Philox streams.  mode: 0 Gibbs, 1 VB, 2 ICM.  R / RT: dense rows x ld doubles, bits / bitsT
+ * their mask words (bnmtf_pack_dataset_f64 / bnmtf_transpose_dataset_f64).  all_U / all_V (Gibbs, or NULL) receive the draw
+ * of every sweep ([sweep][n][K]), sum_U / sum_V (or NULL) the running sums of the draws of sweeps burn_in, burn_in + thinning,
+ * ... (bnmf_gibbs_optimised.py:182-187); partial: 16 x 16 doubles of scratch; times (or NULL): sweeps + 1 %globaltimer values.
+ * bnmtf_small_cluster_size returns the cluster size used for (I, J, K), 0 when the problem does not qualify. */
+int bnmtf_small_cluster_size(int64_t I, int64_t J, int K, int vb);
+int bnmtf_small_sweeps_f64(int mode, const double* R, const uint32_t* bits, const double* RT, const uint32_t* bitsT, int64_t I,
+                           int64_t J, int64_t ldJ, int64_t ldI, int K, double* U, double* varU, double* muU, double* tauU,
+                           const double* lambdaU, double* V, double* varV, double* muV, double* tauV, const double* lambdaV,
+                           double* scalars, double* trace, uint64_t* iter, int64_t trace_cap, double alpha, double beta,
+                           double digamma_alpha_s, double lgamma_alpha, double lgamma_alpha_s, double minimum_TN, uint64_t seed,
+                           int sweeps, double* all_U, double* all_V, double* sum_U, double* sum_V, int burn_in, int thinning,
+                           double* partial, uint64_t* times, void* stream);
 /* K-means with missing values, assignment step (code/models/kmeans/kmeans.py:105-133, closest_cluster / compute_MSE):
  * dist[i*K + c] = sum_j M_ij MC_cj (X_ij - C_cj)^2 / sum_j M_ij MC_cj, +inf when point and centroid share no observed
  * coordinate.  X, M: n x d; centroids, mask_centroids: K x d; all dense row-major doubles.  The sums are taken in numpy's
