@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 namespace bnmtf {
 
 constexpr int SM_KMAX = 16;
-constexpr int SM_THREADS = 256;
+constexpr int SM_THREADS = 512;
 constexpr int SM_WARPS = SM_THREADS / 32;
 constexpr int SM_PARTIAL = 16;       // doubles of scratch per CTA
 
@@ -56,10 +56,10 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // shared-memory carve-up (doubles unless noted); sizes computed identically on the host (small_smem_bytes)
 struct SmallSmem {
-  double* Rs; double* RTs; uint32_t* Ms; uint32_t* MTs; double* buf; double* stats; double* red;
+  double* Rs; double* RTs; uint32_t* Ms; uint32_t* MTs; double* buf; double* stats; double* red; double* ubuf;
 };
 
-__host__ __device__ inline size_t small_layout(int I, int J, int K, int vb, int nr0, int nr1, size_t off[7]) {
+__host__ __device__ inline size_t small_layout(int I, int J, int K, int vb, int nr0, int nr1, size_t off[8]) {
   const int wJ = (J + 31) / 32, wI = (I + 31) / 32, nmax = nr0 > nr1 ? nr0 : nr1, cmax = I > J ? I : J;
   const int ns = K * (K + 1) / 2 + 2 * K;
   size_t o = 0;
@@ -70,20 +70,86 @@ __host__ __device__ inline size_t small_layout(int I, int J, int K, int vb, int 
   off[4] = o; o += (size_t)cmax * K * (vb ? 2 : 1) * 8;
   off[5] = o; o += (size_t)nmax * (ns > K ? ns : K) * 8;
   off[6] = o; o += 64 * 8;
+  off[7] = o; o += (size_t)K * nmax * 8;                 // the update chains' current row values, [k][row]
   return o;
+}
+
+// row statistics of one phase: a warp per row, lane = (column group, k).  K is a compile-time constant here: with a
+// run-time K every "if (k2 < K)" of the unrolled inner loop became a basic block of its own and the ten shared-memory
+// loads of an iteration were issued one after the other (measured: 490 clk per iteration instead of ~60).
+template <int K, bool VB>
+__device__ void small_stats(const SmallSmem& sm, const double* __restrict__ slice, const uint32_t* __restrict__ mb, int cols, int nr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpr = (cols + 31) / 32;
+  constexpr int NT = K * (K + 1) / 2, NS = NT + 2 * K, NG = 32 / K;
+  const int grp = lane / K, kk = lane - grp * K;
+  const bool active = lane < NG * K;
+  const double* X = sm.buf;
+  const double* XV = sm.buf + (size_t)cols * K;
+  for (int r = warp; r < nr; r += SM_WARPS) {
+    double g[K];
+#pragma unroll
+    for (int k2 = 0; k2 < K; ++k2) g[k2] = 0.0;
+    double c = 0.0, sv = 0.0;
+    if (active) {
+      const double* rrow = slice + (size_t)r * cols;
+      const uint32_t* mrow = mb + (size_t)r * wpr;
+#pragma unroll 2
+      for (int j = grp; j < cols; j += NG) {
+        const bool m = (mrow[j >> 5] >> (j & 31)) & 1u;
+        const double* xj = X + (size_t)j * K;
+        const double x = m ? xj[kk] : 0.0;
+        c = fma(rrow[j], x, c);
+        if (VB) sv += m ? XV[(size_t)j * K + kk] : 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < K; ++k2) g[k2] = fma(x, xj[k2], g[k2]);
+      }
+    }
+    // add the column groups (fixed order) into the lanes of group 0; the shuffled values are the groups' own partial sums
+    // (they are never modified here: every lane takes part in every shuffle)
+    double ct = c, svt = sv, gt[K];
+#pragma unroll
+    for (int k2 = 0; k2 < K; ++k2) gt[k2] = g[k2];
+#pragma unroll
+    for (int gg = 1; gg < NG; ++gg) {
+      const int src = (kk + gg * K) & 31;
+      ct += __shfl_sync(0xffffffffu, c, src);
+      if (VB) svt += __shfl_sync(0xffffffffu, sv, src);
+#pragma unroll
+      for (int k2 = 0; k2 < K; ++k2) gt[k2] += __shfl_sync(0xffffffffu, g[k2], src);
+    }
+    if (lane < K) {
+      double* st = sm.stats + (size_t)r * NS;
+#pragma unroll
+      for (int k2 = 0; k2 < K; ++k2)
+        if (k2 >= kk) st[tri_index(kk, k2, K)] = gt[k2];
+      st[NT + kk] = ct;
+      st[NT + K + kk] = svt;
+    }
+  }
+}
+
+template <bool VB>
+__device__ void small_stats_k(int K, const SmallSmem& sm, const double* slice, const uint32_t* mb, int cols, int nr) {
+  switch (K) {
+#define BNMTF_SMALL_K(KV) case KV: small_stats<KV, VB>(sm, slice, mb, cols, nr); break;
+    BNMTF_SMALL_K(1) BNMTF_SMALL_K(2) BNMTF_SMALL_K(3) BNMTF_SMALL_K(4) BNMTF_SMALL_K(5) BNMTF_SMALL_K(6) BNMTF_SMALL_K(7) BNMTF_SMALL_K(8)
+    BNMTF_SMALL_K(9) BNMTF_SMALL_K(10) BNMTF_SMALL_K(11) BNMTF_SMALL_K(12) BNMTF_SMALL_K(13) BNMTF_SMALL_K(14) BNMTF_SMALL_K(15)
+    BNMTF_SMALL_K(16)
+#undef BNMTF_SMALL_K
+  }
 }
 
 // one phase: rows [r0, r0 + nr) of the side-s data (s = 0: rows of R, factor U; s = 1: rows of R^T, factor V)
 template <int MODE>
 __device__ void small_phase(const SmallArgs& a, const SmallSmem& sm, int s, int r0, int nr, unsigned long long it, int sweep,
-                            double& ex_out) {
+                            double& ex_out, double* dbg) {
   const int K = a.K, o = 1 - s;
   const int cols = s == 0 ? a.J : a.I;
-  const int wpr = (cols + 31) / 32;
   const double* slice = s == 0 ? sm.Rs : sm.RTs;
   const uint32_t* mb = s == 0 ? sm.Ms : sm.MTs;
   constexpr bool VB = MODE == MODE_VB;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int NT = K * (K + 1) / 2, NS = NT + 2 * K;
   // 1. the other factor, from L2 (written by the other CTAs before the last cluster barrier)
   double* X = sm.buf;
@@ -93,98 +159,54 @@ __device__ void small_phase(const SmallArgs& a, const SmallSmem& sm, int s, int 
     if (VB) XV[i] = __ldcg(a.var[o] + i);
   }
   __syncthreads();
-  // 2. row statistics: a warp per row, lane = (column group, k)
-  const int NG = 32 / K, grp = lane / K, kk = lane - grp * K;
-  const bool active = lane < NG * K;
-  for (int r = warp; r < nr; r += SM_WARPS) {
-    double g[SM_KMAX];
-#pragma unroll
-    for (int k2 = 0; k2 < SM_KMAX; ++k2) g[k2] = 0.0;
-    double c = 0.0, sv = 0.0;
-    if (active) {
-      const double* rrow = slice + (size_t)r * cols;
-      const uint32_t* mrow = mb + (size_t)r * wpr;
-      for (int j = grp; j < cols; j += NG) {
-        const bool m = (mrow[j >> 5] >> (j & 31)) & 1u;
-        const double* xj = X + (size_t)j * K;
-        const double x = m ? xj[kk] : 0.0;
-        c = fma(rrow[j], x, c);
-        if (VB) sv += m ? XV[(size_t)j * K + kk] : 0.0;
-#pragma unroll
-        for (int k2 = 0; k2 < SM_KMAX; ++k2)
-          if (k2 < K) g[k2] = fma(x, xj[k2], g[k2]);
-      }
-    }
-    // add the column groups (fixed order) into the lanes of group 0; the shuffled values are the groups' own partial sums
-    // (they are never modified here: every lane takes part in every shuffle)
-    double ct = c, svt = sv, gt[SM_KMAX];
-#pragma unroll
-    for (int k2 = 0; k2 < SM_KMAX; ++k2) gt[k2] = g[k2];
-    for (int gg = 1; gg < NG; ++gg) {
-      const int src = (kk + gg * K) & 31;
-      ct += __shfl_sync(0xffffffffu, c, src);
-      if (VB) svt += __shfl_sync(0xffffffffu, sv, src);
-#pragma unroll
-      for (int k2 = 0; k2 < SM_KMAX; ++k2)
-        if (k2 < K) gt[k2] += __shfl_sync(0xffffffffu, g[k2], src);
-    }
-    if (lane < K) {
-      double* st = sm.stats + (size_t)r * NS;
-#pragma unroll
-      for (int k2 = 0; k2 < SM_KMAX; ++k2)
-        if (k2 < K && k2 >= kk) st[tri_index(kk, k2, K)] = gt[k2];
-      st[NT + kk] = ct;
-      st[NT + K + kk] = svt;
-    }
-  }
+  if (dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[0] = (double)(t & 0xffffffffffffull); }
+  // 2. row statistics
+  small_stats_k<VB>(K, sm, slice, mb, cols, nr);
   __syncthreads();
-  // 3. the K sequential updates: a thread per row (solve.cu::k_bnmf_row_solve_lane is the large-matrix form of this loop)
+  if (dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[1] = (double)(t & 0xffffffffffffull); }
+  // 3. the K sequential updates: a thread per row (solve.cu::k_bnmf_row_solve_lane is the large-matrix form of this loop).
+  // Run-time loops with the row's current values in shared memory ([k][thread]): the truncated-normal code exists once.
   double ex = 0.0;
   if (tid < nr) {
     const int row = r0 + tid;
     const double* st = sm.stats + (size_t)tid * NS;
+    double* u = sm.ubuf + tid;                          // u[k * nr_stride]
+    const int us = a.nrow[0] > a.nrow[1] ? a.nrow[0] : a.nrow[1];
     const double tau = __ldcg(a.scalars + S_TAU);
-    double u[SM_KMAX];
-#pragma unroll
-    for (int k = 0; k < SM_KMAX; ++k) u[k] = k < K ? __ldcg(a.fac[s] + (size_t)row * K + k) : 0.0;
-#pragma unroll
-    for (int k = 0; k < SM_KMAX; ++k) {
-      if (k < K) {
-        double acck = 0.0, part = 0.0;
-#pragma unroll
-        for (int c2 = 0; c2 < SM_KMAX; ++c2) {
-          if (c2 < k) acck = fma(st[tri_index(c2, k, K)], u[c2], acck);
-          else if (c2 > k && c2 < K) part = fma(st[tri_index(k, c2, K)], u[c2], part);
-        }
-        const double gkk = st[tri_index(k, k, K)], rxk = st[NT + k], svk = VB ? st[NT + K + k] : 0.0;
-        const double sres = rxk - (acck + part);
-        const double b = VB ? gkk + svk : gkk;
-        const size_t idx = (size_t)row * K + k;
-        const double lam = a.lam[s][idx];
-        const double tau_k = tau * b;
-        const double mu_k = (1.0 / tau_k) * (-lam + tau * sres);
-        double val = 0.0, vv = 0.0;
-        if (MODE == MODE_GIBBS) {
-          Philox rng(a.seed, it * 16ull + (unsigned long long)s, (unsigned long long)row * K + k);
-          val = tn_draw(mu_k, tau_k, rng);
-        } else if (VB) {
-          tn_moments(mu_k, tau_k, val, vv);
-        } else {
-          val = (mu_k != mu_k) ? mu_k : fmax(mu_k, 0.0);   // numpy.maximum propagates NaN (nmf_icm.py:129)
-          val = (val != val) ? val : fmax(val, a.min_tn);
-        }
-        u[k] = val;
-        a.fac[s][idx] = val;
-        if (VB) a.var[s][idx] = vv;
-        a.mu[s][idx] = mu_k;
-        a.tauf[s][idx] = tau_k;
-        ex += vv * (gkk + svk) + val * val * svk;
-        if (MODE == MODE_GIBBS) {
-          double* all = s == 0 ? a.all_U : a.all_V;
-          if (all) all[((size_t)sweep * (s == 0 ? a.I : a.J) + row) * K + k] = val;
-          double* sums = s == 0 ? a.sum_U : a.sum_V;
-          if (sums && sweep >= a.burn_in && (sweep - a.burn_in) % a.thinning == 0) sums[idx] += val;
-        }
+    for (int k = 0; k < K; ++k) u[k * us] = __ldcg(a.fac[s] + (size_t)row * K + k);
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      double acck = 0.0, part = 0.0;
+      for (int c2 = 0; c2 < k; ++c2) acck = fma(st[tri_index(c2, k, K)], u[c2 * us], acck);
+      for (int c2 = k + 1; c2 < K; ++c2) part = fma(st[tri_index(k, c2, K)], u[c2 * us], part);
+      const double gkk = st[tri_index(k, k, K)], rxk = st[NT + k], svk = VB ? st[NT + K + k] : 0.0;
+      const double sres = rxk - (acck + part);
+      const double b = VB ? gkk + svk : gkk;
+      const size_t idx = (size_t)row * K + k;
+      const double lam = a.lam[s][idx];
+      const double tau_k = tau * b;
+      const double mu_k = (1.0 / tau_k) * (-lam + tau * sres);
+      double val = 0.0, vv = 0.0;
+      if (MODE == MODE_GIBBS) {
+        Philox rng(a.seed, it * 16ull + (unsigned long long)s, (unsigned long long)row * K + k);
+        val = tn_draw(mu_k, tau_k, rng);
+      } else if (VB) {
+        tn_moments(mu_k, tau_k, val, vv);
+      } else {
+        val = (mu_k != mu_k) ? mu_k : fmax(mu_k, 0.0);   // numpy.maximum propagates NaN (nmf_icm.py:129)
+        val = (val != val) ? val : fmax(val, a.min_tn);
+      }
+      u[k * us] = val;
+      a.fac[s][idx] = val;
+      if (VB) a.var[s][idx] = vv;
+      a.mu[s][idx] = mu_k;
+      a.tauf[s][idx] = tau_k;
+      ex += vv * (gkk + svk) + val * val * svk;
+      if (MODE == MODE_GIBBS) {
+        double* all = s == 0 ? a.all_U : a.all_V;
+        if (all) all[((size_t)sweep * (s == 0 ? a.I : a.J) + row) * K + k] = val;
+        double* sums = s == 0 ? a.sum_U : a.sum_V;
+        if (sums && sweep >= a.burn_in && (sweep - a.burn_in) % a.thinning == 0) sums[idx] += val;
       }
     }
   }
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_small_sweeps(SmallArgs a) {
   const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, K = a.K;
   constexpr bool VB = MODE == MODE_VB;
-  size_t off[7];
+  size_t off[8];
   small_layout(a.I, a.J, K, VB, a.nrow[0], a.nrow[1], off);
   SmallSmem sm;
   sm.Rs = reinterpret_cast<double*>(smem_raw + off[0]);
@@ -208,6 +230,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_small_sweeps(SmallArgs a) {
   sm.buf = reinterpret_cast<double*>(smem_raw + off[4]);
   sm.stats = reinterpret_cast<double*>(smem_raw + off[5]);
   sm.red = reinterpret_cast<double*>(smem_raw + off[6]);
+  sm.ubuf = reinterpret_cast<double*>(smem_raw + off[7]);
   // this CTA's rows of both orientations
   int r0[2], nr[2];
   for (int s = 0; s < 2; ++s) {
@@ -243,15 +266,28 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_small_sweeps(SmallArgs a) {
   }
   const int NT = K * (K + 1) / 2;
   (void)NT;
+  auto stamp = [&](int sweep, int q) {                 // stage boundaries of the last sweep (rank 0), for tools/small_sweep_times.py
+    if (rank == 0 && tid == 0 && sweep == a.sweeps - 1) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.partial[16 * SM_PARTIAL + q] = (double)(t & 0xffffffffffffull);
+      if (q == 0 || q == 8) a.partial[16 * SM_PARTIAL + 9 + (q >> 3)] = (double)(clock64() & 0xffffffffffffll);     // -> SM clock
+    }
+  };
   for (int sweep = 0; sweep < a.sweeps; ++sweep) {
     const unsigned long long it = __ldcg(a.iter);
     double ex0, ex1;
-    small_phase<MODE>(a, sm, 0, r0[0], nr[0], it, sweep, ex0);
+    stamp(sweep, 0);
+    small_phase<MODE>(a, sm, 0, r0[0], nr[0], it, sweep, ex0, (rank == 0 && sweep == a.sweeps - 1) ? a.partial + 16 * SM_PARTIAL + 11 : nullptr);
+    stamp(sweep, 1);
     __threadfence();
     cluster.sync();
-    small_phase<MODE>(a, sm, 1, r0[1], nr[1], it, sweep, ex1);
+    stamp(sweep, 2);
+    small_phase<MODE>(a, sm, 1, r0[1], nr[1], it, sweep, ex1, nullptr);
+    stamp(sweep, 3);
     __threadfence();
     cluster.sync();
+    stamp(sweep, 4);
     // ---- metrics over this CTA's rows of R with the new factors; VB: extra term and factor-side ELBO terms ----
     double* own = sm.stats;                     // the row statistics are no longer needed
     for (int i = tid; i < nr[0] * K; i += SM_THREADS) own[i] = __ldcg(a.fac[0] + (size_t)r0[0] * K + i);
@@ -286,8 +322,10 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_small_sweeps(SmallArgs a) {
       const double t = block_sum(vals[q], sm.red);
       if (tid == 0) a.partial[(size_t)rank * SM_PARTIAL + q] = t;
     }
+    stamp(sweep, 5);
     __threadfence();
     cluster.sync();
+    stamp(sweep, 6);
     // ---- one thread: add the partial sums in rank order, end of sweep (tau, trace, sweep counter) ----
     if (rank == 0 && tid == 0) {
       double m8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ex1s = 0.0, el8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -311,13 +349,15 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_small_sweeps(SmallArgs a) {
       }
       __threadfence();
     }
+    stamp(sweep, 7);
     cluster.sync();
+    stamp(sweep, 8);
     (void)ex0;
   }
 }
 
 static size_t small_smem_bytes(int I, int J, int K, int vb, int C) {
-  size_t off[7];
+  size_t off[8];
   return small_layout(I, J, K, vb, (I + C - 1) / C, (J + C - 1) / C, off);
 }
 
@@ -328,7 +368,7 @@ int small_cluster_size(int I, int J, int K, int vb) {
     const int nr0 = (I + C - 1) / C, nr1 = (J + C - 1) / C;
     if (nr0 > SM_THREADS || nr1 > SM_THREADS) continue;
     if (C < 16 && (nr0 > 48 || nr1 > 48) ) continue;                 // prefer short per-CTA row lists (the chains are a thread per row)
-    if (small_smem_bytes(I, J, K, vb, C) <= 220 * 1024) return C;
+    if (small_smem_bytes(I, J, K, vb, C) <= 226 * 1024) return C;
   }
   return 0;
 }

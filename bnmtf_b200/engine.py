@@ -865,7 +865,7 @@ class BNMFEngine:
             ok = self.comm.world == 1 and os.environ.get("BNMTF_SMALL", "1") != "0"
             self._small_c = int(_lib.call("bnmtf_small_cluster_size", self.ds.I, self.ds.J, self.K, int(self.vb))) if ok else 0
             if self._small_c:
-                self._small_partial = torch.zeros(16 * 16, dtype=torch.float64, device=self.ds.device)
+                self._small_partial = torch.zeros(16 * 16 + 32, dtype=torch.float64, device=self.ds.device)   # + stage stamps
         return self._small_c
 
     def sweep_many(self, sweeps, minimum_TN=0.0, all_U=None, all_V=None, times=None, sums=None):
