@@ -388,9 +388,19 @@ class _TwoFactorBase(object):
         small enough for the single-kernel sweep (csrc/small.cu: the whole run is then one launch, and all_times comes
         from the device's own clock)."""
         eng.alloc_trace(iterations)
+        launched = False
         if iterations > 0 and eng.small_cluster() and (per_iteration is None or samples is not None or sums is not None):
             times = torch.zeros(iterations + 1, dtype=torch.int64, device=eng.ds.device)
-            eng.sweep_many(iterations, minimum_TN, samples[0] if samples else None, samples[1] if samples else None, times, sums)
+            try:
+                eng.sweep_many(iterations, minimum_TN, samples[0] if samples else None, samples[1] if samples else None, times, sums)
+                launched = True
+            except _lib.BnmtfError as exc:
+                # e.g. no 16 free SMs in one GPC for the cluster while other work runs: nothing has been modified, the
+                # multi-kernel path below does the same run
+                import warnings
+                warnings.warn("bnmtf_b200: single-kernel sweep not launched (%s); using the per-phase kernels" % exc)
+                eng._small_c = 0
+        if launched:
             torch.cuda.synchronize()
             t = times.cpu().numpy()
             self.all_times = [float(x - t[0]) / 1e9 for x in t[1:]]

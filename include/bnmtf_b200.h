@@ -132,7 +132,8 @@ int bnmtf_stats_gram_umma_f64(const uint32_t* bits, int64_t rows, int64_t ld, in
  * with the same formulas and Philox streams.  mode: 0 Gibbs, 1 VB, 2 ICM.  R / RT: dense rows x ld doubles, bits / bitsT
  * their mask words (bnmtf_pack_dataset_f64 / bnmtf_transpose_dataset_f64).  all_U / all_V (Gibbs, or NULL) receive the draw
  * of every sweep ([sweep][n][K]), sum_U / sum_V (or NULL) the running sums of the draws of sweeps burn_in, burn_in + thinning,
- * ... (bnmf_gibbs_optimised.py:182-187); partial: 16 x 16 doubles of scratch; times (or NULL): sweeps + 1 %globaltimer values.
+ * ... (bnmf_gibbs_optimised.py:182-187); partial: 288 doubles of scratch (16 x 16 partial sums + the stage
+ * timestamps of the last sweep, read by tools/small_sweep_times.py); times (or NULL): sweeps + 1 %globaltimer values.
  * bnmtf_small_cluster_size returns the cluster size used for (I, J, K), 0 when the problem does not qualify. */
 int bnmtf_small_cluster_size(int64_t I, int64_t J, int K, int vb);
 int bnmtf_small_sweeps_f64(int mode, const double* R, const uint32_t* bits, const double* RT, const uint32_t* bitsT, int64_t I,
