@@ -404,8 +404,8 @@ class _TwoFactorBase(object):
             torch.cuda.synchronize()
             t = times.cpu().numpy()
             self.all_times = [float(x - t[0]) / 1e9 for x in t[1:]]
-            XFER[1] += eng.trace.numel() * 8
-            tr = eng.trace.cpu().numpy()[:iterations]
+            XFER[1] += iterations * 64
+            tr = eng.trace[:iterations].cpu().numpy()
             for i, metric in enumerate(METRICS):
                 self.all_performances[metric] = [float(v) for v in tr[:, 1 + i]]
             return tr
@@ -421,8 +421,8 @@ class _TwoFactorBase(object):
             marks.append(ev)
         torch.cuda.synchronize()
         self.all_times = [start.elapsed_time(ev) / 1e3 for ev in marks]
-        XFER[1] += eng.trace.numel() * 8
-        tr = eng.trace.cpu().numpy()[:iterations]
+        XFER[1] += iterations * 64
+        tr = eng.trace[:iterations].cpu().numpy()
         for i, metric in enumerate(METRICS):
             self.all_performances[metric] = [float(v) for v in tr[:, 1 + i]]
         return tr

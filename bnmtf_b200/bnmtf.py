@@ -224,7 +224,7 @@ class BNMTFEngine:
         _lib.call("bnmf_finish_sweep_f64", self.m, self.alpha, self.beta, self.digamma_alpha_s, self.lgamma_alpha,
                   self.lgamma_alpha_s, nfe, _ptr(self.m8), _ptr(self.ex1), _ptr(self.el8), _ptr(self.scalars), trace_ptr,
                   _ptr(self.iter if record else self.iter_scratch), self.trace_base + self.trace_cap if record else 0,
-                  self.seed, 1 if update_tau else 0, _stream())
+                  self.seed, 1 if update_tau else 0, 0, _stream())
         if record:
             self.sweeps_done += 1
 

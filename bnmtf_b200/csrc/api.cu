@@ -391,12 +391,12 @@ int bnmtf_reduce1_f64(const double* x, int64_t n, double* out, void* stream) {
 int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_alpha_s, double lgamma_alpha,
                           double lgamma_alpha_s, int64_t n_factor_elems, const double* m8, const double* ex1,
                           const double* el8, double* scalars, double* trace, uint64_t* iter, int trace_cap,
-                          uint64_t seed, int update_tau, void* stream) {
+                          uint64_t seed, int update_tau, const uint64_t* trace_window, void* stream) {
   FinishArgs a;
   a.mode = mode; a.alpha = alpha; a.beta = beta; a.digamma_alpha_s = digamma_alpha_s; a.lgamma_alpha = lgamma_alpha;
   a.lgamma_alpha_s = lgamma_alpha_s; a.n_factor_elems = (int)n_factor_elems; a.m8 = m8; a.ex1 = ex1; a.el8 = el8;
   a.scalars = scalars; a.trace = trace; a.iter = reinterpret_cast<unsigned long long*>(iter); a.trace_cap = trace_cap;
-  a.seed = seed; a.update_tau = update_tau;
+  a.seed = seed; a.update_tau = update_tau; a.trace_window = reinterpret_cast<const unsigned long long*>(trace_window);
   if (mode == BNMTF_MODE_VB && (!ex1 || !el8)) { set_error("finish_sweep: VB needs ex1 and el8"); return -2; }
   return launch_finish(a, ST(stream));
 }

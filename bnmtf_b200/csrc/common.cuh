@@ -81,6 +81,9 @@ struct FinishArgs {
   const double* m8; const double* ex1; const double* el8;
   double* scalars; double* trace; unsigned long long* iter; int trace_cap;
   unsigned long long seed; int update_tau;
+  // optional (device): {first sweep number of the trace, one past the last}.  Given: row = *iter - window[0]; else the row
+  // is *iter itself and trace_cap its limit.  Lets a captured sweep be replayed for later runs with the same buffer.
+  const unsigned long long* trace_window;
 };
 
 // ---- tri-factorisation argument blocks (nmtf.cu) ----------------------------------------------------------

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_small_sweeps(SmallArgs a) {
       f.mode = MODE; f.alpha = a.alpha; f.beta = a.beta; f.digamma_alpha_s = a.digamma_alpha_s;
       f.lgamma_alpha = a.lgamma_alpha; f.lgamma_alpha_s = a.lgamma_alpha_s; f.n_factor_elems = (a.I + a.J) * K;
       f.m8 = m8; f.ex1 = &ex1s; f.el8 = el8; f.scalars = a.scalars; f.trace = a.trace; f.iter = a.iter;
-      f.trace_cap = a.trace_cap; f.seed = a.seed; f.update_tau = 1;
+      f.trace_cap = a.trace_cap; f.seed = a.seed; f.update_tau = 1; f.trace_window = nullptr;
       finish_sweep(f);
       if (a.times) {
         unsigned long long t;

@@ -62,8 +62,10 @@ __device__ inline void finish_sweep(const FinishArgs& a) {
       S[S_TAU] = (alpha_s - 1.0) / beta_s;
     }
   }
-  if (a.trace && it < (unsigned long long)a.trace_cap) {
-    double* tr = a.trace + it * kTraceWidth;
+  unsigned long long row = it, lim = (unsigned long long)a.trace_cap;
+  if (a.trace_window) { lim = a.trace_window[1]; row = it - a.trace_window[0]; if (it < a.trace_window[0]) lim = 0; }
+  if (a.trace && it < lim) {
+    double* tr = a.trace + row * kTraceWidth;
     tr[0] = S[S_TAU]; tr[1] = S[S_MSE]; tr[2] = S[S_R2]; tr[3] = S[S_RP]; tr[4] = elbo; tr[5] = se2; tr[6] = S[S_ESD];
     tr[7] = S[S_LOGTAU];
   }

@@ -714,12 +714,13 @@ class BNMFEngine:
             self.ex1.zero_()
 
     def finish(self, update_tau=True, record=True):
-        # the kernel writes trace row number *iter; rebase the pointer so that row trace_base is row 0
-        trace_ptr = _ptr(self.trace) - self.trace_base * 64 if (record and self.trace is not None) else 0
+        # the kernel writes trace row number *iter - trace_win[0] (device-side window: the same launch arguments serve
+        # every run that reuses the buffer, so a captured sweep stays valid from one run() to the next)
+        trace_ptr = _ptr(self.trace) if (record and self.trace is not None) else 0
         _lib.call("bnmf_finish_sweep_f64", self.m, self.alpha, self.beta, self.digamma_alpha_s, self.lgamma_alpha,
                   self.lgamma_alpha_s, (self.ds.I + self.ds.J) * self.K, _ptr(self.m8), _ptr(self.ex1), _ptr(self.el8),
                   _ptr(self.scalars), trace_ptr, _ptr(self.iter if record else self.iter_scratch),
-                  self.trace_base + self.trace_cap if record else 0, self.seed, 1 if update_tau else 0, _stream())
+                  0, self.seed, 1 if update_tau else 0, _ptr(self.trace_win) if record else 0, _stream())
         if record:
             self.sweeps_done += 1
 
@@ -744,13 +745,13 @@ class BNMFEngine:
         while the trace buffer stays the same, the sweep counter lives on the device), so from the second sweep of a
         run on it is replayed as one CUDA graph: the small kernels between the big ones no longer wait for the host."""
         if self.use_graph and not getattr(thread_flags, "no_graph", False):
-            key = (self.trace.data_ptr() if self.trace is not None else 0, self.trace_base, self.trace_cap, float(minimum_TN))
+            key = (self.trace.data_ptr() if self.trace is not None else 0, float(minimum_TN))
             if self._graph is not None and self._graph_key == key:
                 self._graph.replay()
                 _lib.launch_count[0] += self._graph_kernels       # a replay launches every kernel node of the capture
                 self.sweeps_done += 1
                 return
-            if self._graph_seen == key and self.trace_cap >= 8:       # (a short run does not repay the capture)
+            if self._graph_seen == key:                # second sweep with these arguments (in this run() or an earlier one)
                 done, count0 = self.sweeps_done, _lib.launch_count[0]
                 g = capture_graph(lambda: self._sweep_eager(minimum_TN))          # captured, not executed
                 self._graph_kernels = _lib.launch_count[0] - count0
@@ -884,6 +885,13 @@ class BNMFEngine:
         self.sweeps_done += int(sweeps)
 
     def alloc_trace(self, iterations):
+        """Trace rows for the next `iterations` sweeps.  The buffer is kept from run to run while it is large enough (only
+        the device-side window moves), so the CUDA graph of a sweep survives across run() calls -- run(1) in a loop, the way
+        the reference's convergence experiments and bench.py's end-to-end figure drive a model, replays it too."""
         self.trace_cap = int(iterations)
-        self.trace = torch.zeros((max(1, self.trace_cap), 8), dtype=torch.float64, device=self.ds.device)
+        if self.trace is None or self.trace.shape[0] < max(1, self.trace_cap):
+            self.trace = torch.zeros((max(64, self.trace_cap), 8), dtype=torch.float64, device=self.ds.device)
         self.trace_base = self.sweeps_done
+        if getattr(self, "trace_win", None) is None:
+            self.trace_win = torch.zeros(2, dtype=torch.int64, device=self.ds.device)
+        self.trace_win.copy_(torch.tensor([self.trace_base, self.trace_base + self.trace_cap], dtype=torch.int64))

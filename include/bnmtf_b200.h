@@ -230,11 +230,13 @@ int bnmtf_vb_factor_terms_f64(const double* ex, const double* var, const double*
                               const double* lambda, int64_t n, double* partials, int nblocks, void* stream);
 int bnmtf_reduce8_f64(const double* partials, int n, double* out8, void* stream);
 int bnmtf_reduce1_f64(const double* x, int64_t n, double* out, void* stream);
-/* End of a sweep: metrics -> scalars, tau update (Gibbs draw / VB expectation / ICM mode), trace row, ++*iter. */
+/* End of a sweep: metrics -> scalars, tau update (Gibbs draw / VB expectation / ICM mode), trace row, ++*iter.
+ * The trace row is number *iter (limit trace_cap) -- or, with trace_window (device, {first sweep, one past the last}),
+ * number *iter - trace_window[0]: a captured sweep can then be replayed for later runs that reuse the trace buffer. */
 int bnmf_finish_sweep_f64(int mode, double alpha, double beta, double digamma_alpha_s, double lgamma_alpha,
                           double lgamma_alpha_s, int64_t n_factor_elems, const double* m8, const double* ex1,
                           const double* el8, double* scalars, double* trace, uint64_t* iter, int trace_cap,
-                          uint64_t seed, int update_tau, void* stream);
+                          uint64_t seed, int update_tau, const uint64_t* trace_window /*or NULL*/, void* stream);
 
 /* ---- layer 2: tri-factorisation R ~ F S G^T (bnmtf_gibbs_optimised.py, bnmtf_vb_optimised.py, nmtf_icm.py) ---- */
 /* Row statistics w.r.t. the OTHER outer factor (dimension Lo, one segment: RXo rows x KPo, Go rows x gram_len(Lo),
