@@ -38,6 +38,9 @@ SIGNATURES = {
     "bnmtf_small_cluster_size": [c_i64, c_i64, c_i, c_i],
     "bnmtf_small_sweeps_f64": [c_i, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                c_p, c_p, c_p, c_p, c_p, c_i64, c_d, c_d, c_d, c_d, c_d, c_d, c_u64, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "bnmtf_small_tri_cluster_size": [c_i64, c_i64, c_i, c_i, c_i],
+    "bnmtf_small_tri_sweeps_f64": [c_i, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64,
+                                   c_d, c_d, c_d, c_d, c_d, c_d, c_u64, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "bnmtf_kmeans_distances_f64": [c_p, c_p, c_i64, c_i64, c_p, c_p, c_i, c_p, c_p],
     "bnmtf_stats_gram_fixup_f64": [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
     "bnmtf_gram_umma_workspace_bytes": [c_i, c_i, c_i64],
@@ -71,7 +74,7 @@ SIGNATURES = {
 _RESTYPES = {"bnmtf_last_error": ctypes.c_char_p, "bnmtf_ld_for": c_i64, "bnmtf_gram_len": c_i64,
              "bnmtf_gram_umma_workspace_bytes": c_i64, "bnmtf_rx_planes_bytes": c_i64,
              "bnmtf_rx_umma_workspace_bytes": c_i64, "bnmtf_peer_sync_bytes": c_i64}
-_PLAIN = {"bnmtf_small_cluster_size", "bnmtf_fixed_point_digits", "bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "bnmtf_gram_len",
+_PLAIN = {"bnmtf_small_cluster_size", "bnmtf_small_tri_cluster_size", "bnmtf_fixed_point_digits", "bnmtf_version", "bnmtf_last_error", "bnmtf_ld_for", "bnmtf_kp_for", "bnmtf_gram_len",
           "bnmtf_gram_umma_workspace_bytes", "bnmtf_rx_planes_bytes", "bnmtf_rx_umma_workspace_bytes", "bnmtf_peer_sync_bytes"}
 
 _lib = None
@@ -79,7 +82,7 @@ _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches count)
 KERNELS_PER_CALL = {"bnmtf_pack_dataset_f64": 1, "bnmtf_pack_mask_f64": 1, "bnmtf_transpose_dataset_f64": 1,
                     "bnmtf_pad_factor_f64": 1, "bnmtf_stats_rx_f64": 1, "bnmtf_stats_rx_umma_f64": 5,
-                    "bnmtf_rx_planes_pack_f64": 2, "bnmtf_range_guard_f64": 1, "bnmtf_stats_gated_f64": 2, "bnmtf_stats_gram_f64": 1, "bnmtf_stats_gram_fixup_f64": 1, "bnmtf_kmeans_distances_f64": 1, "bnmtf_small_sweeps_f64": 1, "bnmtf_stats_gram_umma_f64": 4, "bnmtf_mstat_reduce_f64": 2,
+                    "bnmtf_rx_planes_pack_f64": 2, "bnmtf_range_guard_f64": 1, "bnmtf_stats_gated_f64": 2, "bnmtf_stats_gram_f64": 1, "bnmtf_stats_gram_fixup_f64": 1, "bnmtf_kmeans_distances_f64": 1, "bnmtf_small_sweeps_f64": 1, "bnmtf_small_tri_sweeps_f64": 1, "bnmtf_stats_gram_umma_f64": 4, "bnmtf_mstat_reduce_f64": 2,
                     "bnmtf_metrics_from_sums_f64": 1, "bnmtf_select_metrics_f64": 1,
                     "bnmtf_gram_full_f64": 2, "bnmf_row_solve_f64": 1, "bnmtf_masked_metrics_f64": 3,
                     "bnmtf_dense_metrics_f64": 2, "bnmtf_vb_factor_terms_f64": 1, "bnmtf_reduce8_f64": 1,

@@ -392,7 +392,7 @@ class _TwoFactorBase(object):
         if iterations > 0 and eng.small_cluster() and (per_iteration is None or samples is not None or sums is not None):
             times = torch.zeros(iterations + 1, dtype=torch.int64, device=eng.ds.device)
             try:
-                eng.sweep_many(iterations, minimum_TN, samples[0] if samples else None, samples[1] if samples else None, times, sums)
+                eng.sweep_many(iterations, minimum_TN, samples, times, sums)
                 launched = True
             except _lib.BnmtfError as exc:
                 # e.g. no 16 free SMs in one GPC for the cluster while other work runs: nothing has been modified, the

@@ -98,8 +98,40 @@ class BNMTFEngine:
         self.lgamma_alpha_s = float(gammaln(self.alpha_s))
         self.sterm = None
 
+    # ---- small problems: the whole run as ONE kernel (csrc/small.cu::k_small_tri) -------------------------------
     def small_cluster(self):
-        return 0                     # (the single-kernel sweep of csrc/small.cu covers the two-factor models only)
+        if getattr(self, "_small_c", None) is None:
+            ok = os.environ.get("BNMTF_SMALL", "1") != "0"
+            self._small_c = int(_lib.call("bnmtf_small_tri_cluster_size", self.ds.I, self.ds.J, self.K, self.L, int(self.vb))) if ok else 0
+            if self._small_c:
+                import ctypes
+                D, dev = self.K * self.L, self.ds.device
+                self._small_partial = torch.zeros(16 * 16 + 32, dtype=torch.float64, device=dev)
+                self._small_H = torch.zeros(17 * (D * D + 2 * D), dtype=torch.float64, device=dev)
+                tab = lambda *ts: (ctypes.c_void_p * 5)(*[_ptr(t) or None for t in ts])
+                S = self.S
+                self._small_tabs = (tab(self.F.fac, self.F.var, self.F.mu, self.F.tauf, self.F.lam),
+                                    tab(self.G.fac, self.G.var, self.G.mu, self.G.tauf, self.G.lam),
+                                    tab(S["fac"], S["var"] if self.vb else None, S["mu"], S["tauf"], S["lam"]))
+        return self._small_c
+
+    def sweep_many(self, sweeps, minimum_TN=0.0, samples=None, times=None, sums=None, orders=None):
+        """`sweeps` iterations of run() in one launch.  samples = (all_F, all_S, all_G): device tensors for the Gibbs draw of
+        every sweep; orders: int32 device tensor [sweeps, K*L + K + L] (VB: the three shuffled orders of every sweep)."""
+        assert sums is None
+        import ctypes
+        ds, D = self.ds, self.K * self.L
+        trace_ptr = _ptr(self.trace) - self.trace_base * 64 if self.trace is not None else 0
+        aF, aS, aG = samples if samples is not None else (None, None, None)
+        HL = D * D + 2 * D
+        tF, tG, tS = self._small_tabs
+        _lib.call("bnmtf_small_tri_sweeps_f64", self.m, _ptr(ds.R), _ptr(ds.bits), _ptr(ds.RT), _ptr(ds.bitsT), ds.I, ds.J, ds.ldJ,
+                  ds.ldI, self.K, self.L, ctypes.cast(tF, ctypes.c_void_p), ctypes.cast(tG, ctypes.c_void_p),
+                  ctypes.cast(tS, ctypes.c_void_p), _ptr(self.scalars), trace_ptr, _ptr(self.iter), self.trace_base + self.trace_cap,
+                  self.alpha, self.beta, self.digamma_alpha_s, self.lgamma_alpha, self.lgamma_alpha_s, float(minimum_TN), self.seed,
+                  int(sweeps), _ptr(orders), _ptr(aF), _ptr(aS), _ptr(aG), _ptr(self._small_partial), _ptr(self._small_H),
+                  self._small_H.data_ptr() + 8 * 16 * HL, _ptr(times), _stream())
+        self.sweeps_done += int(sweeps)
 
     # ---- layer 1 ------------------------------------------------------------------------------------------
     def _stats(self, st, R, bits, rows, ld, other, dim, need_rx=True):
@@ -495,7 +527,7 @@ class bnmtf_gibbs_optimised(_PointEstimateNMTF):
 
         def keep(it):
             all_F[it].copy_(eng.F.fac), all_S[it].copy_(eng.S["fac"]), all_G[it].copy_(eng.G.fac)
-        tr = self._run_loop(eng, iterations, per_iteration=keep)
+        tr = self._run_loop(eng, iterations, per_iteration=keep, samples=(all_F, all_S, all_G))
         self.all_F, self.all_S, self.all_G = self._down(all_F), self._down(all_S), self._down(all_G)
         self._pull_state(eng, tr, iterations)
         return (self.all_F, self.all_S, self.all_G, self.all_tau)
@@ -629,10 +661,8 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
         self._init_trace_lists()
         K, L = self.K, self.L
         eng.alloc_trace(iterations)
-        start = torch.cuda.Event(enable_timing=True)
-        marks = []
-        start.record()
-        for it in range(iterations):
+
+        def shuffles():
             # the reference's three python-`random` shuffles, in its call order (bnmtf_vb_optimised.py:171-190)
             indices_kl = list(itertools.product(range(0, K), range(0, L)))
             random.shuffle(indices_kl)
@@ -640,12 +670,38 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
             random.shuffle(indices_k)
             indices_l = list(range(0, L))
             random.shuffle(indices_l)
-            eng.sweep(order={"S": [k * L + l for k, l in indices_kl], "F": indices_k, "G": indices_l})
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append(ev)
-        torch.cuda.synchronize()
-        self.all_times = [start.elapsed_time(ev) / 1e3 for ev in marks]
+            return [k * L + l for k, l in indices_kl], indices_k, indices_l
+        launched = False
+        if iterations > 0 and eng.small_cluster():
+            # small matrix: the whole run is one kernel (csrc/small.cu); the shuffled orders of every sweep go up front
+            orders = np.array([sum(map(list, shuffles()), []) for _ in range(iterations)], dtype=np.int32)
+            od = torch.from_numpy(orders).to(eng.ds.device)
+            times = torch.zeros(iterations + 1, dtype=torch.int64, device=eng.ds.device)
+            try:
+                eng.sweep_many(iterations, 0.0, None, times, None, od)
+                launched = True
+            except _lib.BnmtfError as exc:
+                import warnings
+                warnings.warn("bnmtf_b200: single-kernel sweep not launched (%s); using the per-phase kernels" % exc)
+                eng._small_c = 0
+            if launched:
+                torch.cuda.synchronize()
+                t = times.cpu().numpy()
+                self.all_times = [float(x - t[0]) / 1e9 for x in t[1:]]
+            else:
+                todo = [(list(o[:K * L]), list(o[K * L:K * L + K]), list(o[K * L + K:])) for o in orders.tolist()]
+        if not launched:
+            start = torch.cuda.Event(enable_timing=True)
+            marks = []
+            start.record()
+            for it in range(iterations):
+                oS, oF, oG = todo[it] if (iterations > 0 and 'todo' in locals()) else shuffles()
+                eng.sweep(order={"S": oS, "F": oF, "G": oG})
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+            torch.cuda.synchronize()
+            self.all_times = [start.elapsed_time(ev) / 1e3 for ev in marks]
         tr = eng.trace.cpu().numpy()[:iterations]
         for i, metric in enumerate(METRICS):
             self.all_performances[metric] = [float(v) for v in tr[:, 1 + i]]

@@ -70,6 +70,22 @@ struct SmallArgs {
   double* partial;
   unsigned long long* times;
 };
+struct TriArgs {
+  int mode, I, J, K, L, ldJ, ldI, nrow[2];
+  const double* R; const uint32_t* bits; const double* RT; const uint32_t* bitsT;
+  double* fac[3]; double* var[3]; double* mu[3]; double* tauf[3]; const double* lam[3];
+  double* scalars; double* trace; unsigned long long* iter; int trace_cap;
+  double alpha, beta, digamma_alpha_s, lgamma_alpha, lgamma_alpha_s, min_tn;
+  unsigned long long seed;
+  int sweeps;
+  const int* orders;
+  double* all_F; double* all_S; double* all_G;
+  double* partial;
+  double* Hpart; double* Hsum;
+  unsigned long long* times;
+};
+int small_tri_cluster_size(int, int, int, int, int);
+int launch_small_tri(TriArgs, cudaStream_t);
 int small_cluster_size(int, int, int, int);
 int launch_small_sweeps(SmallArgs, cudaStream_t);
 int launch_kmeans_dist(const double*, const double*, int, int, const double*, const double*, int, double*, cudaStream_t);
@@ -289,6 +305,35 @@ int bnmtf_small_sweeps_f64(int mode, const double* R, const uint32_t* bits, cons
   a.all_U = all_U; a.all_V = all_V; a.sum_U = sum_U; a.sum_V = sum_V; a.burn_in = burn_in; a.thinning = thinning < 1 ? 1 : thinning;
   a.partial = partial; a.times = reinterpret_cast<unsigned long long*>(times);
   return launch_small_sweeps(a, ST(stream));
+}
+
+int bnmtf_small_tri_cluster_size(int64_t I, int64_t J, int K, int L, int vb) {
+  if (I > 1000000 || J > 1000000) return 0;
+  return small_tri_cluster_size((int)I, (int)J, K, L, vb);
+}
+
+int bnmtf_small_tri_sweeps_f64(int mode, const double* R, const uint32_t* bits, const double* RT, const uint32_t* bitsT, int64_t I,
+                               int64_t J, int64_t ldJ, int64_t ldI, int K, int L, double* const* F5, double* const* G5,
+                               double* const* S5, double* scalars, double* trace, uint64_t* iter, int64_t trace_cap, double alpha,
+                               double beta, double digamma_alpha_s, double lgamma_alpha, double lgamma_alpha_s, double minimum_TN,
+                               uint64_t seed, int sweeps, const int32_t* orders, double* all_F, double* all_S, double* all_G,
+                               double* partial, double* Hpart, double* Hsum, uint64_t* times, void* stream) {
+  if (mode < 0 || mode > 2) { set_error("small_tri_sweeps: bad mode %d", mode); return -2; }
+  if (!F5 || !G5 || !S5) { set_error("small_tri_sweeps: factor pointer tables missing"); return -2; }
+  TriArgs a;
+  a.mode = mode; a.I = (int)I; a.J = (int)J; a.K = K; a.L = L; a.ldJ = (int)ldJ; a.ldI = (int)ldI; a.nrow[0] = a.nrow[1] = 0;
+  a.R = R; a.bits = bits; a.RT = RT; a.bitsT = bitsT;
+  double* const* tabs[3] = {F5, G5, S5};               // each: {fac, var, mu, tauf, lambda} (HOST arrays of device pointers)
+  for (int f = 0; f < 3; ++f) {
+    a.fac[f] = tabs[f][0]; a.var[f] = tabs[f][1]; a.mu[f] = tabs[f][2]; a.tauf[f] = tabs[f][3]; a.lam[f] = tabs[f][4];
+    if (!a.fac[f] || !a.mu[f] || !a.tauf[f] || !a.lam[f] || (mode == 1 && !a.var[f])) { set_error("small_tri_sweeps: missing factor array"); return -2; }
+  }
+  a.scalars = scalars; a.trace = trace; a.iter = reinterpret_cast<unsigned long long*>(iter); a.trace_cap = (int)trace_cap;
+  a.alpha = alpha; a.beta = beta; a.digamma_alpha_s = digamma_alpha_s; a.lgamma_alpha = lgamma_alpha;
+  a.lgamma_alpha_s = lgamma_alpha_s; a.min_tn = minimum_TN; a.seed = seed; a.sweeps = sweeps; a.orders = orders;
+  a.all_F = all_F; a.all_S = all_S; a.all_G = all_G; a.partial = partial; a.Hpart = Hpart; a.Hsum = Hsum;
+  a.times = reinterpret_cast<unsigned long long*>(times);
+  return launch_small_tri(a, ST(stream));
 }
 
 int bnmtf_kmeans_distances_f64(const double* X, const double* M, int64_t n, int64_t d, const double* centroids,

@@ -869,11 +869,12 @@ class BNMFEngine:
                 self._small_partial = torch.zeros(16 * 16 + 32, dtype=torch.float64, device=self.ds.device)   # + stage stamps
         return self._small_c
 
-    def sweep_many(self, sweeps, minimum_TN=0.0, all_U=None, all_V=None, times=None, sums=None):
+    def sweep_many(self, sweeps, minimum_TN=0.0, samples=None, times=None, sums=None, orders=None):
         """`sweeps` iterations of run() in one launch (small_cluster() must be non-zero).  all_U / all_V: device tensors
         [sweeps, n, K] that receive the Gibbs draw of every sweep; sums = (sum_U, sum_V, burn_in, thinning): running sums of
         the kept draws instead; times: int64 device tensor of sweeps + 1 timestamps."""
         sU, sV, burn_in, thinning = sums if sums is not None else (None, None, 0, 1)
+        all_U, all_V = samples if samples is not None else (None, None)
         trace_ptr = _ptr(self.trace) - self.trace_base * 64 if self.trace is not None else 0
         ds, U, V = self.ds, self.U, self.V
         _lib.call("bnmtf_small_sweeps_f64", self.m, _ptr(ds.R), _ptr(ds.bits), _ptr(ds.RT), _ptr(ds.bitsT), ds.I, ds.J, ds.ldJ, ds.ldI,

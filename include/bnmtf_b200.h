@@ -143,6 +143,18 @@ int bnmtf_small_sweeps_f64(int mode, const double* R, const uint32_t* bits, cons
                            double digamma_alpha_s, double lgamma_alpha, double lgamma_alpha_s, double minimum_TN, uint64_t seed,
                            int sweeps, double* all_U, double* all_V, double* sum_U, double* sum_V, int burn_in, int thinning,
                            double* partial, uint64_t* times, void* stream);
+/* The same for the tri-factorisation R ~ F S G^T (bnmtf_gibbs_optimised.py:138-180, bnmtf_vb_optimised.py:160-204,
+ * nmtf_icm.py:132-173; K, L <= 16).  F5 / G5 / S5: HOST arrays of five device pointers {values (exp), var (VB, else NULL),
+ * mu, tau, lambda} of F (I x K), G (J x L), S (K x L).  orders (VB; device, or NULL for the natural order): per sweep the
+ * K*L flat indices k*L + l of the S updates, then the K column indices of F, then the L of G (the reference's three
+ * shuffles, bnmtf_vb_optimised.py:171-190).  Hpart: 16 x (D^2 + 2D) doubles, Hsum: D^2 + 2D, D = K*L; partial: 288. */
+int bnmtf_small_tri_cluster_size(int64_t I, int64_t J, int K, int L, int vb);
+int bnmtf_small_tri_sweeps_f64(int mode, const double* R, const uint32_t* bits, const double* RT, const uint32_t* bitsT, int64_t I,
+                               int64_t J, int64_t ldJ, int64_t ldI, int K, int L, double* const* F5, double* const* G5,
+                               double* const* S5, double* scalars, double* trace, uint64_t* iter, int64_t trace_cap, double alpha,
+                               double beta, double digamma_alpha_s, double lgamma_alpha, double lgamma_alpha_s, double minimum_TN,
+                               uint64_t seed, int sweeps, const int32_t* orders, double* all_F, double* all_S, double* all_G,
+                               double* partial, double* Hpart, double* Hsum, uint64_t* times, void* stream);
 /* K-means with missing values, assignment step (code/models/kmeans/kmeans.py:105-133, closest_cluster / compute_MSE):
  * dist[i*K + c] = sum_j M_ij MC_cj (X_ij - C_cj)^2 / sum_j M_ij MC_cj, +inf when point and centroid share no observed
  * coordinate.  X, M: n x d; centroids, mask_centroids: K x d; all dense row-major doubles.  The sums are taken in numpy's

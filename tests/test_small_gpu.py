@@ -77,3 +77,65 @@ def test_large_or_wide_problems_keep_the_multi_kernel_path():
     assert _lib.call("bnmtf_small_cluster_size", 622, 138, 17, 0) == 0          # K > 16
     assert _lib.call("bnmtf_small_cluster_size", 5000, 300, 10, 0) == 0         # more than 256 rows per CTA of the largest cluster
     assert _lib.call("bnmtf_small_cluster_size", 2000, 2000, 10, 1) == 0        # does not fit shared memory
+
+
+# ---- tri-factorisation ------------------------------------------------------------------------------------------
+PRI3 = {"alpha": 1.0, "beta": 1.0, "lambdaF": 0.1, "lambdaS": 0.1, "lambdaG": 0.1}
+
+
+def run3(cls_name, R, M, K, L, its, small, monkeypatch):
+    import random
+    import bnmtf_b200
+    monkeypatch.setenv("BNMTF_SMALL", "1" if small else "0")
+    np.random.seed(4), random.seed(4)
+    m = getattr(bnmtf_b200, cls_name)(R, M, K, L, PRI3, seed=9)
+    m.initialise("random", "random")
+    out = m.run(its) if cls_name != "nmtf_icm" else m.run(its, minimum_TN=0.1)
+    from bnmtf_b200 import _lib
+    fits = _lib.call("bnmtf_small_tri_cluster_size", R.shape[0], R.shape[1], K, L, int(cls_name == "bnmtf_vb_optimised")) > 0
+    assert bool(m._engine().small_cluster()) == (small and fits)
+    return m, out
+
+
+@pytest.mark.parametrize("I,J,K,L", [(100, 80, 5, 5), (130, 45, 7, 3), (257, 300, 4, 9), (622, 138, 7, 7), (40, 33, 2, 3)])
+@pytest.mark.parametrize("cls_name", ["bnmtf_vb_optimised", "nmtf_icm", "bnmtf_gibbs_optimised"])
+def test_tri_factor_single_kernel_sweeps_match_the_multi_kernel_path(monkeypatch, cls_name, I, J, K, L):
+    """csrc/small.cu::k_small_tri against bnmtf.py::BNMTFEngine's per-phase kernels: bnmtf_vb_optimised.run (shuffled S, F, G
+    orders, covariance terms, ELBO), nmtf_icm.run, bnmtf_gibbs_optimised.run (same Philox streams: the same chain)."""
+    R, M = problem(I, J, max(K, L), I + J + K + L)
+    R = np.abs(R) + 0.5
+    its = 8
+    a, out_a = run3(cls_name, R, M, K, L, its, True, monkeypatch)
+    b, out_b = run3(cls_name, R, M, K, L, its, False, monkeypatch)
+    # (VB-NMTF feeds the last bits of its truncated-normal moments back every sweep: tests/golden/vb_nmtf_sensitivity.json;
+    # R^2 near zero is 1 - SSE/SST: an absolute floor)
+    tol = dict(rtol=1e-6, atol=1e-8)
+    for metric in ("MSE", "R^2", "Rp"):
+        x, y = np.array(a.all_performances[metric]), np.array(b.all_performances[metric])
+        if metric == "Rp":
+            # (the first ICM sweep clamps every entry to minimum_TN: a constant prediction, Rp = 0/0 up to rounding)
+            ok = np.isfinite(x) & np.isfinite(y) & (np.abs(y) > 1e-6)
+            x, y = x[ok], y[ok]
+        np.testing.assert_allclose(x, y, **tol)
+    if cls_name == "bnmtf_vb_optimised":
+        for name in ("expF", "expS", "expG", "varF", "varS", "varG", "muS", "tauS"):
+            np.testing.assert_allclose(getattr(a, name), getattr(b, name), rtol=1e-6, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(a.all_exp_tau, b.all_exp_tau, **tol)
+        np.testing.assert_allclose(a.all_elbo, b.all_elbo, rtol=1e-8)
+    else:
+        for name in ("F", "S", "G"):
+            np.testing.assert_allclose(getattr(a, name), getattr(b, name), rtol=1e-6, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(a.all_tau, b.all_tau, **tol)
+    if cls_name == "bnmtf_gibbs_optimised":
+        for x, y in zip(out_a[:3], out_b[:3]):
+            assert np.asarray(x).shape == np.asarray(y).shape
+            np.testing.assert_allclose(np.asarray(x), np.asarray(y), rtol=1e-5, atol=1e-9)
+    assert len(a.all_times) == its and all(t1 > t0 for t0, t1 in zip(a.all_times, a.all_times[1:]))
+
+
+def test_tri_factor_eligibility():
+    from bnmtf_b200 import _lib
+    assert _lib.call("bnmtf_small_tri_cluster_size", 100, 80, 5, 5, 1) == 4
+    assert _lib.call("bnmtf_small_tri_cluster_size", 622, 138, 5, 5, 1) == 16
+    assert _lib.call("bnmtf_small_tri_cluster_size", 622, 138, 10, 10, 0) == 0      # K*L > 50: the per-phase kernels are faster
+    assert _lib.call("bnmtf_small_tri_cluster_size", 5000, 300, 5, 5, 0) == 0

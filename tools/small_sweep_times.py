@@ -33,3 +33,23 @@ for name, f, K in (("toy 100x80", "toy_bnmf_vb.npz", 10), ("GDSC 622x138", "gdsc
                 print("      SM clock during the last sweep: %.0f MHz" % ((full[10] - full[9]) / (st[8] - st[0]) * 1e3))
                 print("      stages of the last sweep (us): U phase %.1f | barrier %.1f | V phase %.1f | barrier %.1f | metrics %.1f | "
                       "barrier %.1f | end of sweep %.1f | barrier %.1f" % tuple((st[1:] - st[:-1]) / 1e3), flush=True)
+
+import random
+pri3 = {"alpha": 1.0, "beta": 1.0, "lambdaF": 0.1, "lambdaS": 0.1, "lambdaG": 0.1}
+for name, f, K, L in (("toy 100x80", "toy_bnmtf_vb.npz", 5, 5), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 5, 5), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 10, 10)):
+    d = np.load(os.path.join(G, f))
+    R, M = d["R"], d["M"]
+    for cls in (bnmtf_b200.bnmtf_gibbs_optimised, bnmtf_b200.bnmtf_vb_optimised, bnmtf_b200.nmtf_icm):
+        for small in ("1", "0"):
+            os.environ["BNMTF_SMALL"] = small
+            np.random.seed(0), random.seed(0)
+            m = cls(R, M, K, L, pri3, seed=1)
+            m.initialise("random", "random")
+            m.run(20)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            m.run(300)
+            torch.cuda.synchronize()
+            wall = time.time() - t0
+            print("%-13s %-22s K=%d L=%d small=%s  device %.1f us/sweep   wall %.1f us/sweep   MSE %.6f" % (
+                name, cls.__name__, K, L, small, m.all_times[-1] / 300 * 1e6, wall / 300 * 1e6, m.all_performances["MSE"][-1]), flush=True)
