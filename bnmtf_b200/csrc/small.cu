@@ -476,18 +476,23 @@ __device__ void tri_transform_row(const double* __restrict__ st, int Lo, int Ks,
     out[NTs + k] = c;
     out[NTs + Ks + k] = e;
   }
-  for (int k = 0; k < Ks; ++k)
+  for (int k = 0; k < Ks; ++k) {
+    double T[SM_KMAX];                                    // T[l] = sum_q S[k][q] GG[q][l], once per k
+    for (int l = 0; l < Lo; ++l) {
+      double t = 0.0;
+      for (int q = 0; q < Lo; ++q) t = fma(S(k, q), GG(q, l), t);
+      T[l] = t;
+    }
     for (int k2 = k; k2 < Ks; ++k2) {
       double v = 0.0;
       for (int l = 0; l < Lo; ++l) {
-        double t = 0.0;                                   // T[k][l] = sum_q S[k][q] GG[q][l]
-        for (int q = 0; q < Lo; ++q) t = fma(S(k, q), GG(q, l), t);
         const double s2 = S(k2, l);
-        v = fma(t, s2, v);
+        v = fma(T[l], s2, v);
         if (VB && k != k2) v = fma(S(k, l) * s2, sv[l], v);
       }
       out[tri_index(k, k2, Ks)] = v;
     }
+  }
 }
 
 // the sequential updates of one row on its effective statistics (dimension Ks), in `order` (or natural order)
@@ -829,9 +834,10 @@ static size_t tri_smem_bytes(int I, int J, int K, int L, int vb, int C) {
 }
 
 int small_tri_cluster_size(int I, int J, int K, int L, int vb) {
-  // K*L <= 50: the K*L scalar S updates are a serial chain and every row's S-transform is one thread's work -- measured on the
-  // GDSC matrix at K = L = 10 the per-phase kernels are faster (426 vs 761 us per Gibbs sweep), at K = L = 5 slower (182 vs 142)
-  if (K < 1 || L < 1 || K > SM_KMAX || L > SM_KMAX || K * L > 50 || I < 1 || J < 1) return 0;
+  // K*L <= 64: the K*L scalar S updates are a serial chain and every row's S-transform is one thread's work -- measured on the
+  // GDSC matrix (us per Gibbs / VB / ICM sweep, single kernel vs per-phase kernels): K = L = 5: 114 / 137 / 80 vs 182 / 248 /
+  // 181; K = L = 7: 203 / 241 / 146 vs 240 / 318 / 192; K = L = 10: 425 / - / 689 vs 426 / 526 / 601
+  if (K < 1 || L < 1 || K > SM_KMAX || L > SM_KMAX || K * L > 64 || I < 1 || J < 1) return 0;
   for (int C = 1; C <= 16; C *= 2) {
     const int nr0 = (I + C - 1) / C, nr1 = (J + C - 1) / C;
     if (nr0 > SM_THREADS || nr1 > SM_THREADS) continue;

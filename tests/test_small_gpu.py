@@ -137,5 +137,5 @@ def test_tri_factor_eligibility():
     from bnmtf_b200 import _lib
     assert _lib.call("bnmtf_small_tri_cluster_size", 100, 80, 5, 5, 1) == 4
     assert _lib.call("bnmtf_small_tri_cluster_size", 622, 138, 5, 5, 1) == 16
-    assert _lib.call("bnmtf_small_tri_cluster_size", 622, 138, 10, 10, 0) == 0      # K*L > 50: the per-phase kernels are faster
+    assert _lib.call("bnmtf_small_tri_cluster_size", 622, 138, 10, 10, 0) == 0      # K*L > 64: the per-phase kernels are as fast
     assert _lib.call("bnmtf_small_tri_cluster_size", 5000, 300, 5, 5, 0) == 0

@@ -36,7 +36,8 @@ for name, f, K in (("toy 100x80", "toy_bnmf_vb.npz", 10), ("GDSC 622x138", "gdsc
 
 import random
 pri3 = {"alpha": 1.0, "beta": 1.0, "lambdaF": 0.1, "lambdaS": 0.1, "lambdaG": 0.1}
-for name, f, K, L in (("toy 100x80", "toy_bnmtf_vb.npz", 5, 5), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 5, 5), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 10, 10)):
+for name, f, K, L in (("toy 100x80", "toy_bnmtf_vb.npz", 5, 5), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 5, 5), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 7, 7),
+                      ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 8, 6), ("GDSC 622x138", "gdsc_bnmtf_vb.npz", 10, 10)):
     d = np.load(os.path.join(G, f))
     R, M = d["R"], d["M"]
     for cls in (bnmtf_b200.bnmtf_gibbs_optimised, bnmtf_b200.bnmtf_vb_optimised, bnmtf_b200.nmtf_icm):
