@@ -671,11 +671,12 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
             indices_l = list(range(0, L))
             random.shuffle(indices_l)
             return [k * L + l for k, l in indices_kl], indices_k, indices_l
+        # the orders of every sweep are drawn up front, in the reference's call order (three shuffles per iteration)
+        todo = [shuffles() for _ in range(iterations)]
         launched = False
         if iterations > 0 and eng.small_cluster():
-            # small matrix: the whole run is one kernel (csrc/small.cu); the shuffled orders of every sweep go up front
-            orders = np.array([sum(map(list, shuffles()), []) for _ in range(iterations)], dtype=np.int32)
-            od = torch.from_numpy(orders).to(eng.ds.device)
+            # small matrix: the whole run is one kernel (csrc/small.cu::k_small_tri)
+            od = torch.from_numpy(np.array([oS + oF + oG for oS, oF, oG in todo], dtype=np.int32)).to(eng.ds.device)
             times = torch.zeros(iterations + 1, dtype=torch.int64, device=eng.ds.device)
             try:
                 eng.sweep_many(iterations, 0.0, None, times, None, od)
@@ -688,14 +689,11 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
                 torch.cuda.synchronize()
                 t = times.cpu().numpy()
                 self.all_times = [float(x - t[0]) / 1e9 for x in t[1:]]
-            else:
-                todo = [(list(o[:K * L]), list(o[K * L:K * L + K]), list(o[K * L + K:])) for o in orders.tolist()]
         if not launched:
             start = torch.cuda.Event(enable_timing=True)
             marks = []
             start.record()
-            for it in range(iterations):
-                oS, oF, oG = todo[it] if (iterations > 0 and 'todo' in locals()) else shuffles()
+            for oS, oF, oG in todo:
                 eng.sweep(order={"S": oS, "F": oF, "G": oG})
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
