@@ -710,12 +710,11 @@ class bnmf_vb_optimised(_TwoFactorBase):
         if init == 'random':
             self.muU = np.random.exponential(scale=1.0 / self.lambdaU)
             self.muV = np.random.exponential(scale=1.0 / self.lambdaV)
-        self.expU, self.varU = np.zeros((self.I, self.K)), np.zeros((self.I, self.K))
-        self.expV, self.varV = np.zeros((self.J, self.K)), np.zeros((self.J, self.K))
-        for k in range(0, self.K):
-            self.update_exp_U(k)
-        for k in range(0, self.K):
-            self.update_exp_V(k)
+        # (the reference's column-by-column update_exp_U / update_exp_V loops, :112-115, as one device call per factor: the
+        # moments are element-wise)
+        from .distributions import TN_matrix_moments
+        self.expU, self.varU = TN_matrix_moments(self.muU, self.tauU)
+        self.expV, self.varV = TN_matrix_moments(self.muV, self.tauV)
         self.update_tau()
         self.update_exp_tau()
 

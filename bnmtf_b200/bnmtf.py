@@ -618,15 +618,12 @@ class bnmtf_vb_optimised(_ThreeFactorBase):
             self.muG = np.random.exponential(scale=1.0 / self.lambdaG)
         elif init_FG == 'kmeans':
             self.muF, self.muG = self._kmeans_init(0.0)
-        self.expF, self.varF = np.zeros((self.I, self.K)), np.zeros((self.I, self.K))
-        self.expS, self.varS = np.zeros((self.K, self.L)), np.zeros((self.K, self.L))
-        self.expG, self.varG = np.zeros((self.J, self.L)), np.zeros((self.J, self.L))
-        for k in range(0, self.K):
-            self.update_exp_F(k)
-        for k, l in itertools.product(range(0, self.K), range(0, self.L)):
-            self.update_exp_S(k, l)
-        for l in range(0, self.L):
-            self.update_exp_G(l)
+        # (the reference's update_exp_F / update_exp_S / update_exp_G loops, :141-146, as one device call per factor: the
+        # moments are element-wise)
+        from .distributions import TN_matrix_moments
+        self.expF, self.varF = TN_matrix_moments(self.muF, self.tauF)
+        self.expS, self.varS = TN_matrix_moments(self.muS, self.tauS)
+        self.expG, self.varG = TN_matrix_moments(self.muG, self.tauG)
         self.update_tau()
         self.update_exp_tau()
 

@@ -76,6 +76,14 @@ def _moments(mus, taus):
     return ex.cpu().numpy(), var.cpu().numpy()
 
 
+def TN_matrix_moments(mus, taus):
+    """Expectation and variance of every entry of a matrix of truncated normals in one device call (what the K column-wise
+    update_exp_* calls of the reference's initialise() compute: truncated_normal_vector.py:53-73, entry by entry)."""
+    shape = np.shape(mus)
+    ex, var = _moments(np.ravel(np.asarray(mus, dtype=np.float64)), np.ravel(np.asarray(taus, dtype=np.float64)))
+    return ex.reshape(shape), var.reshape(shape)
+
+
 def TN_vector_expectation(mus, taus):
     return list(_moments(mus, taus)[0])
 
