@@ -254,7 +254,9 @@ def run_nmtf(args, rank, world, device, dist, barrier, max_over_ranks, sum_over_
     N = float(I) * J
     hbm, kind = bench.measured_peaks()
     sweep_s = total_ms / 1e3 / (2.0 * args.steps)
-    b_alg = 2.0 * N * 8.125 + N * 8.125          # F and G phases stream R once each (as BNMF) + the prediction metrics pass
+    stat = engs["vb"].metrics_mode == "stats"
+    # F and G phases stream R once each (as BNMF); the metrics come from the G-phase statistics or from a third pass
+    b_alg = 2.0 * N * 8.125 + (0.0 if stat else N * 8.125)
     line.update({"metric": "BNMTF Gibbs+VB sweeps/sec at %dx%d K=L=%d" % (I, J, K), "value": world * 2.0 * args.steps / (total_ms / 1e3),
                  "unit": "sweeps/s", "ms_per_step": total_ms / (2.0 * args.steps), "scaling": "weak",
                  "dtype": bench.DTYPE, "data": "synthetic",
@@ -263,8 +265,10 @@ def run_nmtf(args, rank, world, device, dist, barrier, max_over_ranks, sum_over_
                             "stats_kernels": engs["vb"].stats_impl, "gibbs_sweeps_per_s": args.steps / (ms["gibbs"] / 1e3),
                             "vb_sweeps_per_s": args.steps / (ms["vb"] / 1e3),
                             "train_MSE_after": {k: float(v[engine.S_MSE]) for k, v in sc.items()},
-                            "l2": "inputs (2 x %.1f GiB of digit planes + one 16 GiB pass for the metrics per sweep) far larger than L2" % (N * 6 / 2 ** 30)},
-                 "roofline": {"bound": "hbm", "kernel": "whole sweep (two statistics phases on the tcgen05 kernels + the direct metrics pass)",
+                            "metrics": engs["vb"].metrics_mode,
+                            "l2": "inputs (2 x %.1f GiB of digit planes%s per sweep) far larger than L2"
+                                  % (N * 6 / 2 ** 30, "" if stat else " + one 16 GiB pass for the metrics")},
+                 "roofline": {"bound": "hbm", "kernel": "whole sweep (two statistics phases on the tcgen05 kernels%s)" % ("" if stat else " + the direct metrics pass"),
                               "achieved": b_alg / sweep_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": b_alg / sweep_s / 1e9 / hbm,
                               "traffic": None, "algorithmic_bytes_per_sweep": b_alg, "peak_kind": kind},
                  "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary()})

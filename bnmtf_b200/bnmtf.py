@@ -56,7 +56,7 @@ class BNMTFEngine:
         n, KPm, GLm = max(I, J), max(KPk, KPl), max(GLk, GLl)
         self.eff = {"RX": f64(n, KPm), "G": f64(n, GLm), "SV": f64(n, KPm)}      # effective-factor statistics
         self.gscratch = f64(296 * (GLm + KPm))       # bnmtf_gram_full_f64: up to 296 partial results
-        self.nparts = 64
+        self.nparts = max(1, min(148, -(-I // 16)))    # CTAs of the S-phase reduction (16 rows per step, csrc/nmtf.cu)
         self.sq_len = D * D + 2 * D
         self.sq_part, self.sq_out = f64(self.nparts * self.sq_len), f64(self.sq_len)
         self.extra = f64(J)
@@ -64,7 +64,7 @@ class BNMTFEngine:
         self.m8, self.el8, self.ex1 = self.red[0:8], self.red[8:16], self.red[16:17]
         self.nseg_m = max(1, min(ds.ldJ // 128, -(-1776 // ((I + 127) // 128))))
         self.mpart = f64(((I + 127) // 128) * self.nseg_m * 8)
-        self.nb_terms = 32
+        self.nb_terms = 32 if max(I * self.K, J * self.L) <= (1 << 16) else 296      # CTAs of the ELBO factor terms
         self.elpart = f64(3 * self.nb_terms * 8)
         # Statistics kernels: the fp64 mma.sync ones at toy / GDSC sizes (latency-bound there, fewer launches), the tcgen05
         # fixed-point ones of the two-factor engine for large matrices (BNMTF_NMTF_STATS=umma|dmma overrides).  A dataset
@@ -84,6 +84,14 @@ class BNMTFEngine:
                                     for d, ld in ((self.L, ds.ldJ), (self.K, ds.ldI)))
                 self.ws = torch.zeros(self.ws_bytes + 1024, dtype=torch.uint8, device=dev)
                 self.ws_ptr = (self.ws.data_ptr() + 1023) // 1024 * 1024
+        # training metrics of a sweep: "stats" = from the column statistics of the G phase (csrc/nmtf.cu::k_nmtf_mstat: no
+        # third pass over R; the direct pass runs only when the device-side cancellation guard trips, as in the two-factor
+        # engine), "direct" = always the pass over R
+        self.metrics_mode = os.environ.get("BNMTF_METRICS", "stats" if self.stats_impl == "umma" else "direct")
+        self.guard = 1e-5
+        self.mstat, self.mstat_part, self.sums4, self.m8d = f64(J, 4), f64(256), f64(4), f64(8)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._side = self._ev = None
         self.statics = f64(3)
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(ds.bits), I, ds.ldJ, _ptr(self.FS.Xp), _ptr(self.G.Xp),
                   self.L, self.nseg_m, 0, _ptr(self.mpart), _ptr(self.m8), 0, _stream())
@@ -134,6 +142,12 @@ class BNMTFEngine:
         self.sweeps_done += int(sweeps)
 
     # ---- layer 1 ------------------------------------------------------------------------------------------
+    @staticmethod
+    def split(dim):
+        if "BNMTF_SPLIT" in os.environ:
+            return int(os.environ["BNMTF_SPLIT"])
+        return 64 if dim > 16 else (80 if dim > 8 else 96)
+
     def _stats(self, st, R, bits, rows, ld, other, dim, need_rx=True):
         other.pad()
         if self.polarity == 0:
@@ -144,13 +158,36 @@ class BNMTFEngine:
             # statistics of the tri-factorisation ARE two-factor statistics w.r.t. G (rows) and F (columns); one segment,
             # because the transform / S-reduction kernels read one record per row
             side = 0 if R is self.ds.R else 1
-            if need_rx:
+            sums = 1 if (side == 1 and self.metrics_mode == "stats") else 0        # slot (k, K): masked column sums of F
+
+            def rx(max_ctas):
                 planes, rscale = self.ds.ensure_planes(side)[:2]
                 _lib.call("bnmtf_stats_rx_umma_f64", planes.data_ptr(), _ptr(rscale), _ptr(R), _ptr(bits), rows, ld, other.n,
-                          _ptr(other.Xp), dim, 1, 0, _ptr(st["RX"]), self.wsrx_ptr, self.wsrx_bytes, _stream())
-            _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, other.n, _ptr(other.Xp), _ptr(other.Vp), dim,
-                      self.polarity, 1, 128 if ld >= 256 else 64, 1, 0, 0, _ptr(st["G"]), _ptr(st["SV"]) if self.vb else 0,
-                      self.ws_ptr, self.ws_bytes, _stream())
+                          _ptr(other.Xp), dim, 1, max_ctas, _ptr(st["RX"]), self.wsrx_ptr, self.wsrx_bytes, _stream())
+
+            def gram():
+                _lib.call("bnmtf_stats_gram_umma_f64", _ptr(bits), rows, ld, other.n, _ptr(other.Xp), _ptr(other.Vp), dim,
+                          self.polarity, 1, 128 if ld >= 256 else 64, 1, sums, 0, _ptr(st["G"]), _ptr(st["SV"]) if self.vb else 0,
+                          self.ws_ptr, self.ws_bytes, _stream())
+            split = self.split(dim)
+            if need_rx and split > 0:
+                # SM split of the two-factor engine (engine.py::_stats_kernels): the HBM-bound R.X kernel on `split` SMs of
+                # a high-priority stream, the tensor-bound Gram kernel on the rest
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.ds.device, priority=-1)
+                    self._ev = [torch.cuda.Event(), torch.cuda.Event()]
+                main = torch.cuda.current_stream()
+                self._ev[0].record(main)
+                self._side.wait_event(self._ev[0])
+                with torch.cuda.stream(self._side):
+                    rx(split)
+                    self._ev[1].record(self._side)
+                gram()
+                main.wait_event(self._ev[1])
+            else:
+                if need_rx:
+                    rx(0)
+                gram()
             return
         if need_rx:
             _lib.call("bnmtf_stats_rx_f64", _ptr(R), _ptr(bits), rows, ld, _ptr(other.Xp), dim, 1, _ptr(st["RX"]), _stream())
@@ -220,7 +257,9 @@ class BNMTFEngine:
                   _ptr(self.iter if use_iter else self.iter_scratch), 2, _stream())
         del keep
 
-    def metrics(self, bits=None):
+    def metrics(self, bits=None, gated=False):
+        """Masked sums over `bits` (default: the training mask) with the current factors -> self.m8.  gated: -> self.m8d,
+        and the pass over R only runs if the device flag of the statistics-based metrics is raised."""
         ds = self.ds
         _lib.call("bnmtf_small_matmul_f64", _ptr(self.F.fac), _ptr(self.S["fac"]), ds.I, self.K, self.L, 0,
                   _ptr(self.FS.fac), _stream())
@@ -229,7 +268,20 @@ class BNMTFEngine:
         bits = ds.bits if bits is None else bits
         statics = _ptr(self.statics) if bits is ds.bits else 0
         _lib.call("bnmtf_masked_metrics_f64", _ptr(ds.R), _ptr(bits), ds.I, ds.ldJ, _ptr(self.FS.Xp), _ptr(self.G.Xp),
-                  self.L, self.nseg_m, statics, _ptr(self.mpart), _ptr(self.m8), 0, _stream())
+                  self.L, self.nseg_m, statics, _ptr(self.mpart), _ptr(self.m8d if gated else self.m8),
+                  _ptr(self.flag) if gated else 0, _stream())
+
+    def metrics_from_stats(self):
+        """Training metrics right after the G phase of a sweep: the column statistics are current w.r.t. F, and S and G
+        are the new ones, so the three masked sums follow from them column by column (k_nmtf_mstat)."""
+        ds = self.ds
+        _lib.call("bnmtf_nmtf_mstat_f64", ds.J, self.K, self.L, self.polarity, _ptr(self.col["RX"]), _ptr(self.col["G"]),
+                  _ptr(self.col["full"]), _ptr(self.G.fac), _ptr(self.S["fac"]), _ptr(self.mstat), _stream())
+        _lib.call("bnmtf_mstat_reduce_f64", _ptr(self.mstat), ds.J, _ptr(self.mstat_part), _ptr(self.sums4), _stream())
+        _lib.call("bnmtf_metrics_from_sums_f64", _ptr(self.sums4), _ptr(self.statics), self.guard, _ptr(self.m8),
+                  _ptr(self.flag), _stream())
+        self.metrics(gated=True)                 # returns at once unless the guard tripped
+        _lib.call("bnmtf_select_metrics_f64", _ptr(self.flag), _ptr(self.m8d), _ptr(self.m8), _stream())
 
     def vb_extra(self):
         """Variance terms of exp_square_diff; the column statistics must be current w.r.t. F."""
@@ -318,7 +370,10 @@ class BNMTFEngine:
             self.phase_S(minimum_TN=minimum_TN)
             self.stats_cols()
             self.phase_G(minimum_TN=minimum_TN)
-        self.metrics()
+        if self.metrics_mode == "stats":
+            self.metrics_from_stats()
+        else:
+            self.metrics()
         self.finish(update_tau=True, record=True)
 
     def alloc_trace(self, iterations):

@@ -100,6 +100,8 @@ int launch_nmtf_transform(const TransformArgs&, cudaStream_t);
 int launch_nmtf_sq(const SqArgs&, int, double*, cudaStream_t);
 int launch_coord_solve(const CoordArgs&, cudaStream_t);
 int launch_nmtf_extra(const ExtraArgs&, cudaStream_t);
+int launch_nmtf_mstat(int, int, int, int, const double*, const double*, const double*, const double*, const double*, double*,
+                      cudaStream_t);
 
 int launch_finish(const FinishArgs&, cudaStream_t);
 
@@ -509,6 +511,12 @@ int bnmtf_nmtf_extra_f64(int64_t rows, int K, int L, int polarity, const double*
   a.rows = (int)rows; a.K = K; a.L = L; a.polarity = polarity; a.Go = Go; a.SVo = SVo; a.Gfull_o = Gfull_o; a.G = G;
   a.varG = varG; a.S = S; a.varS = varS; a.extra = extra;
   return launch_nmtf_extra(a, ST(stream));
+}
+
+int bnmtf_nmtf_mstat_f64(int64_t rows, int K, int L, int polarity, const double* RXo, const double* Go,
+                         const double* Gfull_o, const double* G, const double* S, double* mstat, void* stream) {
+  if (check_k(K) || check_k(L)) return -2;
+  return launch_nmtf_mstat((int)rows, K, L, polarity, RXo, Go, Gfull_o, G, S, mstat, ST(stream));
 }
 
 int bnmtf_tn_moments_f64(const double* mu, const double* tau, int64_t n, double* ex, double* var, void* stream) {

@@ -142,56 +142,218 @@ __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
     for (int i = threadIdx.x; i < tot; i += 256) a.partial[(size_t)blockIdx.x * tot + i] = H[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// k_nmtf_sq_tiled: the same reduction as a register-tiled product.  H[(k,l),(k',l')] = sum_i (F_ik F_ik') GG_i[l,l'] is
+// C = A^T B over the rows of R with A_i = vec(F_i F_i^T) (K^2 entries) and B_i = vec(GG_i) (L^2 entries); for VB A_i
+// gets K more entries (varF_i) and B_i L more (the observed variance sums sv_i), which yields the three covariance
+// blocks and the precision terms from the same product:
+//   C[(k,k'), N + l] = sum f_k f_k' sv_l   (cov_term_G)      C[M + k, (l,l')] = sum varF_k GG[l,l']   (cov_term_F)
+//   C[M + k, N + l]  = sum varF_k sv_l     (precision only)
+// 512 threads; SQ_RB rows are staged in shared memory per step, every warp owns SQ_NT blocks of (4x8 threads) x (4x4
+// entries) of C in registers; the last step folds C into the (H, prec, rhs) layout of k_nmtf_sq_partial.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SQ_RB = 16, SQ_NT = 2, SQ_THREADS = 512;
+
+struct SqTiling { int Mext, Next, Mp, Np, WTM, WTN; size_t smem; bool ok; };
+__host__ __device__ inline SqTiling sq_tiling(int K, int L, int vb) {
+  SqTiling t;
+  t.Mext = K * K + (vb ? K : 0); t.Next = L * L + (vb ? L : 0);
+  t.Mp = (t.Mext + 3) & ~3; t.Np = (t.Next + 3) & ~3;
+  t.WTM = (t.Mp / 4 + 3) / 4; t.WTN = (t.Np / 4 + 7) / 8;
+  const size_t stage = (size_t)SQ_RB * (t.Mp + t.Np + 2 * K + L) * sizeof(double);
+  const size_t cmat = (size_t)t.Mp * t.Np * sizeof(double);
+  const size_t tables = (size_t)t.Next * (sizeof(double) + sizeof(int)) + (size_t)t.Mext * sizeof(int) + 16;
+  t.smem = (stage > cmat ? stage : cmat) + tables;
+  t.ok = t.WTM * t.WTN <= (SQ_THREADS / 32) * SQ_NT && K * L <= SQ_THREADS && t.smem <= 200 * 1024;
+  return t;
+}
+
+template <bool VB>
+__global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
+  extern __shared__ double sm[];
+  const int K = a.K, L = a.L, D = K * L, M = K * K, N = L * L;
+  const SqTiling t = sq_tiling(K, L, VB ? 1 : 0);
+  const int Mp = t.Mp, Np = t.Np, Mext = t.Mext;
+  const int ntl = tiles_for(L), KPl = 8 * ntl, gll = ntl * (ntl + 1) / 2 * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // shared memory: [ stage: As | Bs | Fs | VFs | RGs ] (later reused for C) then the tables
+  const size_t stage = (size_t)SQ_RB * (Mp + Np + 2 * K + L), cmat = (size_t)Mp * Np;
+  double* As = sm;
+  double* Bs = As + SQ_RB * Mp;
+  double* Fs = Bs + SQ_RB * Np;
+  double* VFs = Fs + SQ_RB * K;
+  double* RGs = VFs + SQ_RB * K;
+  double* gfB = sm + (stage > cmat ? stage : cmat);            // full-set value of entry n (polarity 0), else 0
+  int* idxB = reinterpret_cast<int*>(gfB + t.Next);             // offset of entry n in a row's Gram tiles / variance sums
+  int* kkA = idxB + t.Next;                                     // k | k' << 16 of entry m
+  const int Next = t.Next;
+  for (int n = tid; n < Next; n += SQ_THREADS) {
+    if (n < N) {
+      int la = n / L, lb = n - la * L;
+      if (la > lb) { const int x = la; la = lb; lb = x; }
+      const int ta = la >> 3, tb = lb >> 3;
+      const int idx = (ta * ntl - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (la & 7) * 8 + (lb & 7);
+      idxB[n] = idx;
+      gfB[n] = a.polarity ? 0.0 : a.Gfull_o[idx];
+    } else {
+      idxB[n] = n - N;
+      gfB[n] = a.polarity ? 0.0 : a.Gfull_o[gll + n - N];
+    }
+  }
+  for (int m = tid; m < Mext; m += SQ_THREADS) kkA[m] = m < M ? ((m / K) | ((m % K) << 16)) : (m - M);
+  for (int i = tid; i < SQ_RB * (Mp + Np); i += SQ_THREADS) As[i] = 0.0;       // (padding entries stay zero)
+  int aoff[SQ_NT], boff[SQ_NT];
+  bool valid[SQ_NT];
+#pragma unroll
+  for (int q = 0; q < SQ_NT; ++q) {
+    const int w = q * (SQ_THREADS / 32) + warp;
+    const int wtm = w / t.WTN, wtn = w - wtm * t.WTN;
+    aoff[q] = 4 * (wtm * 4 + (lane >> 3));
+    boff[q] = 4 * (wtn * 8 + (lane & 7));
+    valid[q] = w < t.WTM * t.WTN && aoff[q] < Mp && boff[q] < Np;
+  }
+  double acc[SQ_NT][4][4];
+#pragma unroll
+  for (int q = 0; q < SQ_NT; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.0;
+  double rhs = 0.0;                                             // thread d < D: sum_i F_ik RG_il
+  const int dk = tid < D ? tid / L : 0, dl = tid < D ? tid - dk * L : 0;
+  const int nbatch = (a.rows + SQ_RB - 1) / SQ_RB;
+  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+    const int row0 = bt * SQ_RB;
+    __syncthreads();                                            // the previous step's products are done
+    // (flat loops: every thread has a few independent global loads in flight)
+#pragma unroll 4
+    for (int e = tid; e < SQ_RB * Next; e += SQ_THREADS) {
+      const int r = e / Next, n = e - r * Next, row = row0 + r;
+      const bool in = row < a.rows;
+      const double* src = n < N ? a.Go + (size_t)row * gll + idxB[n] : a.SVo + (size_t)row * KPl + idxB[n];
+      const double raw = in ? __ldg(src) : 0.0;
+      Bs[r * Np + n] = in ? (a.polarity ? raw : gfB[n] - raw) : 0.0;
+    }
+    for (int e = tid; e < SQ_RB * K; e += SQ_THREADS) {
+      const int r = e / K, row = row0 + r;
+      const bool in = row < a.rows;
+      Fs[e] = in ? a.F[(size_t)row0 * K + e] : 0.0;
+      VFs[e] = (VB && in) ? a.varF[(size_t)row0 * K + e] : 0.0;
+    }
+    for (int e = tid; e < SQ_RB * L; e += SQ_THREADS) {
+      const int r = e / L, l = e - r * L, row = row0 + r;
+      RGs[e] = row < a.rows ? a.RXo[(size_t)row * KPl + l] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < SQ_RB * Mext; e += SQ_THREADS) {
+      const int r = e / Mext, m = e - r * Mext, c = kkA[m];
+      As[r * Mp + m] = m < M ? Fs[r * K + (c & 0xffff)] * Fs[r * K + (c >> 16)] : VFs[r * K + c];
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < SQ_RB; ++r) {
+#pragma unroll
+      for (int q = 0; q < SQ_NT; ++q) {
+        if (!valid[q]) continue;
+        const double2 a0 = *reinterpret_cast<const double2*>(As + r * Mp + aoff[q]);
+        const double2 a1 = *reinterpret_cast<const double2*>(As + r * Mp + aoff[q] + 2);
+        const double2 b0 = *reinterpret_cast<const double2*>(Bs + r * Np + boff[q]);
+        const double2 b1 = *reinterpret_cast<const double2*>(Bs + r * Np + boff[q] + 2);
+        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[q][i][j] = fma(av[i], bv[j], acc[q][i][j]);
+      }
+      if (tid < D) rhs = fma(Fs[r * K + dk], RGs[r * L + dl], rhs);
+    }
+  }
+  __syncthreads();
+  double* C = sm;                                               // Mp x Np, over the staging area
+#pragma unroll
+  for (int q = 0; q < SQ_NT; ++q)
+    if (valid[q])
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) C[(size_t)(aoff[q] + i) * Np + boff[q] + j] = acc[q][i][j];
+  __syncthreads();
+  double* out = a.partial + (size_t)blockIdx.x * ((size_t)D * D + 2 * D);
+  for (int i = tid; i < D * D; i += SQ_THREADS) {
+    const int d = i / D, d2 = i - d * D;
+    const int k = d / L, l = d - k * L, k2 = d2 / L, l2 = d2 - k2 * L;
+    double v = C[(size_t)(k * K + k2) * Np + l * L + l2];
+    if (VB) {
+      if (l == l2 && k != k2) v += C[(size_t)(k * K + k2) * Np + N + l];
+      if (k == k2 && l != l2) v += C[(size_t)(M + k) * Np + l * L + l2];
+    }
+    out[i] = v;
+  }
+  if (tid < D) {
+    double p = C[(size_t)(dk * K + dk) * Np + dl * L + dl];
+    if (VB) p += C[(size_t)(dk * K + dk) * Np + N + dl] + C[(size_t)(M + dk) * Np + dl * L + dl] + C[(size_t)(M + dk) * Np + N + dl];
+    out[D * D + tid] = p;
+    out[D * D + D + tid] = rhs;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_coord_solve: sequential scalar updates of x (D entries) on the small system (H, prec, rhs):
 //   s = rhs_d - sum_{d' != d} H[d][d'] x_d' ; tau_d = tau * prec_d ; mu_d = 1/tau_d (-lambda_d + tau s)
 // Single CTA.  Reproduces tauS/muS + TN_draw / TN moments / TN_mode for every (k,l) in `order`.
 // ---------------------------------------------------------------------------------------------------
 
+template <bool STAGED>
 __global__ void __launch_bounds__(256) k_coord_solve(CoordArgs a) {
-  extern __shared__ double xs[];   // D
-  __shared__ double red[8];
-  __shared__ double bcast;
+  // the D updates are one dependent chain: the whole CTA stages H (when D*D doubles fit shared memory), then warp 0 runs
+  // the chain alone -- warp-synchronous, every lane holds the full dot product and evaluates the same update
+  extern __shared__ double xs[];   // x, rhs, prec, lambda: D each  (+ D*D: H)
   const int D = a.D;
-  for (int i = threadIdx.x; i < D; i += 256) xs[i] = a.x[i];
+  double *rhs_s = xs + D, *prec_s = rhs_s + D, *lam_s = prec_s + D, *Hs = lam_s + D;
+  for (int i = threadIdx.x; i < D; i += 256) {
+    xs[i] = a.x[i]; rhs_s[i] = a.rhs[i]; prec_s[i] = a.prec[i]; lam_s[i] = a.lambda[i];
+  }
+  if (STAGED)
+    for (int i = threadIdx.x; i < D * D; i += 256) Hs[i] = a.H[i];
   __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   const double tau = a.scalars[S_TAU];
   const unsigned long long it = a.iter ? *a.iter : 0ull;
   for (int o = 0; o < a.n_order; ++o) {
     const int d = a.order ? a.order[o] : o;
+    const double* Hrow = STAGED ? Hs + (size_t)d * D : a.H + (size_t)d * D;
     double part = 0.0;
-    for (int i = threadIdx.x; i < D; i += 256)
-      if (i != d) part = fma(a.H[(size_t)d * D + i], xs[i], part);
-    part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double dot = 0.0;
-      for (int w = 0; w < 8; ++w) dot += red[w];
-      const double s = a.rhs[d] - dot;
-      const double tau_d = tau * a.prec[d];
-      const double mu_d = (1.0 / tau_d) * (-a.lambda[d] + tau * s);
-      double val = xs[d], vv = 0.0;
+    for (int i = lane; i < D; i += 32)
+      if (i != d) part = fma(Hrow[i], xs[i], part);
+    const double dot = warp_sum(part);
+    const double s = rhs_s[d] - dot;
+    const double tau_d = tau * prec_s[d];
+    const double mu_d = (1.0 / tau_d) * (-lam_s[d] + tau * s);
+    double val = xs[d], vv = 0.0;
+    if (a.apply) {
+      if (a.mode == MODE_GIBBS) {
+        Philox rng(a.seed, it * 16ull + a.salt, (unsigned long long)d);
+        val = tn_draw(mu_d, tau_d, rng);
+      } else if (a.mode == MODE_VB) {
+        tn_moments(mu_d, tau_d, val, vv);
+      } else {
+        val = (mu_d != mu_d) ? mu_d : fmax(mu_d, 0.0);
+        val = (val != val) ? val : fmax(val, a.min_tn);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
       if (a.apply) {
-        if (a.mode == MODE_GIBBS) {
-          Philox rng(a.seed, it * 16ull + a.salt, (unsigned long long)d);
-          val = tn_draw(mu_d, tau_d, rng);
-        } else if (a.mode == MODE_VB) {
-          tn_moments(mu_d, tau_d, val, vv);
-          a.var[d] = vv;
-        } else {
-          val = (mu_d != mu_d) ? mu_d : fmax(mu_d, 0.0);
-          val = (val != val) ? val : fmax(val, a.min_tn);
-        }
+        if (a.mode == MODE_VB) a.var[d] = vv;
         a.x[d] = val;
       }
       if (a.mu) a.mu[d] = mu_d;
       if (a.tauf) a.tauf[d] = tau_d;
-      bcast = val;
+      xs[d] = val;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) xs[d] = bcast;
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -244,6 +406,44 @@ __global__ void k_nmtf_extra(ExtraArgs a) {
   if (lane == 0) a.extra[row] = acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// k_nmtf_mstat: the three masked sums the training metrics need, per column j of R, from the column statistics
+// w.r.t. F (c_j = sum_i m r F_i, FF_j = sum_i m F_i F_i^T, s_j = sum_i m F_i: slot (k, K) of the Gram tiles) and the
+// current S and G_j.  With y = S G_j:   sum_i m r p = y.c_j,   sum_i m p^2 = y^T FF_j y,   sum_i m p = y.s_j
+// (p = F S G^T; compute_statistics of the reference, bnmtf_gibbs_optimised.py:251-281, takes them from a pass over R).
+// mstat: rows x 4 (rp, pp, sp, 0) -- the layout k_mstat_partial of solve.cu reduces.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_nmtf_mstat(int rows, int K, int L, int polarity, const double* __restrict__ RXo,
+                             const double* __restrict__ Go, const double* __restrict__ Gfull_o,
+                             const double* __restrict__ G, const double* __restrict__ S, double* __restrict__ mstat) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.x * nw + warp;
+  if (row >= rows) return;
+  const int ntk = tiles_for(K), KPk = 8 * ntk, glk = ntk * (ntk + 1) / 2 * 64;
+  double* y = sm + (size_t)warp * K;
+  const double* g = G + (size_t)row * L;
+  for (int k = lane; k < K; k += 32) {
+    double t = 0.0;
+    for (int l = 0; l < L; ++l) t = fma(S[k * L + l], g[l], t);
+    y[k] = t;
+  }
+  __syncwarp();
+  const double* gp = Go + (size_t)row * glk;
+  double rp = 0.0, pp = 0.0, sp = 0.0;
+  for (int i = lane; i < K * K; i += 32) {
+    const int k = i / K, k2 = i - k * K;
+    pp = fma(y[k] * y[k2], gram_at(gp, Gfull_o, polarity, ntk, k, k2), pp);
+  }
+  for (int k = lane; k < K; k += 32) {
+    rp = fma(y[k], RXo[(size_t)row * KPk + k], rp);
+    sp = fma(y[k], gram_at(gp, Gfull_o, polarity, ntk, k, K), sp);
+  }
+  rp = warp_sum(rp); pp = warp_sum(pp); sp = warp_sum(sp);
+  if (lane == 0) *reinterpret_cast<double4*>(mstat + (size_t)row * 4) = make_double4(rp, pp, sp, 0.0);
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------
 static int pick_warps(size_t per_warp_bytes, int max_warps) {
   int w = (int)(96 * 1024 / (per_warp_bytes ? per_warp_bytes : 1));
@@ -272,6 +472,15 @@ __global__ void k_sum_partials2(const double* __restrict__ partial, int nparts, 
 }
 int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
   const int D = a.K * a.L;
+  const SqTiling t = sq_tiling(a.K, a.L, a.vb);
+  if (t.ok) {
+    auto kern = a.vb ? k_nmtf_sq_tiled<true> : k_nmtf_sq_tiled<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    kern<<<nparts, SQ_THREADS, t.smem, st>>>(a);
+    const int len = D * D + 2 * D;
+    k_sum_partials2<<<(len + 127) / 128, 128, 0, st>>>(a.partial, nparts, len, out);
+    return check_launch("nmtf_sq");
+  }
   const size_t small = ((size_t)a.L * a.L + 2 * a.L + 2 * a.K) * sizeof(double);
   const size_t smem = ((size_t)D * D + 2 * D) * sizeof(double) + small;
   if (smem <= 200 * 1024) {
@@ -287,7 +496,14 @@ int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
 }
 
 int launch_coord_solve(const CoordArgs& a, cudaStream_t st) {
-  k_coord_solve<<<1, 256, (size_t)a.D * sizeof(double), st>>>(a);
+  const size_t staged = ((size_t)a.D * a.D + 4 * a.D) * sizeof(double);
+  if (staged <= 200 * 1024) {
+    cudaFuncSetAttribute(k_coord_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_coord_solve<true><<<1, 256, staged, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_coord_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_coord_solve<false><<<1, 256, (size_t)4 * a.D * sizeof(double), st>>>(a);
+  }
   return check_launch("coord_solve");
 }
 
@@ -297,6 +513,14 @@ int launch_nmtf_extra(const ExtraArgs& a, cudaStream_t st) {
   cudaFuncSetAttribute(k_nmtf_extra, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   k_nmtf_extra<<<(a.rows + warps - 1) / warps, warps * 32, per * warps, st>>>(a);
   return check_launch("nmtf_extra");
+}
+
+int launch_nmtf_mstat(int rows, int K, int L, int polarity, const double* RXo, const double* Go, const double* Gfull_o,
+                      const double* G, const double* S, double* mstat, cudaStream_t st) {
+  const int warps = 8;
+  k_nmtf_mstat<<<(rows + warps - 1) / warps, warps * 32, (size_t)warps * K * sizeof(double), st>>>(
+      rows, K, L, polarity, RXo, Go, Gfull_o, G, S, mstat);
+  return check_launch("nmtf_mstat");
 }
 
 }  // namespace bnmtf

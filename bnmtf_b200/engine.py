@@ -476,7 +476,7 @@ class BNMFEngine:
         self.red = f64(24)          # [0:8] metric sums, [8:16] factor ELBO terms, [16] VB extra term
         self.m8, self.el8, self.ex1, self.sums4 = self.red[0:8], self.red[8:16], self.red[16:17], self.red[17:21]
         self.mpart = f64(((rI + 127) // 128) * self.nseg[0][2] * 8)
-        self.nb_terms = 64
+        self.nb_terms = 64 if max(rI, rJ) * self.K <= (1 << 17) else 296      # CTAs of the ELBO factor terms
         self.elpart = f64(2 * self.nb_terms * 8) if self.vb else None
         self.sterm = None
         self.order_dev = None

@@ -324,6 +324,7 @@ def test_large_matrices_run_the_tcgen05_statistics(monkeypatch, cls_name, its):
         else:
             m.run(its)
         assert m._engine().stats_impl == impl
+        assert m._engine().metrics_mode == ("stats" if impl == "umma" else "direct")
         out[impl] = m
     monkeypatch.delenv("BNMTF_NMTF_STATS")
     a, b = out["umma"], out["dmma"]
@@ -343,3 +344,39 @@ def test_large_matrices_run_the_tcgen05_statistics(monkeypatch, cls_name, its):
     m.initialise("random", "random")
     m.run(1) if cls_name != "nmtf_icm" else m.run(1, minimum_TN=0.1)
     assert m._engine().stats_impl == "umma"
+
+
+@pytest.mark.parametrize("missing", [0.2, 0.8])
+@pytest.mark.parametrize("cls_name", ["bnmtf_vb_optimised", "bnmtf_gibbs_optimised"])
+def test_metrics_from_the_column_statistics(monkeypatch, cls_name, missing):
+    """With the tcgen05 statistics the training metrics of a sweep come from the column statistics of the G phase
+    (csrc/nmtf.cu::k_nmtf_mstat) instead of a pass over R (compute_statistics, bnmtf_gibbs_optimised.py:251-281): same
+    traces as the direct pass, for both mask polarities, and the direct pass takes over when the guard trips."""
+    import bnmtf_b200
+    rng = np.random.RandomState(8)
+    I, J, K, L = 1200, 3600, 4, 7
+    R = np.abs(rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (K, L)) @ rng.exponential(1.0, (J, L)).T + rng.normal(size=(I, J))) + 0.5
+    M = (rng.rand(I, J) >= missing).astype(float)
+    pri = {"alpha": 1.0, "beta": 1.0, "lambdaF": 0.1, "lambdaS": 0.1, "lambdaG": 0.1}
+    cls = getattr(bnmtf_b200, cls_name)
+    out = {}
+    for mode in ("stats", "direct", "guard"):
+        monkeypatch.setenv("BNMTF_METRICS", "direct" if mode == "direct" else "stats")
+        np.random.seed(2), random.seed(2)
+        m = cls(R, M, K, L, pri, seed=9)
+        m.initialise("random", "random")
+        eng = m._engine()
+        assert eng.stats_impl == "umma" and eng.polarity == (0 if missing < 0.5 else 1)
+        if mode == "guard":
+            eng.guard = 1e9                    # every sweep: the statistics-based sums are rejected on the device
+        m.run(3)
+        assert int(eng.flag.item()) == (1 if mode == "guard" else 0)
+        out[mode] = m
+    a, b, c = out["stats"], out["direct"], out["guard"]
+    # the sums behind the metrics carry the 1e-11..1e-10 relative error of the fixed-point statistics, and MSE / R^2 / Rp are
+    # differences of such sums: 1e-8 on the metrics; the fallback run repeats the direct run up to the rounding of one
+    # more column in the Gram kernel's launch plan
+    for key in ("MSE", "R^2", "Rp"):
+        close(a.all_performances[key], b.all_performances[key], rtol=1e-8, what=key)
+        close(c.all_performances[key], b.all_performances[key], rtol=1e-11, what=key + " (fallback)")
+    close(a.exptau if cls_name == "bnmtf_vb_optimised" else a.tau, b.exptau if cls_name == "bnmtf_vb_optimised" else b.tau, rtol=1e-8)
