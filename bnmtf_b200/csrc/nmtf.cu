@@ -226,14 +226,28 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
   for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
     const int row0 = bt * SQ_RB;
     __syncthreads();                                            // the previous step's products are done
-    // (flat loops: every thread has a few independent global loads in flight)
-#pragma unroll 4
-    for (int e = tid; e < SQ_RB * Next; e += SQ_THREADS) {
-      const int r = e / Next, n = e - r * Next, row = row0 + r;
-      const bool in = row < a.rows;
-      const double* src = n < N ? a.Go + (size_t)row * gll + idxB[n] : a.SVo + (size_t)row * KPl + idxB[n];
-      const double raw = in ? __ldg(src) : 0.0;
-      Bs[r * Np + n] = in ? (a.polarity ? raw : gfB[n] - raw) : 0.0;
+    // (flat, in chunks of four predicated elements per thread: four independent global loads in flight each)
+    for (int base = tid; base < SQ_RB * Next; base += 4 * SQ_THREADS) {
+      double raw[4];
+      int dst[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = base + j * SQ_THREADS;
+        const bool live = e < SQ_RB * Next;
+        const int r = live ? e / Next : 0, n = e - r * Next, row = row0 + r;
+        const bool in = live && row < a.rows;
+        const int off = live ? idxB[n] : 0;
+        const double* src = n < N ? a.Go + (size_t)row * gll + off : a.SVo + (size_t)row * KPl + off;
+        raw[j] = in ? __ldg(src) : 0.0;
+        dst[j] = live ? (r * Np + n) | (in ? 0 : 1 << 30) : -1;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (dst[j] < 0) continue;
+        const int o = dst[j] & ~(1 << 30);
+        const int n = o % Np;
+        Bs[o] = (dst[j] >> 30) ? 0.0 : (a.polarity ? raw[j] : gfB[n] - raw[j]);
+      }
     }
     for (int e = tid; e < SQ_RB * K; e += SQ_THREADS) {
       const int r = e / K, row = row0 + r;
@@ -463,12 +477,25 @@ int launch_nmtf_transform(const TransformArgs& a, cudaStream_t st) {
 int sq_partial_len(int K, int L) { const int D = K * L; return D * D + 2 * D; }
 
 int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st);   // defined below
-__global__ void k_sum_partials2(const double* __restrict__ partial, int nparts, int len, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= len) return;
+// 256 threads = 32 entries x 8 groups of partials: thread (g, e) adds the partials g, g + 8, ... of its entry, then the eight
+// group sums are added in a fixed order
+__global__ void __launch_bounds__(256) k_sum_partials2(const double* __restrict__ partial, int nparts, int len,
+                                                        double* __restrict__ out) {
+  __shared__ double red[8][32];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * len + i];
-  out[i] = s;
+  if (i < len)
+#pragma unroll 4
+    for (int p = g; p < nparts; p += 8) s += partial[(size_t)p * len + i];
+  red[g][e] = s;
+  __syncthreads();
+  if (g == 0 && i < len) {
+    double t = red[0][e];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][e];
+    out[i] = t;
+  }
 }
 int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
   const int D = a.K * a.L;
@@ -478,7 +505,7 @@ int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     kern<<<nparts, SQ_THREADS, t.smem, st>>>(a);
     const int len = D * D + 2 * D;
-    k_sum_partials2<<<(len + 127) / 128, 128, 0, st>>>(a.partial, nparts, len, out);
+    k_sum_partials2<<<(len + 31) / 32, 256, 0, st>>>(a.partial, nparts, len, out);
     return check_launch("nmtf_sq");
   }
   const size_t small = ((size_t)a.L * a.L + 2 * a.L + 2 * a.K) * sizeof(double);
@@ -491,7 +518,7 @@ int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
     k_nmtf_sq_partial<true><<<nparts, 256, small, st>>>(a);
   }
   const int len = D * D + 2 * D;
-  k_sum_partials2<<<(len + 127) / 128, 128, 0, st>>>(a.partial, nparts, len, out);
+  k_sum_partials2<<<(len + 31) / 32, 256, 0, st>>>(a.partial, nparts, len, out);
   return check_launch("nmtf_sq");
 }
 

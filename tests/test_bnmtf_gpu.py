@@ -380,3 +380,68 @@ def test_metrics_from_the_column_statistics(monkeypatch, cls_name, missing):
         close(a.all_performances[key], b.all_performances[key], rtol=1e-8, what=key)
         close(c.all_performances[key], b.all_performances[key], rtol=1e-11, what=key + " (fallback)")
     close(a.exptau if cls_name == "bnmtf_vb_optimised" else a.tau, b.exptau if cls_name == "bnmtf_vb_optimised" else b.tau, rtol=1e-8)
+
+
+@pytest.mark.parametrize("K,L", [(3, 4), (10, 10), (5, 9), (2, 30), (12, 12)])
+@pytest.mark.parametrize("vb", [0, 1])
+@pytest.mark.parametrize("polarity", [0, 1])
+def test_s_phase_reduction_is_the_einsum(K, L, vb, polarity):
+    """bnmtf_nmtf_sq_f64 (csrc/nmtf.cu: the register-tiled product k_nmtf_sq_tiled, and k_nmtf_sq_partial for shapes it does
+    not take, here K = L = 12) against the defining sums of the S update (bnmtf_vb_optimised.py:245-262,
+    bnmtf_gibbs_optimised.py:201-205) written with numpy on the same row statistics."""
+    import torch
+    from bnmtf_b200 import _lib
+    from bnmtf_b200.engine import _ptr, _stream, kp_for, gram_len
+    rng = np.random.RandomState(100 * K + L)
+    rows, D = 777, K * L
+    nt, KP, GL = kp_for(L) // 8, kp_for(L), gram_len(L)
+    Gm = rng.rand(rows, 40, L)
+    GG = np.einsum("ijl,ijm->ilm", Gm, Gm)                       # per-row Gram matrices (symmetric positive)
+    sv, rg = rng.rand(rows, L) * 3.0, rng.randn(rows, L) * 5.0
+    F, vF = rng.exponential(1.0, (rows, K)), rng.rand(rows, K) * 0.3
+    full_GG, full_sv = GG.max(axis=0) * 1.5 + 1.0, sv.max(axis=0) * 1.5 + 1.0
+
+    def pack(mats):                                               # (n, L, L) -> packed upper-triangular 8x8 tiles
+        out = np.zeros((mats.shape[0], GL))
+        P = np.zeros((mats.shape[0], KP, KP))
+        P[:, :L, :L] = mats
+        p = 0
+        for ta in range(nt):
+            for tb in range(ta, nt):
+                out[:, p * 64:(p + 1) * 64] = P[:, 8 * ta:8 * ta + 8, 8 * tb:8 * tb + 8].reshape(-1, 64)
+                p += 1
+        return out
+    # what the statistics kernels hold: sums over the observed set (polarity 1) or over the missing set (polarity 0)
+    held_GG = GG if polarity else full_GG[None] - GG
+    held_sv = sv if polarity else full_sv[None] - sv
+    dev = torch.device("cuda:0")
+    up = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
+    svp = np.zeros((rows, KP)); svp[:, :L] = held_sv
+    rgp = np.zeros((rows, KP)); rgp[:, :L] = rg
+    fullrec = np.zeros(GL + KP); fullrec[:GL] = pack(full_GG[None])[0]; fullrec[GL:GL + L] = full_sv
+    Go, SVo, RXo, Gfull, Fd, vFd = up(pack(held_GG)), up(svp), up(rgp), up(fullrec), up(F), up(vF)
+    nparts, ln = 37, D * D + 2 * D
+    part, out = torch.zeros(nparts * ln, dtype=torch.float64, device=dev), torch.zeros(ln, dtype=torch.float64, device=dev)
+    _lib.call("bnmtf_nmtf_sq_f64", rows, K, L, polarity, vb, _ptr(RXo), _ptr(Go), _ptr(SVo) if vb else 0, _ptr(Gfull), _ptr(Fd),
+              _ptr(vFd) if vb else 0, _ptr(part), nparts, _ptr(out), _stream())
+    got = out.cpu().numpy()
+    H = np.einsum("ik,im,iln->klmn", F, F, GG)
+    prec = np.einsum("ik,il->kl", F * F, np.einsum("ill->il", GG))
+    if vb:
+        covG = np.einsum("ik,im,il->kml", F, F, sv)
+        covF = np.einsum("ik,iln->kln", vF, GG)
+        for k in range(K):
+            for l in range(L):
+                for k2 in range(K):
+                    if k2 != k:
+                        H[k, l, k2, l] += covG[k, k2, l]
+                for l2 in range(L):
+                    if l2 != l:
+                        H[k, l, k, l2] += covF[k, l, l2]
+        prec = np.einsum("ik,il->kl", vF + F * F, np.einsum("ill->il", GG) + sv)
+    rhs = np.einsum("ik,il->kl", F, rg)
+    Hg = got[:D * D].reshape(D, D)
+    off = ~np.eye(D, dtype=bool)                                  # (the diagonal of H is never read by the coordinate updates)
+    close(Hg[off], H.reshape(D, D)[off], rtol=1e-11, what="H")
+    close(got[D * D:D * D + D], prec.reshape(-1), rtol=1e-11, what="precision")
+    close(got[D * D + D:], rhs.reshape(-1), rtol=1e-11, what="right-hand side")
