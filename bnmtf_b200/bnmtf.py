@@ -56,9 +56,10 @@ class BNMTFEngine:
         n, KPm, GLm = max(I, J), max(KPk, KPl), max(GLk, GLl)
         self.eff = {"RX": f64(n, KPm), "G": f64(n, GLm), "SV": f64(n, KPm)}      # effective-factor statistics
         self.gscratch = f64(296 * (GLm + KPm))       # bnmtf_gram_full_f64: up to 296 partial results
-        self.nparts = max(1, min(148, -(-I // 16)))    # CTAs of the S-phase reduction (16 rows per step, csrc/nmtf.cu)
+        self.nparts = int(_lib.call("bnmtf_nmtf_sq_parts", I, self.K, self.L, int(self.vb)))    # row partitions of the S-phase reduction
         self.sq_len = D * D + 2 * D
-        self.sq_part, self.sq_out = f64(self.nparts * self.sq_len), f64(self.sq_len)
+        self.sq_part = f64(self.nparts * int(_lib.call("bnmtf_nmtf_sq_scratch_len", self.K, self.L, int(self.vb))))
+        self.sq_out = f64(self.sq_len)
         self.extra = f64(J)
         self.red = f64(24)
         self.m8, self.el8, self.ex1 = self.red[0:8], self.red[8:16], self.red[16:17]

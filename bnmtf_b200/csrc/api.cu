@@ -98,6 +98,8 @@ int launch_np_metrics(const double*, const uint32_t*, const double*, int, int, i
 int launch_small_matmul(const double*, const double*, int, int, int, int, double*, cudaStream_t);
 int launch_nmtf_transform(const TransformArgs&, cudaStream_t);
 int launch_nmtf_sq(const SqArgs&, int, double*, cudaStream_t);
+long long sq_scratch_len(int, int, int);
+int sq_parts(long long, int, int, int);
 int launch_coord_solve(const CoordArgs&, cudaStream_t);
 int launch_nmtf_extra(const ExtraArgs&, cudaStream_t);
 int launch_nmtf_mstat(int, int, int, int, const double*, const double*, const double*, const double*, const double*, double*,
@@ -490,6 +492,14 @@ int bnmtf_nmtf_sq_f64(int64_t rows, int K, int L, int polarity, int vb, const do
   a.rows = (int)rows; a.K = K; a.L = L; a.polarity = polarity; a.vb = vb; a.RXo = RXo; a.Go = Go; a.SVo = SVo;
   a.Gfull_o = Gfull_o; a.F = F; a.varF = varF; a.partial = partial;
   return launch_nmtf_sq(a, nparts, out, ST(stream));
+}
+int64_t bnmtf_nmtf_sq_scratch_len(int K, int L, int vb) {
+  if (check_k(K) || check_k(L)) return -2;
+  return (int64_t)sq_scratch_len(K, L, vb);
+}
+int bnmtf_nmtf_sq_parts(int64_t rows, int K, int L, int vb) {
+  if (check_k(K) || check_k(L)) return -2;
+  return sq_parts((long long)rows, K, L, vb);
 }
 int bnmtf_coord_solve_f64(int mode, int D, const double* H, const double* prec, const double* rhs, const double* lambda,
                           double* x, double* var, double* mu, double* tauf, const double* scalars, const int* order,

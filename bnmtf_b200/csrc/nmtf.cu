@@ -150,22 +150,38 @@ __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
 // blocks and the precision terms from the same product:
 //   C[(k,k'), N + l] = sum f_k f_k' sv_l   (cov_term_G)      C[M + k, (l,l')] = sum varF_k GG[l,l']   (cov_term_F)
 //   C[M + k, N + l]  = sum varF_k sv_l     (precision only)
-// 512 threads; SQ_RB rows are staged in shared memory per step, every warp owns SQ_NT blocks of (4x8 threads) x (4x4
-// entries) of C in registers; the last step folds C into the (H, prec, rhs) layout of k_nmtf_sq_partial.
+// 512 threads; `rb` rows are staged in shared memory per step, every warp owns SQ_NT blocks of (4x8 threads) x (4x4
+// entries) of C in registers.  grid = (row partitions, passes): a CTA covers a PM x PN rectangle of the WTM x WTN warp
+// blocks of C (pass = blockIdx.y; one pass up to K = L = 10), stages only that rectangle's columns of A and B of its
+// share of the rows, and writes the rectangle into its row partition's slice of `partial` (Mp x Np, then the K*L
+// right-hand sides); k_sq_assemble adds the slices and folds C into (H, prec, rhs).
 // ---------------------------------------------------------------------------------------------------
-constexpr int SQ_RB = 16, SQ_NT = 2, SQ_THREADS = 512;
+constexpr int SQ_NT = 2, SQ_THREADS = 512, SQ_BLOCKS = (SQ_THREADS / 32) * SQ_NT, SQ_RHS = 2, SQ_MAX_PASSES = 64;
 
-struct SqTiling { int Mext, Next, Mp, Np, WTM, WTN; size_t smem; bool ok; };
+struct SqTiling { int Mext, Next, Mp, Np, WTM, WTN, PM, PN, npm, npn, npass, rb; size_t smem, plen; bool ok; };
 __host__ __device__ inline SqTiling sq_tiling(int K, int L, int vb) {
   SqTiling t;
   t.Mext = K * K + (vb ? K : 0); t.Next = L * L + (vb ? L : 0);
   t.Mp = (t.Mext + 3) & ~3; t.Np = (t.Next + 3) & ~3;
-  t.WTM = (t.Mp / 4 + 3) / 4; t.WTN = (t.Np / 4 + 7) / 8;
-  const size_t stage = (size_t)SQ_RB * (t.Mp + t.Np + 2 * K + L) * sizeof(double);
-  const size_t cmat = (size_t)t.Mp * t.Np * sizeof(double);
+  t.WTM = (t.Mp / 4 + 3) / 4; t.WTN = (t.Np / 4 + 7) / 8;     // warp blocks of 16 x 32 entries
+  // a pass (one CTA) covers a PM x PN rectangle of warp blocks, PM * PN = SQ_BLOCKS: the shape with the fewest passes, then
+  // the fewest staged columns (16 PM of A, 32 PN of B per row)
+  t.PM = SQ_BLOCKS; t.PN = 1; t.npass = 1 << 30;
+  int best_cols = 1 << 30;
+  for (int pn = 1; pn <= SQ_BLOCKS; pn <<= 1) {
+    const int pm = SQ_BLOCKS / pn;
+    const int np = ((t.WTM + pm - 1) / pm) * ((t.WTN + pn - 1) / pn), cols = 16 * pm + 32 * pn;
+    if (np < t.npass || (np == t.npass && cols < best_cols)) { t.PM = pm; t.PN = pn; t.npass = np; best_cols = cols; }
+  }
+  t.npm = (t.WTM + t.PM - 1) / t.PM; t.npn = (t.WTN + t.PN - 1) / t.PN;
+  t.plen = ((size_t)t.Mp * t.Np + (size_t)K * L + 1) & ~(size_t)1;       // (even: 16-byte aligned slices)
   const size_t tables = (size_t)t.Next * (sizeof(double) + sizeof(int)) + (size_t)t.Mext * sizeof(int) + 16;
-  t.smem = (stage > cmat ? stage : cmat) + tables;
-  t.ok = t.WTM * t.WTN <= (SQ_THREADS / 32) * SQ_NT && K * L <= SQ_THREADS && t.smem <= 200 * 1024;
+  t.rb = 16; t.smem = 0;
+  for (; t.rb >= 2; t.rb >>= 1) {
+    t.smem = (size_t)t.rb * (16 * t.PM + 32 * t.PN + 2 * K + L) * sizeof(double) + tables;
+    if (t.smem <= 200 * 1024) break;
+  }
+  t.ok = t.rb >= 2 && t.npass <= SQ_MAX_PASSES && K * L <= SQ_THREADS * SQ_RHS;
   return t;
 }
 
@@ -174,20 +190,22 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
   extern __shared__ double sm[];
   const int K = a.K, L = a.L, D = K * L, M = K * K, N = L * L;
   const SqTiling t = sq_tiling(K, L, VB ? 1 : 0);
-  const int Mp = t.Mp, Np = t.Np, Mext = t.Mext;
+  const int Mp = t.Mp, Np = t.Np, Mext = t.Mext, Next = t.Next, RB = t.rb;
   const int ntl = tiles_for(L), KPl = 8 * ntl, gll = ntl * (ntl + 1) / 2 * 64;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // shared memory: [ stage: As | Bs | Fs | VFs | RGs ] (later reused for C) then the tables
-  const size_t stage = (size_t)SQ_RB * (Mp + Np + 2 * K + L), cmat = (size_t)Mp * Np;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, pass = blockIdx.y;
+  // this pass's rectangle of C: columns [acol0, acol0 + AW) of A and [bcol0, bcol0 + BW) of B, of which an / bn exist
+  const int pi = pass / t.npn, pj = pass - pi * t.npn;
+  const int AW = 16 * t.PM, BW = 32 * t.PN, acol0 = pi * AW, bcol0 = pj * BW;
+  const int an = (acol0 + AW < Mext ? acol0 + AW : Mext) - acol0, bn = (bcol0 + BW < Next ? bcol0 + BW : Next) - bcol0;
+  // shared memory: the staged rows As | Bs | Fs | VFs | RGs, then the tables
   double* As = sm;
-  double* Bs = As + SQ_RB * Mp;
-  double* Fs = Bs + SQ_RB * Np;
-  double* VFs = Fs + SQ_RB * K;
-  double* RGs = VFs + SQ_RB * K;
-  double* gfB = sm + (stage > cmat ? stage : cmat);            // full-set value of entry n (polarity 0), else 0
-  int* idxB = reinterpret_cast<int*>(gfB + t.Next);             // offset of entry n in a row's Gram tiles / variance sums
-  int* kkA = idxB + t.Next;                                     // k | k' << 16 of entry m
-  const int Next = t.Next;
+  double* Bs = As + RB * AW;
+  double* Fs = Bs + RB * BW;
+  double* VFs = Fs + RB * K;
+  double* RGs = VFs + RB * K;
+  double* gfB = RGs + RB * L;                                   // full-set value of entry n (polarity 0), else 0
+  int* idxB = reinterpret_cast<int*>(gfB + Next);               // offset of entry n in a row's Gram tiles / variance sums
+  int* kkA = idxB + Next;                                       // k | k' << 16 of entry m
   for (int n = tid; n < Next; n += SQ_THREADS) {
     if (n < N) {
       int la = n / L, lb = n - la * L;
@@ -202,16 +220,16 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
     }
   }
   for (int m = tid; m < Mext; m += SQ_THREADS) kkA[m] = m < M ? ((m / K) | ((m % K) << 16)) : (m - M);
-  for (int i = tid; i < SQ_RB * (Mp + Np); i += SQ_THREADS) As[i] = 0.0;       // (padding entries stay zero)
+  for (int i = tid; i < RB * (AW + BW); i += SQ_THREADS) As[i] = 0.0;          // (padding entries stay zero)
   int aoff[SQ_NT], boff[SQ_NT];
   bool valid[SQ_NT];
 #pragma unroll
   for (int q = 0; q < SQ_NT; ++q) {
-    const int w = q * (SQ_THREADS / 32) + warp;
-    const int wtm = w / t.WTN, wtn = w - wtm * t.WTN;
-    aoff[q] = 4 * (wtm * 4 + (lane >> 3));
-    boff[q] = 4 * (wtn * 8 + (lane & 7));
-    valid[q] = w < t.WTM * t.WTN && aoff[q] < Mp && boff[q] < Np;
+    const int b = q * (SQ_THREADS / 32) + warp;                // block of the rectangle; offsets are relative to it
+    const int pm = b / t.PN, pn = b - pm * t.PN;
+    aoff[q] = 4 * (pm * 4 + (lane >> 3));
+    boff[q] = 4 * (pn * 8 + (lane & 7));
+    valid[q] = acol0 + aoff[q] < Mp && bcol0 + boff[q] < Np;
   }
   double acc[SQ_NT][4][4];
 #pragma unroll
@@ -220,95 +238,134 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.0;
-  double rhs = 0.0;                                             // thread d < D: sum_i F_ik RG_il
-  const int dk = tid < D ? tid / L : 0, dl = tid < D ? tid - dk * L : 0;
-  const int nbatch = (a.rows + SQ_RB - 1) / SQ_RB;
+  // pass 0 also accumulates the right-hand sides: thread -> entries d = tid, tid + 512:  sum_i F_ik RG_il
+  double rhs[SQ_RHS];
+  int dk[SQ_RHS], dl[SQ_RHS];
+#pragma unroll
+  for (int c = 0; c < SQ_RHS; ++c) {
+    const int d = tid + c * SQ_THREADS;
+    rhs[c] = 0.0;
+    dk[c] = (pass == 0 && d < D) ? d / L : -1;
+    dl[c] = dk[c] >= 0 ? d - dk[c] * L : 0;
+  }
+  const int nbatch = (a.rows + RB - 1) / RB;
   for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
-    const int row0 = bt * SQ_RB;
+    const int row0 = bt * RB;
     __syncthreads();                                            // the previous step's products are done
     // (flat, in chunks of four predicated elements per thread: four independent global loads in flight each)
-    for (int base = tid; base < SQ_RB * Next; base += 4 * SQ_THREADS) {
+    for (int base = tid; base < RB * bn; base += 4 * SQ_THREADS) {
       double raw[4];
       int dst[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int e = base + j * SQ_THREADS;
-        const bool live = e < SQ_RB * Next;
-        const int r = live ? e / Next : 0, n = e - r * Next, row = row0 + r;
+        const bool live = e < RB * bn;
+        const int r = live ? e / bn : 0, c = e - r * bn, n = bcol0 + c, row = row0 + r;
         const bool in = live && row < a.rows;
         const int off = live ? idxB[n] : 0;
         const double* src = n < N ? a.Go + (size_t)row * gll + off : a.SVo + (size_t)row * KPl + off;
         raw[j] = in ? __ldg(src) : 0.0;
-        dst[j] = live ? (r * Np + n) | (in ? 0 : 1 << 30) : -1;
+        dst[j] = live ? (r * BW + c) | (in ? 0 : 1 << 30) : -1;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (dst[j] < 0) continue;
         const int o = dst[j] & ~(1 << 30);
-        const int n = o % Np;
+        const int n = bcol0 + o % BW;
         Bs[o] = (dst[j] >> 30) ? 0.0 : (a.polarity ? raw[j] : gfB[n] - raw[j]);
       }
     }
-    for (int e = tid; e < SQ_RB * K; e += SQ_THREADS) {
+    for (int e = tid; e < RB * K; e += SQ_THREADS) {
       const int r = e / K, row = row0 + r;
       const bool in = row < a.rows;
       Fs[e] = in ? a.F[(size_t)row0 * K + e] : 0.0;
       VFs[e] = (VB && in) ? a.varF[(size_t)row0 * K + e] : 0.0;
     }
-    for (int e = tid; e < SQ_RB * L; e += SQ_THREADS) {
+    for (int e = tid; e < RB * L; e += SQ_THREADS) {
       const int r = e / L, l = e - r * L, row = row0 + r;
       RGs[e] = row < a.rows ? a.RXo[(size_t)row * KPl + l] : 0.0;
     }
     __syncthreads();
-    for (int e = tid; e < SQ_RB * Mext; e += SQ_THREADS) {
-      const int r = e / Mext, m = e - r * Mext, c = kkA[m];
-      As[r * Mp + m] = m < M ? Fs[r * K + (c & 0xffff)] * Fs[r * K + (c >> 16)] : VFs[r * K + c];
+    for (int e = tid; e < RB * an; e += SQ_THREADS) {
+      const int r = e / an, ca = e - r * an, m = acol0 + ca, c = kkA[m];
+      As[r * AW + ca] = m < M ? Fs[r * K + (c & 0xffff)] * Fs[r * K + (c >> 16)] : VFs[r * K + c];
     }
     __syncthreads();
 #pragma unroll 2
-    for (int r = 0; r < SQ_RB; ++r) {
+    for (int r = 0; r < RB; ++r) {
 #pragma unroll
       for (int q = 0; q < SQ_NT; ++q) {
         if (!valid[q]) continue;
-        const double2 a0 = *reinterpret_cast<const double2*>(As + r * Mp + aoff[q]);
-        const double2 a1 = *reinterpret_cast<const double2*>(As + r * Mp + aoff[q] + 2);
-        const double2 b0 = *reinterpret_cast<const double2*>(Bs + r * Np + boff[q]);
-        const double2 b1 = *reinterpret_cast<const double2*>(Bs + r * Np + boff[q] + 2);
+        const double2 a0 = *reinterpret_cast<const double2*>(As + r * AW + aoff[q]);
+        const double2 a1 = *reinterpret_cast<const double2*>(As + r * AW + aoff[q] + 2);
+        const double2 b0 = *reinterpret_cast<const double2*>(Bs + r * BW + boff[q]);
+        const double2 b1 = *reinterpret_cast<const double2*>(Bs + r * BW + boff[q] + 2);
         const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[q][i][j] = fma(av[i], bv[j], acc[q][i][j]);
       }
-      if (tid < D) rhs = fma(Fs[r * K + dk], RGs[r * L + dl], rhs);
+#pragma unroll
+      for (int c = 0; c < SQ_RHS; ++c)
+        if (dk[c] >= 0) rhs[c] = fma(Fs[r * K + dk[c]], RGs[r * L + dl[c]], rhs[c]);
     }
   }
-  __syncthreads();
-  double* C = sm;                                               // Mp x Np, over the staging area
+  double* C = a.partial + (size_t)blockIdx.x * t.plen;          // this row partition's Mp x Np (+ D) slice
 #pragma unroll
   for (int q = 0; q < SQ_NT; ++q)
     if (valid[q])
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        double2* o = reinterpret_cast<double2*>(C + (size_t)(acol0 + aoff[q] + i) * Np + bcol0 + boff[q]);
+        o[0] = make_double2(acc[q][i][0], acc[q][i][1]);
+        o[1] = make_double2(acc[q][i][2], acc[q][i][3]);
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) C[(size_t)(aoff[q] + i) * Np + boff[q] + j] = acc[q][i][j];
-  __syncthreads();
-  double* out = a.partial + (size_t)blockIdx.x * ((size_t)D * D + 2 * D);
-  for (int i = tid; i < D * D; i += SQ_THREADS) {
+  for (int c = 0; c < SQ_RHS; ++c)
+    if (dk[c] >= 0) C[(size_t)Mp * Np + tid + c * SQ_THREADS] = rhs[c];
+}
+
+// adds the row partitions' slices of C and folds them into (H, prec, rhs): 256 threads = 32 entries x 8 groups of slices
+template <bool VB>
+__global__ void __launch_bounds__(256) k_sq_assemble(const double* __restrict__ partial, int nparts, int K, int L,
+                                                      double* __restrict__ out) {
+  __shared__ double red[8][32];
+  const SqTiling t = sq_tiling(K, L, VB ? 1 : 0);
+  const int D = K * L, M = K * K, N = L * L, Np = t.Np, len = D * D + 2 * D;
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  size_t idx[4];
+  int cnt = 0;
+  if (i < D * D) {
     const int d = i / D, d2 = i - d * D;
     const int k = d / L, l = d - k * L, k2 = d2 / L, l2 = d2 - k2 * L;
-    double v = C[(size_t)(k * K + k2) * Np + l * L + l2];
+    idx[cnt++] = (size_t)(k * K + k2) * Np + l * L + l2;
+    if (VB && l == l2 && k != k2) idx[cnt++] = (size_t)(k * K + k2) * Np + N + l;          // cov_term_G
+    if (VB && k == k2 && l != l2) idx[cnt++] = (size_t)(M + k) * Np + l * L + l2;          // cov_term_F
+  } else if (i < D * D + D) {
+    const int d = i - D * D, k = d / L, l = d - k * L;
+    idx[cnt++] = (size_t)(k * K + k) * Np + l * L + l;
     if (VB) {
-      if (l == l2 && k != k2) v += C[(size_t)(k * K + k2) * Np + N + l];
-      if (k == k2 && l != l2) v += C[(size_t)(M + k) * Np + l * L + l2];
+      idx[cnt++] = (size_t)(k * K + k) * Np + N + l;
+      idx[cnt++] = (size_t)(M + k) * Np + l * L + l;
+      idx[cnt++] = (size_t)(M + k) * Np + N + l;
     }
-    out[i] = v;
+  } else if (i < len) {
+    idx[cnt++] = (size_t)t.Mp * Np + (i - D * D - D);
   }
-  if (tid < D) {
-    double p = C[(size_t)(dk * K + dk) * Np + dl * L + dl];
-    if (VB) p += C[(size_t)(dk * K + dk) * Np + N + dl] + C[(size_t)(M + dk) * Np + dl * L + dl] + C[(size_t)(M + dk) * Np + N + dl];
-    out[D * D + tid] = p;
-    out[D * D + D + tid] = rhs;
+  double s = 0.0;
+  for (int p = g; p < nparts; p += 8) {
+    const double* c = partial + (size_t)p * t.plen;
+    for (int q = 0; q < cnt; ++q) s += c[idx[q]];
+  }
+  red[g][e] = s;
+  __syncthreads();
+  if (g == 0 && i < len) {
+    double v = red[0][e];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v += red[w][e];
+    out[i] = v;
   }
 }
 
@@ -475,6 +532,20 @@ int launch_nmtf_transform(const TransformArgs& a, cudaStream_t st) {
 }
 
 int sq_partial_len(int K, int L) { const int D = K * L; return D * D + 2 * D; }
+// doubles of scratch per row partition of bnmtf_nmtf_sq_f64, and the number of row partitions that fills the device
+long long sq_scratch_len(int K, int L, int vb) {
+  const SqTiling t = sq_tiling(K, L, vb);
+  const long long old_len = (long long)K * L * K * L + 2LL * K * L;
+  return (t.ok && (long long)t.plen > old_len) ? (long long)t.plen : old_len;
+}
+int sq_parts(long long rows, int K, int L, int vb) {
+  const SqTiling t = sq_tiling(K, L, vb);
+  const int rb = t.ok ? t.rb : 16, passes = t.ok ? t.npass : 1;
+  long long p = (rows + rb - 1) / rb;
+  const long long cap = 148 / passes > 0 ? 148 / passes : 1;
+  if (p > cap) p = cap;
+  return p < 1 ? 1 : (int)p;
+}
 
 int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st);   // defined below
 // 256 threads = 32 entries x 8 groups of partials: thread (g, e) adds the partials g, g + 8, ... of its entry, then the eight
@@ -501,11 +572,16 @@ int launch_nmtf_sq(const SqArgs& a, int nparts, double* out, cudaStream_t st) {
   const int D = a.K * a.L;
   const SqTiling t = sq_tiling(a.K, a.L, a.vb);
   if (t.ok) {
-    auto kern = a.vb ? k_nmtf_sq_tiled<true> : k_nmtf_sq_tiled<false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    kern<<<nparts, SQ_THREADS, t.smem, st>>>(a);
     const int len = D * D + 2 * D;
-    k_sum_partials2<<<(len + 31) / 32, 256, 0, st>>>(a.partial, nparts, len, out);
+    if (a.vb) {
+      cudaFuncSetAttribute(k_nmtf_sq_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      k_nmtf_sq_tiled<true><<<dim3(nparts, t.npass), SQ_THREADS, t.smem, st>>>(a);
+      k_sq_assemble<true><<<(len + 31) / 32, 256, 0, st>>>(a.partial, nparts, a.K, a.L, out);
+    } else {
+      cudaFuncSetAttribute(k_nmtf_sq_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      k_nmtf_sq_tiled<false><<<dim3(nparts, t.npass), SQ_THREADS, t.smem, st>>>(a);
+      k_sq_assemble<false><<<(len + 31) / 32, 256, 0, st>>>(a.partial, nparts, a.K, a.L, out);
+    }
     return check_launch("nmtf_sq");
   }
   const size_t small = ((size_t)a.L * a.L + 2 * a.L + 2 * a.K) * sizeof(double);

@@ -39,6 +39,12 @@ def test_plain_helpers(lib):
     assert l.bnmtf_ld_for(80) == 128 and l.bnmtf_ld_for(32768) == 32768
     assert l.bnmtf_kp_for(20) == 24 and l.bnmtf_kp_for(7) == 8 and l.bnmtf_kp_for(8) == 16
     assert l.bnmtf_gram_len(20) == 6 * 64
+    # scratch and row partitions of the S-phase reduction (host-side queries, through the same wrapper the engine uses)
+    for K, L, vb in ((10, 10, 1), (10, 10, 0), (20, 20, 1), (3, 4, 0), (32, 32, 1), (63, 63, 1)):
+        D = K * L
+        assert lib.call("bnmtf_nmtf_sq_scratch_len", K, L, vb) >= D * D + 2 * D
+        assert 1 <= lib.call("bnmtf_nmtf_sq_parts", 65536, K, L, vb) <= 148
+        assert lib.call("bnmtf_nmtf_sq_parts", 1, K, L, vb) == 1
 
 
 def test_constructor_validation_matches_reference_messages():

@@ -207,9 +207,11 @@ def test_vb_rectangular_core_matches_oracle(golden, K, L, init_FG):
 
 
 def test_large_core_uses_the_global_memory_accumulator(golden):
-    """K * L = 13 * 14 = 182: the (KL x KL) normal matrix of the S phase no longer fits shared memory (limit ~158), so
-    the reduction accumulates in global memory (csrc/nmtf.cu, k_nmtf_sq_partial<true>) -- the reference has no size
-    limit and its grid searches go to K, L of 20-30.  Two VB sweeps and two ICM sweeps against the oracle."""
+    """K * L = 13 * 14 = 182: the (KL x KL) normal matrix of the S phase no longer fits shared memory (limit ~158): the
+    tiled reduction covers it in several passes over the rows, each CTA writing its blocks to global memory, and the
+    coordinate chain reads H from global memory (csrc/nmtf.cu, k_nmtf_sq_tiled with gridDim.y > 1, k_coord_solve<false>) --
+    the reference has no size limit and its grid searches go to K, L of 20-30.  Two VB sweeps and two ICM sweeps against
+    the oracle."""
     from oracle import bnmtf_oracle as orc
     import bnmtf_b200
     g = golden("toy_bnmtf_vb")
@@ -382,12 +384,13 @@ def test_metrics_from_the_column_statistics(monkeypatch, cls_name, missing):
     close(a.exptau if cls_name == "bnmtf_vb_optimised" else a.tau, b.exptau if cls_name == "bnmtf_vb_optimised" else b.tau, rtol=1e-8)
 
 
-@pytest.mark.parametrize("K,L", [(3, 4), (10, 10), (5, 9), (2, 30), (12, 12)])
+@pytest.mark.parametrize("K,L", [(3, 4), (10, 10), (5, 9), (2, 30), (12, 12), (20, 20), (3, 40), (32, 32)])
 @pytest.mark.parametrize("vb", [0, 1])
 @pytest.mark.parametrize("polarity", [0, 1])
 def test_s_phase_reduction_is_the_einsum(K, L, vb, polarity):
-    """bnmtf_nmtf_sq_f64 (csrc/nmtf.cu: the register-tiled product k_nmtf_sq_tiled, and k_nmtf_sq_partial for shapes it does
-    not take, here K = L = 12) against the defining sums of the S update (bnmtf_vb_optimised.py:245-262,
+    """bnmtf_nmtf_sq_f64 (csrc/nmtf.cu: the register-tiled product k_nmtf_sq_tiled -- one pass over the rows up to K = L = 10,
+    several for the larger shapes -- and k_nmtf_sq_partial for shapes it does not take, here VB at K = L = 32: more than 64
+    passes) against the defining sums of the S update (bnmtf_vb_optimised.py:245-262,
     bnmtf_gibbs_optimised.py:201-205) written with numpy on the same row statistics."""
     import torch
     from bnmtf_b200 import _lib
@@ -421,11 +424,14 @@ def test_s_phase_reduction_is_the_einsum(K, L, vb, polarity):
     fullrec = np.zeros(GL + KP); fullrec[:GL] = pack(full_GG[None])[0]; fullrec[GL:GL + L] = full_sv
     Go, SVo, RXo, Gfull, Fd, vFd = up(pack(held_GG)), up(svp), up(rgp), up(fullrec), up(F), up(vF)
     nparts, ln = 37, D * D + 2 * D
-    part, out = torch.zeros(nparts * ln, dtype=torch.float64, device=dev), torch.zeros(ln, dtype=torch.float64, device=dev)
+    scratch = int(_lib.call("bnmtf_nmtf_sq_scratch_len", K, L, vb))
+    assert scratch >= ln and int(_lib.call("bnmtf_nmtf_sq_parts", rows, K, L, vb)) >= 1
+    part, out = torch.zeros(nparts * scratch, dtype=torch.float64, device=dev), torch.zeros(ln, dtype=torch.float64, device=dev)
     _lib.call("bnmtf_nmtf_sq_f64", rows, K, L, polarity, vb, _ptr(RXo), _ptr(Go), _ptr(SVo) if vb else 0, _ptr(Gfull), _ptr(Fd),
               _ptr(vFd) if vb else 0, _ptr(part), nparts, _ptr(out), _stream())
     got = out.cpu().numpy()
-    H = np.einsum("ik,im,iln->klmn", F, F, GG)
+    A = (F[:, :, None] * F[:, None, :]).reshape(rows, K * K)
+    H = (A.T @ GG.reshape(rows, L * L)).reshape(K, K, L, L).transpose(0, 2, 1, 3).copy()      # [k, l, k', l']
     prec = np.einsum("ik,il->kl", F * F, np.einsum("ill->il", GG))
     if vb:
         covG = np.einsum("ik,im,il->kml", F, F, sv)
