@@ -150,12 +150,16 @@ __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
 // blocks and the precision terms from the same product:
 //   C[(k,k'), N + l] = sum f_k f_k' sv_l   (cov_term_G)      C[M + k, (l,l')] = sum varF_k GG[l,l']   (cov_term_F)
 //   C[M + k, N + l]  = sum varF_k sv_l     (precision only)
-// 512 threads; `rb` rows are staged in shared memory per step, every warp owns SQ_NT blocks of (4x8 threads) x (4x4
+// 512 threads; `rb` rows are staged in shared memory per step (cp.async copies of the raw statistics, issued one step ahead
+// so that they land during the products, then converted in shared memory), every warp owns SQ_NT blocks of (4x8 threads) x (4x4
 // entries) of C in registers.  grid = (row partitions, passes): a CTA covers a PM x PN rectangle of the WTM x WTN warp
 // blocks of C (pass = blockIdx.y; one pass up to K = L = 10), stages only that rectangle's columns of A and B of its
 // share of the rows, and writes the rectangle into its row partition's slice of `partial` (Mp x Np, then the K*L
 // right-hand sides); k_sq_assemble adds the slices and folds C into (H, prec, rhs).
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 constexpr int SQ_NT = 2, SQ_THREADS = 512, SQ_BLOCKS = (SQ_THREADS / 32) * SQ_NT, SQ_RHS = 2, SQ_MAX_PASSES = 64;
 
 struct SqTiling { int Mext, Next, Mp, Np, WTM, WTN, PM, PN, npm, npn, npass, rb; size_t smem, plen; bool ok; };
@@ -178,7 +182,8 @@ __host__ __device__ inline SqTiling sq_tiling(int K, int L, int vb) {
   const size_t tables = (size_t)t.Next * (sizeof(double) + sizeof(int)) + (size_t)t.Mext * sizeof(int) + 16;
   t.rb = 16; t.smem = 0;
   for (; t.rb >= 2; t.rb >>= 1) {
-    t.smem = (size_t)t.rb * (16 * t.PM + 32 * t.PN + 2 * K + L) * sizeof(double) + tables;
+    // products side: As | Bs | Fs | RGs;  landing area of the asynchronous copies: Braw | Fraw | VFraw | RGraw
+    t.smem = (size_t)t.rb * (16 * t.PM + 2 * 32 * t.PN + 3 * K + 2 * L) * sizeof(double) + tables;
     if (t.smem <= 200 * 1024) break;
   }
   t.ok = t.rb >= 2 && t.npass <= SQ_MAX_PASSES && K * L <= SQ_THREADS * SQ_RHS;
@@ -197,13 +202,17 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
   const int pi = pass / t.npn, pj = pass - pi * t.npn;
   const int AW = 16 * t.PM, BW = 32 * t.PN, acol0 = pi * AW, bcol0 = pj * BW;
   const int an = (acol0 + AW < Mext ? acol0 + AW : Mext) - acol0, bn = (bcol0 + BW < Next ? bcol0 + BW : Next) - bcol0;
-  // shared memory: the staged rows As | Bs | Fs | VFs | RGs, then the tables
+  // shared memory: what the products read (As | Bs | Fs | RGs), the landing area of the asynchronous copies of the next
+  // rows (Braw | Fraw | VFraw | RGraw), then the tables
   double* As = sm;
   double* Bs = As + RB * AW;
   double* Fs = Bs + RB * BW;
-  double* VFs = Fs + RB * K;
-  double* RGs = VFs + RB * K;
-  double* gfB = RGs + RB * L;                                   // full-set value of entry n (polarity 0), else 0
+  double* RGs = Fs + RB * K;
+  double* Braw = RGs + RB * L;
+  double* Fraw = Braw + RB * BW;
+  double* VFraw = Fraw + RB * K;
+  double* RGraw = VFraw + RB * K;
+  double* gfB = RGraw + RB * L;                                 // full-set value of entry n (polarity 0), else 0
   int* idxB = reinterpret_cast<int*>(gfB + Next);               // offset of entry n in a row's Gram tiles / variance sums
   int* kkA = idxB + Next;                                       // k | k' << 16 of entry m
   for (int n = tid; n < Next; n += SQ_THREADS) {
@@ -239,58 +248,63 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.0;
   // pass 0 also accumulates the right-hand sides: thread -> entries d = tid, tid + 512:  sum_i F_ik RG_il
+  const bool want_rhs = pass == 0;
   double rhs[SQ_RHS];
   int dk[SQ_RHS], dl[SQ_RHS];
 #pragma unroll
   for (int c = 0; c < SQ_RHS; ++c) {
     const int d = tid + c * SQ_THREADS;
     rhs[c] = 0.0;
-    dk[c] = (pass == 0 && d < D) ? d / L : -1;
+    dk[c] = (want_rhs && d < D) ? d / L : -1;
     dl[c] = dk[c] >= 0 ? d - dk[c] * L : 0;
   }
-  const int nbatch = (a.rows + RB - 1) / RB;
-  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
-    const int row0 = bt * RB;
-    __syncthreads();                                            // the previous step's products are done
-    // (flat, in chunks of four predicated elements per thread: four independent global loads in flight each)
-    for (int base = tid; base < RB * bn; base += 4 * SQ_THREADS) {
-      double raw[4];
-      int dst[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = base + j * SQ_THREADS;
-        const bool live = e < RB * bn;
-        const int r = live ? e / bn : 0, c = e - r * bn, n = bcol0 + c, row = row0 + r;
-        const bool in = live && row < a.rows;
-        const int off = live ? idxB[n] : 0;
-        const double* src = n < N ? a.Go + (size_t)row * gll + off : a.SVo + (size_t)row * KPl + off;
-        raw[j] = in ? __ldg(src) : 0.0;
-        dst[j] = live ? (r * BW + c) | (in ? 0 : 1 << 30) : -1;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (dst[j] < 0) continue;
-        const int o = dst[j] & ~(1 << 30);
-        const int n = bcol0 + o % BW;
-        Bs[o] = (dst[j] >> 30) ? 0.0 : (a.polarity ? raw[j] : gfB[n] - raw[j]);
+  // asynchronous copies (cp.async, 8 bytes each) of the raw statistics of the rows [row0, row0 + RB) into the landing area
+  auto fetch = [&](int row0) {
+    for (int e = tid; e < RB * bn; e += SQ_THREADS) {
+      const int r = e / bn, c = e - r * bn, n = bcol0 + c, row = row0 + r;
+      if (row < a.rows) {
+        const double* src = n < N ? a.Go + (size_t)row * gll + idxB[n] : a.SVo + (size_t)row * KPl + idxB[n];
+        cp_async8(Braw + r * BW + c, src);
       }
     }
     for (int e = tid; e < RB * K; e += SQ_THREADS) {
-      const int r = e / K, row = row0 + r;
-      const bool in = row < a.rows;
-      Fs[e] = in ? a.F[(size_t)row0 * K + e] : 0.0;
-      VFs[e] = (VB && in) ? a.varF[(size_t)row0 * K + e] : 0.0;
+      const int row = row0 + e / K;
+      if (row < a.rows) {
+        cp_async8(Fraw + e, a.F + (size_t)row0 * K + e);
+        if (VB) cp_async8(VFraw + e, a.varF + (size_t)row0 * K + e);
+      }
     }
-    for (int e = tid; e < RB * L; e += SQ_THREADS) {
-      const int r = e / L, l = e - r * L, row = row0 + r;
-      RGs[e] = row < a.rows ? a.RXo[(size_t)row * KPl + l] : 0.0;
+    if (want_rhs)
+      for (int e = tid; e < RB * L; e += SQ_THREADS) {
+        const int r = e / L, l = e - r * L, row = row0 + r;
+        if (row < a.rows) cp_async8(RGraw + e, a.RXo + (size_t)row * KPl + l);
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nbatch = (a.rows + RB - 1) / RB;
+  __syncthreads();                                              // tables ready
+  if ((int)blockIdx.x < nbatch) fetch(blockIdx.x * RB);
+  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+    const int row0 = bt * RB;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                            // copies landed; the previous step's products are done
+    // raw -> what the products read: observed-set values of B, the products F_k F_k' (and varF) of A, F and RG for the rhs
+    for (int e = tid; e < RB * bn; e += SQ_THREADS) {
+      const int r = e / bn, c = e - r * bn;
+      const double raw = Braw[r * BW + c];
+      Bs[r * BW + c] = row0 + r < a.rows ? (a.polarity ? raw : gfB[bcol0 + c] - raw) : 0.0;
     }
-    __syncthreads();
     for (int e = tid; e < RB * an; e += SQ_THREADS) {
       const int r = e / an, ca = e - r * an, m = acol0 + ca, c = kkA[m];
-      As[r * AW + ca] = m < M ? Fs[r * K + (c & 0xffff)] * Fs[r * K + (c >> 16)] : VFs[r * K + c];
+      const double v = m < M ? Fraw[r * K + (c & 0xffff)] * Fraw[r * K + (c >> 16)] : VFraw[r * K + c];
+      As[r * AW + ca] = row0 + r < a.rows ? v : 0.0;
     }
-    __syncthreads();
+    if (want_rhs) {
+      for (int e = tid; e < RB * K; e += SQ_THREADS) Fs[e] = row0 + e / K < a.rows ? Fraw[e] : 0.0;
+      for (int e = tid; e < RB * L; e += SQ_THREADS) RGs[e] = row0 + e / L < a.rows ? RGraw[e] : 0.0;
+    }
+    __syncthreads();                                            // the landing area is free again
+    if (bt + (int)gridDim.x < nbatch) fetch((bt + gridDim.x) * RB);           // in flight during the products
 #pragma unroll 2
     for (int r = 0; r < RB; ++r) {
 #pragma unroll
