@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
 //   C[(k,k'), N + l] = sum f_k f_k' sv_l   (cov_term_G)      C[M + k, (l,l')] = sum varF_k GG[l,l']   (cov_term_F)
 //   C[M + k, N + l]  = sum varF_k sv_l     (precision only)
 // 512 threads; `rb` rows are staged in shared memory per step (cp.async copies of the raw statistics, issued one step ahead
-// so that they land during the products, then converted in shared memory), every warp owns SQ_NT blocks of (4x8 threads) x (4x4
-// entries) of C in registers.  grid = (row partitions, passes): a CTA covers a PM x PN rectangle of the WTM x WTN warp
+// so that they land during the products, then converted in shared memory), every warp owns SQ_NT blocks of 16 x 32
+// entries of C in registers and forms them with fp64 DMMA (m8n8k4, the staged rows being the contraction index: one
+// operand register feeds 8 FMAs, so the products run at the fp64 pipe's rate instead of the shared-memory rate).
+// grid = (row partitions, passes): a CTA covers a PM x PN rectangle of the WTM x WTN warp
 // blocks of C (pass = blockIdx.y; one pass up to K = L = 10), stages only that rectangle's columns of A and B of its
 // share of the rows, and writes the rectangle into its row partition's slice of `partial` (Mp x Np, then the K*L
 // right-hand sides); k_sq_assemble adds the slices and folds C into (H, prec, rhs).
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) k_nmtf_sq_partial(SqArgs a) {
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
-constexpr int SQ_NT = 2, SQ_THREADS = 512, SQ_BLOCKS = (SQ_THREADS / 32) * SQ_NT, SQ_RHS = 2, SQ_MAX_PASSES = 64;
+constexpr int SQ_NT = 2, SQ_THREADS = 512, SQ_BLOCKS = (SQ_THREADS / 32) * SQ_NT, SQ_RHS = 2, SQ_MAX_PASSES = 64, SQ_PAD = 4;
 
 struct SqTiling { int Mext, Next, Mp, Np, WTM, WTN, PM, PN, npm, npn, npass, rb; size_t smem, plen; bool ok; };
 __host__ __device__ inline SqTiling sq_tiling(int K, int L, int vb) {
@@ -181,12 +183,12 @@ __host__ __device__ inline SqTiling sq_tiling(int K, int L, int vb) {
   t.plen = ((size_t)t.Mp * t.Np + (size_t)K * L + 1) & ~(size_t)1;       // (even: 16-byte aligned slices)
   const size_t tables = (size_t)t.Next * (sizeof(double) + sizeof(int)) + (size_t)t.Mext * sizeof(int) + 16;
   t.rb = 16; t.smem = 0;
-  for (; t.rb >= 2; t.rb >>= 1) {
-    // products side: As | Bs | Fs | RGs;  landing area of the asynchronous copies: Braw | Fraw | VFraw | RGraw
-    t.smem = (size_t)t.rb * (16 * t.PM + 2 * 32 * t.PN + 3 * K + 2 * L) * sizeof(double) + tables;
+  for (; t.rb >= 4; t.rb >>= 1) {                               // (a multiple of the DMMA depth 4 that divides 16 warps)
+    // products side: As | Bs (padded rows) | Fs | RGs;  landing area of the asynchronous copies: Braw | Fraw | VFraw | RGraw
+    t.smem = (size_t)t.rb * (16 * t.PM + 2 * 32 * t.PN + 2 * SQ_PAD + 3 * K + 2 * L) * sizeof(double) + tables;
     if (t.smem <= 200 * 1024) break;
   }
-  t.ok = t.rb >= 2 && t.npass <= SQ_MAX_PASSES && K * L <= SQ_THREADS * SQ_RHS;
+  t.ok = t.rb >= 4 && t.npass <= SQ_MAX_PASSES && K * L <= SQ_THREADS * SQ_RHS;
   return t;
 }
 
@@ -202,11 +204,14 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
   const int pi = pass / t.npn, pj = pass - pi * t.npn;
   const int AW = 16 * t.PM, BW = 32 * t.PN, acol0 = pi * AW, bcol0 = pj * BW;
   const int an = (acol0 + AW < Mext ? acol0 + AW : Mext) - acol0, bn = (bcol0 + BW < Next ? bcol0 + BW : Next) - bcol0;
+  // row strides of the operand arrays: + 4 doubles, so that the four rows a DMMA fragment load touches (4 x 32 bytes per
+  // half warp) fall into disjoint banks
+  const int AWp = AW + SQ_PAD, BWp = BW + SQ_PAD;
   // shared memory: what the products read (As | Bs | Fs | RGs), the landing area of the asynchronous copies of the next
   // rows (Braw | Fraw | VFraw | RGraw), then the tables
   double* As = sm;
-  double* Bs = As + RB * AW;
-  double* Fs = Bs + RB * BW;
+  double* Bs = As + RB * AWp;
+  double* Fs = Bs + RB * BWp;
   double* RGs = Fs + RB * K;
   double* Braw = RGs + RB * L;
   double* Fraw = Braw + RB * BW;
@@ -229,24 +234,28 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
     }
   }
   for (int m = tid; m < Mext; m += SQ_THREADS) kkA[m] = m < M ? ((m / K) | ((m % K) << 16)) : (m - M);
-  for (int i = tid; i < RB * (AW + BW); i += SQ_THREADS) As[i] = 0.0;          // (padding entries stay zero)
+  for (int i = tid; i < RB * (AWp + BWp); i += SQ_THREADS) As[i] = 0.0;        // (padding entries stay zero)
+  // staging work is split by rows: 16 / RB warps share a staged row and stride over its columns
+  const int wpr = (SQ_THREADS / 32) / RB, srow = warp % RB, scol = (warp / RB) * 32 + lane, sstep = 32 * wpr;
+  // products: every warp owns SQ_NT blocks of 16 x 32 entries of the rectangle = 2 x 4 DMMA tiles (8 x 8) each
+  const int g = lane >> 2, t4 = lane & 3;
   int aoff[SQ_NT], boff[SQ_NT];
   bool valid[SQ_NT];
 #pragma unroll
   for (int q = 0; q < SQ_NT; ++q) {
     const int b = q * (SQ_THREADS / 32) + warp;                // block of the rectangle; offsets are relative to it
     const int pm = b / t.PN, pn = b - pm * t.PN;
-    aoff[q] = 4 * (pm * 4 + (lane >> 3));
-    boff[q] = 4 * (pn * 8 + (lane & 7));
-    valid[q] = acol0 + aoff[q] < Mp && bcol0 + boff[q] < Np;
+    aoff[q] = 16 * pm;
+    boff[q] = 32 * pn;
+    valid[q] = acol0 + aoff[q] < Mp && bcol0 + boff[q] < Np;   // (warp-uniform)
   }
-  double acc[SQ_NT][4][4];
+  double acc[SQ_NT][2][4][2];
 #pragma unroll
   for (int q = 0; q < SQ_NT; ++q)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.0;
+      for (int j = 0; j < 4; ++j) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
   // pass 0 also accumulates the right-hand sides: thread -> entries d = tid, tid + 512:  sum_i F_ik RG_il
   const bool want_rhs = pass == 0;
   double rhs[SQ_RHS];
@@ -260,25 +269,21 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
   }
   // asynchronous copies (cp.async, 8 bytes each) of the raw statistics of the rows [row0, row0 + RB) into the landing area
   auto fetch = [&](int row0) {
-    for (int e = tid; e < RB * bn; e += SQ_THREADS) {
-      const int r = e / bn, c = e - r * bn, n = bcol0 + c, row = row0 + r;
-      if (row < a.rows) {
-        const double* src = n < N ? a.Go + (size_t)row * gll + idxB[n] : a.SVo + (size_t)row * KPl + idxB[n];
-        cp_async8(Braw + r * BW + c, src);
+    const int row = row0 + srow;
+    if (row < a.rows) {
+      const double* gp = a.Go + (size_t)row * gll;
+      const double* sp = a.SVo + (size_t)row * KPl;
+      for (int c = scol; c < bn; c += sstep) {
+        const int n = bcol0 + c;
+        cp_async8(Braw + srow * BW + c, n < N ? gp + idxB[n] : sp + idxB[n]);
       }
+      for (int k = scol; k < K; k += sstep) {
+        cp_async8(Fraw + srow * K + k, a.F + (size_t)row * K + k);
+        if (VB) cp_async8(VFraw + srow * K + k, a.varF + (size_t)row * K + k);
+      }
+      if (want_rhs)
+        for (int l = scol; l < L; l += sstep) cp_async8(RGraw + srow * L + l, a.RXo + (size_t)row * KPl + l);
     }
-    for (int e = tid; e < RB * K; e += SQ_THREADS) {
-      const int row = row0 + e / K;
-      if (row < a.rows) {
-        cp_async8(Fraw + e, a.F + (size_t)row0 * K + e);
-        if (VB) cp_async8(VFraw + e, a.varF + (size_t)row0 * K + e);
-      }
-    }
-    if (want_rhs)
-      for (int e = tid; e < RB * L; e += SQ_THREADS) {
-        const int r = e / L, l = e - r * L, row = row0 + r;
-        if (row < a.rows) cp_async8(RGraw + e, a.RXo + (size_t)row * KPl + l);
-      }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   const int nbatch = (a.rows + RB - 1) / RB;
@@ -289,52 +294,60 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) k_nmtf_sq_tiled(SqArgs a) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                            // copies landed; the previous step's products are done
     // raw -> what the products read: observed-set values of B, the products F_k F_k' (and varF) of A, F and RG for the rhs
-    for (int e = tid; e < RB * bn; e += SQ_THREADS) {
-      const int r = e / bn, c = e - r * bn;
-      const double raw = Braw[r * BW + c];
-      Bs[r * BW + c] = row0 + r < a.rows ? (a.polarity ? raw : gfB[bcol0 + c] - raw) : 0.0;
-    }
-    for (int e = tid; e < RB * an; e += SQ_THREADS) {
-      const int r = e / an, ca = e - r * an, m = acol0 + ca, c = kkA[m];
-      const double v = m < M ? Fraw[r * K + (c & 0xffff)] * Fraw[r * K + (c >> 16)] : VFraw[r * K + c];
-      As[r * AW + ca] = row0 + r < a.rows ? v : 0.0;
-    }
-    if (want_rhs) {
-      for (int e = tid; e < RB * K; e += SQ_THREADS) Fs[e] = row0 + e / K < a.rows ? Fraw[e] : 0.0;
-      for (int e = tid; e < RB * L; e += SQ_THREADS) RGs[e] = row0 + e / L < a.rows ? RGraw[e] : 0.0;
+    {
+      const bool in = row0 + srow < a.rows;
+      for (int c = scol; c < bn; c += sstep) {
+        const double raw = Braw[srow * BW + c];
+        Bs[srow * BWp + c] = in ? (a.polarity ? raw : gfB[bcol0 + c] - raw) : 0.0;
+      }
+      const double* fr = Fraw + srow * K;
+      for (int ca = scol; ca < an; ca += sstep) {
+        const int m = acol0 + ca, c = kkA[m];
+        const double v = m < M ? fr[c & 0xffff] * fr[c >> 16] : VFraw[srow * K + c];
+        As[srow * AWp + ca] = in ? v : 0.0;
+      }
+      if (want_rhs) {
+        for (int k = scol; k < K; k += sstep) Fs[srow * K + k] = in ? fr[k] : 0.0;
+        for (int l = scol; l < L; l += sstep) RGs[srow * L + l] = in ? RGraw[srow * L + l] : 0.0;
+      }
     }
     __syncthreads();                                            // the landing area is free again
     if (bt + (int)gridDim.x < nbatch) fetch((bt + gridDim.x) * RB);           // in flight during the products
-#pragma unroll 2
-    for (int r = 0; r < RB; ++r) {
+    for (int kk = 0; kk < RB; kk += 4) {
+      const double* ar = As + (kk + t4) * AWp + g;              // A fragment: lane holds A^T[m = g][r = t4]
+      const double* br = Bs + (kk + t4) * BWp + g;              // B fragment: lane holds B[r = t4][n = g]
 #pragma unroll
       for (int q = 0; q < SQ_NT; ++q) {
         if (!valid[q]) continue;
-        const double2 a0 = *reinterpret_cast<const double2*>(As + r * AW + aoff[q]);
-        const double2 a1 = *reinterpret_cast<const double2*>(As + r * AW + aoff[q] + 2);
-        const double2 b0 = *reinterpret_cast<const double2*>(Bs + r * BW + boff[q]);
-        const double2 b1 = *reinterpret_cast<const double2*>(Bs + r * BW + boff[q] + 2);
-        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+        const double a0 = ar[aoff[q]], a1 = ar[aoff[q] + 8];
+        double bf[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) bf[j] = br[boff[q] + 8 * j];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[q][i][j] = fma(av[i], bv[j], acc[q][i][j]);
+        for (int j = 0; j < 4; ++j) {
+          dmma884(acc[q][0][j][0], acc[q][0][j][1], a0, bf[j]);
+          dmma884(acc[q][1][j][0], acc[q][1][j][1], a1, bf[j]);
+        }
       }
-#pragma unroll
-      for (int c = 0; c < SQ_RHS; ++c)
-        if (dk[c] >= 0) rhs[c] = fma(Fs[r * K + dk[c]], RGs[r * L + dl[c]], rhs[c]);
     }
+    if (want_rhs)
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int c = 0; c < SQ_RHS; ++c)
+          if (dk[c] >= 0) rhs[c] = fma(Fs[r * K + dk[c]], RGs[r * L + dl[c]], rhs[c]);
   }
   double* C = a.partial + (size_t)blockIdx.x * t.plen;          // this row partition's Mp x Np (+ D) slice
 #pragma unroll
   for (int q = 0; q < SQ_NT; ++q)
     if (valid[q])
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double2* o = reinterpret_cast<double2*>(C + (size_t)(acol0 + aoff[q] + i) * Np + bcol0 + boff[q]);
-        o[0] = make_double2(acc[q][i][0], acc[q][i][1]);
-        o[1] = make_double2(acc[q][i][2], acc[q][i][3]);
-      }
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = acol0 + aoff[q] + 8 * i + g, n = bcol0 + boff[q] + 8 * j + 2 * t4;   // lane holds C[g][2 t4 + {0,1}]
+          if (m < Mp && n < Np)
+            *reinterpret_cast<double2*>(C + (size_t)m * Np + n) = make_double2(acc[q][i][j][0], acc[q][i][j][1]);
+        }
 #pragma unroll
   for (int c = 0; c < SQ_RHS; ++c)
     if (dk[c] >= 0) C[(size_t)Mp * Np + tid + c * SQ_THREADS] = rhs[c];
