@@ -259,7 +259,7 @@ int bnmtf_nmtf_transform_f64(int64_t rows, int Ks, int Lo, int polarity, int vb,
                              const double* SVo, const double* Gfull_o, const double* Smat, const double* varS,
                              double* RXs, double* Gs, double* SVs, void* stream);
 /* Reduction over rows for the S phase: out = [H (D x D) | prec (D) | rhs (D)], D = K*L, index d = k*L + l
- * (the sums behind tauS/muS, bnmtf_gibbs_optimised.py:201-205, and update_S, bnmtf_vb_optimised.py:245-262).  The rows are
+ * (the sums behind tauS/muS, bnmtf_gibbs_optimised.py:201-205, and update_S, bnmtf_vb_optimised.py:256-266).  The rows are
  * cut into nparts partitions (bnmtf_nmtf_sq_parts: the count that fills the device for this shape; any count >= 1 is valid);
  * partial: nparts x bnmtf_nmtf_sq_scratch_len(K, L, vb) doubles of scratch, 16-byte aligned. */
 int64_t bnmtf_nmtf_sq_scratch_len(int K, int L, int vb);

@@ -390,7 +390,7 @@ def test_metrics_from_the_column_statistics(monkeypatch, cls_name, missing):
 def test_s_phase_reduction_is_the_einsum(K, L, vb, polarity):
     """bnmtf_nmtf_sq_f64 (csrc/nmtf.cu: the register-tiled product k_nmtf_sq_tiled -- one pass over the rows up to K = L = 10,
     several for the larger shapes -- and k_nmtf_sq_partial for shapes it does not take, here VB at K = L = 32: more than 64
-    passes) against the defining sums of the S update (bnmtf_vb_optimised.py:245-262,
+    passes) against the defining sums of the S update (bnmtf_vb_optimised.py:256-266,
     bnmtf_gibbs_optimised.py:201-205) written with numpy on the same row statistics."""
     import torch
     from bnmtf_b200 import _lib
