@@ -509,7 +509,7 @@ __global__ void k_nmtf_extra(ExtraArgs a) {
 // k_nmtf_mstat: the three masked sums the training metrics need, per column j of R, from the column statistics
 // w.r.t. F (c_j = sum_i m r F_i, FF_j = sum_i m F_i F_i^T, s_j = sum_i m F_i: slot (k, K) of the Gram tiles) and the
 // current S and G_j.  With y = S G_j:   sum_i m r p = y.c_j,   sum_i m p^2 = y^T FF_j y,   sum_i m p = y.s_j
-// (p = F S G^T; compute_statistics of the reference, bnmtf_gibbs_optimised.py:251-281, takes them from a pass over R).
+// (p = F S G^T; predict_while_running / compute_MSE / compute_R2 / compute_Rp of the reference, bnmtf_gibbs_optimised.py:234-258, takes them from a pass over R).
 // mstat: rows x 4 (rp, pp, sp, 0) -- the layout k_mstat_partial of solve.cu reduces.
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_nmtf_mstat(int rows, int K, int L, int polarity, const double* __restrict__ RXo,

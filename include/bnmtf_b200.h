@@ -278,10 +278,10 @@ int bnmtf_coord_solve_f64(int mode, int D, const double* H, const double* prec, 
 int bnmtf_nmtf_extra_f64(int64_t rows, int K, int L, int polarity, const double* Go, const double* SVo,
                          const double* Gfull_o, const double* G, const double* varG, const double* S, const double* varS,
                          double* extra, void* stream);
-/* The masked sums behind the training metrics (sum m r p, sum m p^2, sum m p with p = F S G^T; compute_statistics,
- * bnmtf_gibbs_optimised.py:251-281) per column of R from the column statistics w.r.t. F (RXo, Go with the column sums
- * in slot (k, K): bnmtf_stats_gram_umma_f64 with sums = 1, or bnmtf_stats_gram_f64) and the current S (K x L), G
- * (rows x L).  mstat: rows x 4, reduced by bnmtf_mstat_reduce_f64. */
+/* The masked sums behind the training metrics (sum m r p, sum m p^2, sum m p with p = F S G^T; predict_while_running /
+ * compute_MSE / compute_R2 / compute_Rp, bnmtf_gibbs_optimised.py:234-258) per column of R from the column statistics
+ * w.r.t. F (RXo, Go with the column sums in slot (k, K): bnmtf_stats_gram_umma_f64 with sums = 1, or
+ * bnmtf_stats_gram_f64) and the current S (K x L), G (rows x L).  mstat: rows x 4, reduced by bnmtf_mstat_reduce_f64. */
 int bnmtf_nmtf_mstat_f64(int64_t rows, int K, int L, int polarity, const double* RXo, const double* Go,
                          const double* Gfull_o, const double* G, const double* S, double* mstat, void* stream);
 

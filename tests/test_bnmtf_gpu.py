@@ -352,7 +352,7 @@ def test_large_matrices_run_the_tcgen05_statistics(monkeypatch, cls_name, its):
 @pytest.mark.parametrize("cls_name", ["bnmtf_vb_optimised", "bnmtf_gibbs_optimised"])
 def test_metrics_from_the_column_statistics(monkeypatch, cls_name, missing):
     """With the tcgen05 statistics the training metrics of a sweep come from the column statistics of the G phase
-    (csrc/nmtf.cu::k_nmtf_mstat) instead of a pass over R (compute_statistics, bnmtf_gibbs_optimised.py:251-281): same
+    (csrc/nmtf.cu::k_nmtf_mstat) instead of a pass over R (predict_while_running / compute_MSE / compute_R2 / compute_Rp, bnmtf_gibbs_optimised.py:234-258): same
     traces as the direct pass, for both mask polarities, and the direct pass takes over when the guard trips."""
     import bnmtf_b200
     rng = np.random.RandomState(8)

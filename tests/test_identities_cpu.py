@@ -5,7 +5,7 @@ import numpy as np
 
 def test_tri_factor_metric_sums_follow_from_the_column_statistics():
     """k_nmtf_mstat: with the column statistics w.r.t. F (c_j = sum_i m r F_i, FF_j = sum_i m F_i F_i^T, s_j = sum_i m F_i)
-    and y_j = S G_j, the three masked sums behind MSE / R^2 / Rp (compute_statistics, bnmtf_gibbs_optimised.py:251-281:
+    and y_j = S G_j, the three masked sums behind MSE / R^2 / Rp (predict_while_running / compute_MSE / compute_R2 / compute_Rp, bnmtf_gibbs_optimised.py:234-258:
     they are taken from the prediction F S G^T there) are y.c, y^T FF y and y.s summed over the columns."""
     rng = np.random.RandomState(0)
     I, J, K, L = 37, 29, 4, 6
